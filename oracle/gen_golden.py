@@ -1,0 +1,191 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference cell on the numpy TF1 shim.
+
+    python oracle/gen_golden.py            # needs /root/reference (build container only)
+
+For every case below this imports `/root/reference/{config,ops,mac_cell}.py` (never copied into the
+repo), sets the reference's global `config` through its own `parseArgs()` (`config.py:95-424`),
+restates the ten-line caller `MACnet.MACnetwork` (`model.py:428-458`: construct, zero_state, static
+netLength unroll), and records per-step control / memory / info / contControl and the attention maps.
+Variable *values* come from `mac_network_b200.params.init_params` (so the product, the oracle and the
+reference all see identical weights); variable *names and shapes* are whatever the reference creates
+and are stored in the fixture so the product's enumeration can be checked against them.
+
+The fixtures pin `oracle/mac_oracle.py`; they cannot travel any other way, because neither
+`/root/reference` nor TensorFlow exists on the GPU box.
+"""
+import importlib
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REF = "/root/reference"
+sys.path.insert(0, os.path.join(HERE, "tf1_shim"))
+sys.path.insert(0, REF)
+sys.path.insert(0, ROOT)
+
+import tensorflow as tf                      # noqa: E402  (the shim)
+from mac_network_b200.config import MACConfig  # noqa: E402
+from mac_network_b200.params import init_params, perturb_biases  # noqa: E402
+from mac_network_b200.synthetic import make_inputs  # noqa: E402
+
+COMMON = ["--memoryVariationalDropout", "--relu=ELU", "--controlContextual", "--readProjInputs",
+          "--readMemConcatKB", "--readMemConcatProj", "--readMemProj", "--readCtrl", "--writeMemProj"]
+ARGS = COMMON + ["--initCtrl=Q", "--controlInputUnshared"]
+SMALL = dict(B=3, S=5, N=7, d=16, L=3)
+
+# name -> (flag source, extra flags, shape, train?)
+CASES = {
+    # the five shipped flag files, read from the reference's own configs/ directory
+    "args_small": ("@args.txt", [], SMALL, False),
+    "args1_small": ("@args1.txt", [], SMALL, False),
+    "args2_small": ("@args2.txt", [], SMALL, False),
+    "args3_small": ("@args3.txt", [], SMALL, False),
+    "args4_small": ("@args4.txt", [], SMALL, False),
+    "gqa_small": ("@args3.txt", ["--writeGate"], dict(B=3, S=4, N=9, d=16, L=4), False),
+    # training mode (dropouts at config.py:210-212 defaults, plus a write dropout)
+    "args_train_small": ("@args.txt", [], SMALL, True),
+    "args1_train_small": ("@args1.txt", [], SMALL, True),
+    "gqa_train_small": ("@args3.txt", ["--writeGate", "--writeDropout=0.9"], dict(B=3, S=4, N=9, d=16, L=4), True),
+    "novardp_train_small": (None, [f for f in ARGS if f != "--memoryVariationalDropout"], SMALL, True),
+    # other working flags (SURVEY.md section 8(a) "P2")
+    "p2_control": (None, ARGS + ["--controlConcatWords", "--controlProj", "--controlProjAct=TANH",
+                                 "--controlInWordsProj"], SMALL, False),
+    "p2_control_feed": (None, COMMON + ["--initCtrl=ZERO", "--controlFeedPrev", "--controlContAct=RELU",
+                                        "--controlOutWordsProj", "--controlInputAct=RELU"], SMALL, False),
+    "p2_ablations": (None, ARGS + ["--controlContinuous"], SMALL, False),
+    "p2_wholeq": (None, ARGS + ["--controlWholeQ", "--initMem=Q"], SMALL, False),
+    "p2_unshared": (None, ARGS + ["--unsharedCells", "1", "--initMem=ZERO"], SMALL, False),
+    "p2_read_bl": (None, ARGS + ["--readMemAttType=BL", "--readCtrlAttType=BL", "--readProjShared",
+                                 "--readMemAct=TANH", "--readCtrlAct=NON"], SMALL, False),
+    "p2_read_add": (None, ARGS + ["--readMemAttType=ADD", "--readCtrlAttType=ADD", "--mulBias=0.5",
+                                  "--readCtrlConcatKB", "--readCtrlConcatProj", "--readSmryKBProj"], SMALL, False),
+    "p2_read_plain": (None, ["--relu=STD", "--controlContextual", "--readCtrl", "--readCtrlConcatKB",
+                             "--mulBias=0.25", "--initCtrl=Q"], SMALL, False),
+    "p2_read_noproj": (None, ["--relu=ELU", "--readProjInputs", "--readMemAct=NON"], SMALL, False),
+    "p2_write_info": (None, ARGS + ["--writeInputs=INFO", "--writeInfoProj", "--writeInfoAct=RELU",
+                                    "--writeMergeCtrl", "--writeMemAct=TANH"], SMALL, False),
+    "p2_write_sum": (None, ARGS + ["--writeInputs=SUM", "--writeSelfAtt", "--writeGate",
+                                   "--writeGateBias=-0.5"], SMALL, False),
+    "p2_write_mem": (None, [f for f in ARGS if f != "--writeMemProj"] + ["--writeInputs=MEM"], SMALL, False),
+    "p2_write_mul": (None, ARGS + ["--writeConcatMul", "--writeSelfAtt"], SMALL, False),
+    # BASELINE.json configs[0]/[1]: B=32, S=20, 14x14 KB, d=512, netLength=4 (float32 storage)
+    "args_cpu_ref": ("@args.txt", [], dict(B=32, S=20, N=196, d=512, L=4), False),
+    "gqa_mid": ("@args3.txt", ["--writeGate"], dict(B=8, S=30, N=49, d=512, L=6), False),
+}
+
+_ref_config = importlib.import_module("config")
+_ref_ops = importlib.import_module("ops")
+_ref_cell = importlib.import_module("mac_cell")
+
+
+def set_reference_config(src, extra, shape, train):
+    argv = ["gen_golden"]
+    if src is not None:
+        argv.append("@" + os.path.join(REF, "configs", src[1:]))
+    argv += list(extra)
+    argv += ["--netLength", str(shape["L"]), "--memDim", str(shape["d"]), "--ctrlDim", str(shape["d"]),
+             "--attDim", str(shape["d"])]
+    # a fresh namespace each time: parseArgs() fills the module-global `config` in place
+    for k in list(vars(_ref_config.config).keys()):
+        delattr(_ref_config.config, k)
+    old = sys.argv
+    sys.argv = argv
+    try:
+        _ref_config.parseArgs()
+    finally:
+        sys.argv = old
+    return argv[1:]
+
+
+def cell_flags_from_reference():
+    """The cell-relevant flags, read back from the reference's parsed global config."""
+    import dataclasses
+    kw = {}
+    for f in dataclasses.fields(MACConfig):
+        kw[f.name] = getattr(_ref_config.config, f.name)
+    return kw
+
+
+def run_case(name, src, extra, shape, train, seed=7):
+    argv = set_reference_config(src, extra, shape, train)
+    rc = _ref_config.config
+    kw = cell_flags_from_reference()
+    cfg = MACConfig(**kw).validate()
+    B, S, N, d, L = (shape[k] for k in "BSNdL")
+    inputs = make_inputs(B, S, N, d, seed=seed, dtype=np.float64)
+    params = perturb_biases(init_params(cfg, L, seed=seed + 1, dtype=np.float64), seed=seed + 2)
+    dp = {"memory": rc.memoryDropout, "read": rc.readDropout, "write": rc.writeDropout} if train else \
+         {"memory": 1.0, "read": 1.0, "write": 1.0}          # model.py:118-125: 1.0 at eval
+    store = tf.reset_shim(values=params, seed=seed + 3, dtype=np.float64)
+    feed = {k: (tf.constant(v) if v.dtype != np.int32 else v) for k, v in inputs.items()}   # feed_dict analogue
+
+    # ---- model.py:428-458 restated: MACnetwork scope, construct, zero_state, unroll
+    conts = []
+    with tf.variable_scope("MACnetwork"):
+        cell = _ref_cell.MACCell(
+            vecQuestions=feed["vecQuestions"], questionWords=feed["questionWords"],
+            questionCntxWords=feed["questionCntxWords"], questionLengths=feed["questionLengths"],
+            knowledgeBase=feed["knowledgeBase"], memoryDropout=dp["memory"], readDropout=dp["read"],
+            writeDropout=dp["write"], batchSize=B, train=train, reuse=None)
+        state = cell.zero_state(B, tf.float32)
+        none = tf.zeros((B, 1), dtype=tf.float32)
+        for i in range(rc.netLength):
+            cell.iteration = i
+            _, state = cell(none, state)
+            conts.append(cell.contControl)
+
+    created = {k: list(v.shape) for k, v in store.vars.items()}
+    missing = sorted(set(created) - set(params))
+    unused = sorted(set(params) - set(created))
+    assert not missing and not unused, (name, "reference created but not enumerated:", missing,
+                                        "enumerated but never created:", unused)
+    big = d >= 256
+    st = np.float32 if big else np.float64
+    out = {
+        "control": cell.controls[:, 1:].transpose(1, 0, 2).astype(st),
+        "memory": cell.memories[:, 1:].transpose(1, 0, 2).astype(st),
+        "info": cell.infos[:, 1:].transpose(1, 0, 2).astype(st),
+        "contControl": np.stack(conts).astype(st),
+        "final_control": np.asarray(state.control, st),
+        "final_memory": np.asarray(state.memory, st),
+        "att_question": np.stack(cell.attentions["question"]).astype(st),
+        "att_kb": np.stack(cell.attentions["kb"]).astype(st),
+    }
+    if cell.attentions["gate"]:
+        out["att_gate"] = np.stack(cell.attentions["gate"]).astype(st)
+    for i, a in enumerate(cell.attentions["self"]):
+        out["att_self_%d" % i] = np.asarray(a, st)
+    for i, u in enumerate(store.uniform_draws):
+        out["uniform_%03d" % i] = u.astype(np.float64)
+    # the cell must not modify its inputs (SURVEY 8(b) ownership)
+    chk = make_inputs(B, S, N, d, seed=seed, dtype=np.float64)
+    for k in chk:
+        assert np.array_equal(chk[k], inputs[k]), k
+    meta = {"case": name, "argv": [a.replace(REF + "/", "") for a in argv], "cell_flags": kw, "shape": shape,
+            "train": train, "dropouts": dp, "input_seed": seed, "param_seed": seed + 1, "bias_seed": seed + 2,
+            "variables": created, "n_uniform": len(store.uniform_draws), "reference_commit": "118d9b6a"}
+    out["meta_json"] = np.frombuffer(json.dumps(meta, sort_keys=True).encode(), dtype=np.uint8)
+    return out
+
+
+def main():
+    outdir = os.path.join(ROOT, "tests", "golden")
+    os.makedirs(outdir, exist_ok=True)
+    only = sys.argv[1:]
+    for name, (src, extra, shape, train) in CASES.items():
+        if only and name not in only:
+            continue
+        out = run_case(name, src, extra, shape, train)
+        path = os.path.join(outdir, name + ".npz")
+        np.savez_compressed(path, **out)
+        print("%-22s %8.1f KB  vars=%d draws=%d" % (name, os.path.getsize(path) / 1024.0,
+                                                     len(json.loads(bytes(out["meta_json"]).decode())["variables"]),
+                                                     sum(k.startswith("uniform_") for k in out)))
+
+
+if __name__ == "__main__":
+    main()

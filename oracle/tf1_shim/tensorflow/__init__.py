@@ -1,0 +1,317 @@
+"""Eager numpy stand-in for the slice of the TensorFlow-1.x API that the
+reference's hot path (`mac_cell.py`, `ops.py`, `mi_*_cell.py` import lines) touches.
+
+TEST INFRASTRUCTURE ONLY.  TensorFlow is not installable in this image (no network,
+no cp312 TF1 wheels), so `oracle/gen_golden.py` puts this directory on `sys.path`
+*as* `tensorflow`, imports the UNMODIFIED reference modules from `/root/reference`
+and runs them eagerly.  That pins the oracle (`oracle/mac_oracle.py`) against the
+reference's own Python control flow: scope/variable naming, op order, concat order,
+the nested "_2" layers, which tensors get dropout, what is appended to `attentions`.
+What it cannot pin are TF's kernels themselves (matmul/softmax/elu/...): those are
+restated here from their published definitions.
+
+Everything is an `np.ndarray` in `WORK_DTYPE` (float64 for golden generation).
+Nothing under `mac_network_b200/` may import this module.
+"""
+import contextlib
+import numpy as np
+
+WORK_DTYPE = np.float64
+
+# dtype tokens the reference passes around (tf.zeros(..., dtype=tf.float32), tf.cast(x, tf.float32))
+float32 = "float32"
+float64 = "float64"
+int32 = np.int32
+int64 = np.int64
+
+
+class Tensor(np.ndarray):
+    """TF tensors are immutable: `x += y` in the reference rebinds, it never writes through an alias
+    (e.g. `newMemory += info` at mac_cell.py:337 must not modify `memory`).  Augmented assignment on
+    this ndarray subclass is therefore out-of-place; ufunc results keep the subclass."""
+    def __iadd__(self, o):
+        return np.add(self, o)
+
+    def __isub__(self, o):
+        return np.subtract(self, o)
+
+    def __imul__(self, o):
+        return np.multiply(self, o)
+
+    def __itruediv__(self, o):
+        return np.true_divide(self, o)
+
+
+def _t(x, dtype=None):
+    a = np.asarray(x, dtype=dtype)
+    return a.view(Tensor)
+
+
+def _np_dtype(dtype):
+    if dtype in (float32, float64, None):
+        return WORK_DTYPE
+    return dtype
+
+
+# --------------------------------------------------------------------------- variables
+class _Store(object):
+    def __init__(self):
+        self.reset()
+
+    def reset(self, values=None, seed=0):
+        self.scope = []
+        self.vars = {}            # full name -> ndarray (creation order preserved)
+        self.provided = dict(values or {})
+        self.rng = np.random.RandomState(seed)
+        self.dropout_masks = []   # (site shape, keep) -> recorded masks, in call order
+        self.uniform_draws = []
+        self.mask_source = None   # optional iterator of pre-made masks
+
+
+_store = _Store()
+
+
+def reset_shim(values=None, seed=0, dtype=np.float64):
+    global WORK_DTYPE
+    WORK_DTYPE = dtype
+    _store.reset(values, seed)
+    return _store
+
+
+def shim_store():
+    return _store
+
+
+@contextlib.contextmanager
+def variable_scope(name_or_scope, default_name=None, reuse=None, **kw):
+    name = name_or_scope if name_or_scope is not None else default_name
+    _store.scope.append(name)
+    try:
+        yield name
+    finally:
+        _store.scope.pop()
+
+
+def get_variable(name, shape=None, initializer=None, dtype=None, **kw):
+    full = "/".join(_store.scope + [name])
+    if full in _store.vars:
+        return _store.vars[full]
+    shape = tuple(int(s) for s in (shape if shape is not None else ()))
+    if full in _store.provided:
+        val = _t(_store.provided[full], dtype=WORK_DTYPE)
+        assert val.shape == shape, (full, val.shape, shape)
+    else:
+        val = _t(initializer(shape, _store.rng), dtype=WORK_DTYPE)
+    _store.vars[full] = val
+    return val
+
+
+def random_normal_initializer(mean=0.0, stddev=1.0):
+    return lambda shape, rng: mean + stddev * rng.standard_normal(shape)
+
+
+def zeros_initializer():
+    return lambda shape, rng: np.zeros(shape)
+
+
+def ones_initializer():
+    return lambda shape, rng: np.ones(shape)
+
+
+def constant_initializer(v):
+    return lambda shape, rng: np.full(shape, v, dtype=np.float64)
+
+
+def _xavier_uniform():
+    # tf.contrib.layers.xavier_initializer(uniform=True): limit = sqrt(6/(fan_in+fan_out));
+    # for a 1-D shape [n] TF's _compute_fans gives fan_in = fan_out = n.
+    def init(shape, rng):
+        if len(shape) == 0:
+            fan_in = fan_out = 1
+        elif len(shape) == 1:
+            fan_in = fan_out = shape[0]
+        else:
+            recept = int(np.prod(shape[:-2])) if len(shape) > 2 else 1
+            fan_in, fan_out = shape[-2] * recept, shape[-1] * recept
+        lim = np.sqrt(6.0 / (fan_in + fan_out))
+        return rng.uniform(-lim, lim, size=shape)
+    return init
+
+
+def trainable_variables():
+    return list(_store.vars.values())
+
+
+# --------------------------------------------------------------------------- basic ops
+def shape(x):
+    return np.array(np.shape(x), dtype=np.int64)
+
+
+def fill(dims, value):
+    return np.full(tuple(int(d) for d in dims), value)
+
+
+def concat(values, axis=0):
+    return _t(np.concatenate([np.asarray(v) for v in values], axis=axis))
+
+
+def reshape(x, newshape):
+    return np.reshape(x, tuple(int(s) for s in np.asarray(newshape).reshape(-1)))
+
+
+def matmul(a, b):
+    return np.matmul(a, b)
+
+
+def expand_dims(x, axis):
+    return np.expand_dims(x, axis)
+
+
+def zeros(shape_, dtype=None):
+    return _t(np.zeros(tuple(int(s) for s in shape_), dtype=_np_dtype(dtype)))
+
+
+def zeros_like(x):
+    return np.zeros_like(x)
+
+
+def tile(x, multiples):
+    return _t(np.tile(x, tuple(int(m) for m in multiples)))
+
+
+def constant(v, dtype=None):
+    return _t(v, dtype=_np_dtype(dtype))
+
+
+def identity(x):
+    return x
+
+
+def stack(values, axis=0):
+    return np.stack(values, axis=axis)
+
+
+def reduce_sum(x, axis=None, keepdims=False):
+    return np.sum(x, axis=axis, keepdims=keepdims)
+
+
+def reduce_mean(x, axis=None, keepdims=False):
+    return np.mean(x, axis=axis, keepdims=keepdims)
+
+
+def tanh(x):
+    return np.tanh(x)
+
+
+def sigmoid(x):
+    return 1.0 / (1.0 + np.exp(-x))
+
+
+def maximum(a, b):
+    return np.maximum(a, b)
+
+
+def floor(x):
+    return np.floor(x)
+
+
+def div(a, b):
+    return a / b
+
+
+def to_float(x):
+    return _t(x, dtype=WORK_DTYPE)          # `t = to_float(p); t += u` (ops.py:1055-1056) rebinds
+
+
+def cast(x, dtype):
+    return np.asarray(x).astype(_np_dtype(dtype))
+
+
+def sequence_mask(lengths, maxlen=None):
+    lengths = np.asarray(lengths)
+    maxlen = int(maxlen if maxlen is not None else lengths.max())
+    return np.arange(maxlen)[None, :] < lengths[:, None]
+
+
+def squared_difference(a, b):
+    return (a - b) ** 2
+
+
+def random_uniform(shape_, minval=0, maxval=1, dtype=None):
+    shp = tuple(int(s) for s in shape_)
+    if _store.mask_source is not None:
+        u = np.asarray(next(_store.mask_source), dtype=WORK_DTYPE)
+        assert u.shape == shp
+    else:
+        u = _store.rng.uniform(minval, maxval, size=shp)
+    _store.uniform_draws.append(u)
+    return _t(u, dtype=WORK_DTYPE)
+
+
+# --------------------------------------------------------------------------- tf.nn
+class _RNNCell(object):
+    pass
+
+
+class _rnn_cell(object):
+    RNNCell = _RNNCell
+    LSTMStateTuple = tuple
+
+
+class _nn(object):
+    rnn_cell = _rnn_cell
+
+    @staticmethod
+    def softmax(x, axis=-1):
+        # TF: exp(x - max) / sum(exp(x - max)) along the last axis
+        m = np.max(x, axis=axis, keepdims=True)
+        e = np.exp(x - m)
+        return e / np.sum(e, axis=axis, keepdims=True)
+
+    @staticmethod
+    def elu(x):
+        return np.where(x > 0, x, np.expm1(np.minimum(x, 0)))
+
+    @staticmethod
+    def relu(x):
+        return np.maximum(x, 0)
+
+    @staticmethod
+    def sigmoid(x):
+        return sigmoid(x)
+
+    @staticmethod
+    def dropout(x, keep_prob, **kw):
+        # TF1: x / keep_prob * floor(keep_prob + U[0,1)).  keep_prob == 1.0 is an exact identity
+        # (TF short-circuits a python-number keep_prob of 1 and the formula gives x anyway).
+        keep = float(keep_prob)
+        if keep == 1.0:
+            return x
+        u = random_uniform(np.shape(x))
+        mask = np.floor(keep + u)
+        _store.dropout_masks.append(mask)
+        return x / keep * mask
+
+
+nn = _nn
+
+
+# --------------------------------------------------------------------------- tf.contrib
+class _layers(object):
+    xavier_initializer = staticmethod(_xavier_uniform)
+
+    @staticmethod
+    def batch_norm(*a, **k):
+        raise NotImplementedError("batch_norm is outside the hot-path scope (memoryBN defaults off)")
+
+
+class _rnn(object):
+    DropoutWrapper = object
+
+
+class _contrib(object):
+    layers = _layers
+    rnn = _rnn
+
+
+contrib = _contrib
