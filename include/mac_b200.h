@@ -1,0 +1,165 @@
+/*
+ * mac_b200.h -- C ABI of the B200-native MAC reasoning cell (libmac_b200.so).
+ *
+ * Drop-in boundary for the hot path of stanfordnlp/mac-network: the three units of
+ * `MACCell` (reference `mac_cell.py`) plus the slice of `ops.py` they call.  The reference
+ * has no FFI of its own (it is a TensorFlow-1 graph; the only runtime boundary is
+ * `sess.run`, `model.py:746`), so the entry points below are what a binding for this path
+ * would bind: one call per reference function, same argument meaning, same order of
+ * arithmetic.  INTEGRATION.md shows the Python (ctypes) stub that puts them behind the
+ * reference's `MACCell.control/read/write/__call__`.
+ *
+ * Conventions:
+ *   - all pointers are DEVICE pointers owned by the caller, row-major, feature dim fastest,
+ *     16-byte aligned; float32 unless stated; `lengths` is int32.
+ *   - sizes: B batch, S question length, N knowledge-base cells (H*W), d = memDim = ctrlDim =
+ *     attDim.  d % 64 == 0 is required by the tensor-core path, d % 4 == 0 by the fp32 path.
+ *   - no allocation inside: scratch comes from `workspace` (size from the matching
+ *     `*_workspace_bytes`).  Every call is asynchronous on `stream` (a cudaStream_t).
+ *   - return value: 0 ok; <0 one of MAC_ERR_*; >0 a cudaError_t.  No exceptions, no global
+ *     state except a lazily created per-device attribute cache; re-entrant across streams
+ *     as long as workspaces are not shared.
+ *   - the inputs (knowledge base, words, question vector) are never written.
+ */
+#ifndef MAC_B200_H_
+#define MAC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MAC_B200_ABI_VERSION 1
+
+typedef void* mac_stream_t; /* cudaStream_t */
+
+enum {
+  MAC_OK = 0,
+  MAC_ERR_INVALID = -1,     /* bad size / null pointer */
+  MAC_ERR_ALIGN = -2,       /* pointer or leading dimension not 16-byte aligned */
+  MAC_ERR_UNSUPPORTED = -3, /* flag combination outside the fused path */
+  MAC_ERR_WORKSPACE = -4,   /* workspace too small */
+  MAC_ERR_ARCH = -5         /* not an sm_100 device / tensor-map driver entry point missing */
+};
+
+/* ops.activations (ops.py:181-187) with the config.relu switch (ops.py:161-179) resolved by the caller */
+enum { MAC_ACT_NON = 0, MAC_ACT_TANH = 1, MAC_ACT_SIGMOID = 2, MAC_ACT_ELU = 3, MAC_ACT_RELU = 4 };
+
+/* arithmetic of the d x d projections */
+enum {
+  MAC_PREC_FP32 = 0, /* fp32 FMA pipe, fp32 accumulate: the <=1e-4 parity configuration */
+  MAC_PREC_BF16 = 1  /* bf16 operands on tcgen05 tensor cores, fp32 accumulate in TMEM: the headline configuration */
+};
+
+int mac_b200_abi_version(void);
+const char* mac_b200_strerror(int status);
+/* 1 if the current device is compute capability 10.x (tcgen05/TMEM/TMA available) */
+int mac_b200_device_ok(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * ops.linear (ops.py:298-333) / ops.multiply (ops.py:50-59)
+ *   y[M,n_out] = act( concat_k(x_0 .. x_{nseg-1})[M, sum k_i] @ W[sum k_i, n_out] + b[n_out] + bias_const )
+ * The concat of the reference (ops.py:65-78, mac_cell.py:339-347) is never materialised: the
+ * segments are separate pointers with their own leading dimension `ldx[i]` (elements).
+ * `b` may be NULL.  The reference's nested "<name>_2" layer (ops.py:325-328) is a second call.
+ * --------------------------------------------------------------------------------------------- */
+int mac_linear_fwd(const float* const* x_segs, const int* k_segs, const int* ldx, int nseg,
+                   const float* W, const float* b, float bias_const, int act,
+                   float* y, int ldy, int M, int n_out,
+                   void* workspace, size_t workspace_bytes, mac_stream_t stream);
+size_t mac_linear_workspace_bytes(int M, int K, int n_out);
+
+/* ------------------------------------------------------------------------------------------------
+ * Control unit, attention part (mac_cell.py:155-181 with controlConcatWords/controlProj off):
+ *   logits[t,b,s] = sum_k cc[t,b,k] * in_words[b,s,k] * w_logit[k] + b_logit          (155, 169)
+ *   att[t,b,:]    = softmax_s( logits - 1e30 * [s >= lengths[b]] )                     (175, ops.py:243-247)
+ *   out[t,b,:]    = sum_s att[t,b,s] * out_words[b,s,:]                                (181, ops.py:149-150)
+ * `nsteps` independent query vectors share one pass over the words (with controlFeedPrev off the
+ * whole control chain is memory-independent, so all netLength steps go in one launch).
+ * The same kernel is the write unit's self-attention (mac_cell.py:324-330): in_words = history of
+ * controls, out_words = history of memories, S = i+1, lengths = NULL, cc = projected control.
+ * Strides are in elements: cc[t,b,:] at cc + t*cc_tstride + b*cc_bstride; word row (b,s) at
+ * words + b*bstride + s*rstride (rstride == d: one bulk copy per batch row; step-major history buffers
+ * use rstride = B*d, bstride = d).  att is [nsteps,B,S] and out [nsteps,B,d], both contiguous.
+ * --------------------------------------------------------------------------------------------- */
+int mac_control_attend_fwd(const float* cc, long long cc_tstride, long long cc_bstride,
+                           const float* in_words, long long in_bstride, long long in_rstride,
+                           const float* out_words, long long out_bstride, long long out_rstride,
+                           const int32_t* lengths, const float* w_logit, float b_logit,
+                           float* att, float* out, int nsteps, int B, int S, int d, mac_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Read unit (mac_cell.py:209-277) on the shipped-config path
+ *   (readProjInputs, readMemConcatKB, readMemConcatProj, readMemProj, readCtrl, MUL/MUL, ELU/ELU):
+ *   md = dropout(memory_in, keep_read)                      (ops.py:678-679; memory_in already carries the
+ *                                                            variational mask, mac_cell.py:214-217)
+ *   P  = dropout(KB, keep_read) @ Wx + bx                   (ops.py:688)      [B*N, d]
+ *   y  = md @ Wy + by                                       (ops.py:689)      [B, d]
+ *   H  = ELU([P * y, P] @ Wm + bm)                          (ops.py:700-719, mac_cell.py:236-238)
+ *   I1 = H @ Wm2 + bm2                                      (ops.py:325-328)
+ *   I2 = ELU(I1 * control)                                  (mac_cell.py:248-250, 262)
+ *   kl = dropout(I2, keep_read) . wr + br                   (mac_cell.py:266, ops.py:312-317)
+ *   att = softmax_n(kl);  info = sum_n att * KB             (ops.py:143, 149-150; original KB, mac_cell.py:271-275)
+ * Training: keep_read < 1 draws Philox4x32-10 masks from (seed, step) (see mac_dropout_uniform);
+ * `save` (may be NULL) receives P, H, I1 ([B*N,d] each, in that order) and y ([B,d]) for backward.
+ * --------------------------------------------------------------------------------------------- */
+typedef struct mac_read_weights {
+  const float* Wx;  const float* bx;   /* read/mulmemInter/linearLayerprojX            [d,d],[d]  */
+  const float* Wy;  const float* by;   /* read/mulmemInter/linearLayerprojY            [d,d],[d]  */
+  const float* Wm;  const float* bm;   /* read/linearLayermemKbProj                    [2d,d],[d] */
+  const float* Wm2; const float* bm2;  /* read/linearLayermemKbProj/linearLayermemKbProj_2 [d,d],[d] */
+  const float* wr;  float br;          /* read/inter2att/inter2logits/linearLayerlogits [d], []   */
+  /* bf16 copies of Wx, Wm, Wm2 in the tcgen05 operand layout (mac_pack_weight_bf16); NULL for MAC_PREC_FP32 */
+  const void* Wx_bf16; const void* Wm_bf16; const void* Wm2_bf16;
+} mac_read_weights;
+
+int mac_read_fwd(const float* kb, const void* kb_bf16, const float* memory_in, const float* control,
+                 const mac_read_weights* w, float keep_read, uint64_t seed, int step, int prec,
+                 float* info, float* att, float* save,
+                 void* workspace, size_t workspace_bytes, int B, int N, int d, mac_stream_t stream);
+size_t mac_read_workspace_bytes(int B, int N, int d, int prec);
+
+/* The HBM-bound tail of the read unit on its own (ops.py:143, 149-150):
+ *   att[b,:] = softmax_n( sum_p logit_parts[(b*N+n)*nparts + p] + br );  info[b,:] = sum_n att[b,n] * KB[b,n,:]
+ * kb_is_bf16 != 0: `kb` points at bf16 data. */
+int mac_kb_attend_fwd(const float* logit_parts, int nparts, float br, const void* kb, int kb_is_bf16,
+                      float* att, float* info, int B, int N, int d, mac_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Write unit (mac_cell.py:305-375) for writeInputs=BOTH, writeMemProj, optional self-attention
+ * summary and gate:
+ *   m' = [memory, info(, self_smry)] @ Ww + bw                       (339-352)
+ *   z  = sigmoid(control @ Wg + bg + gate_bias); m' = m'*z + memory*(1-z)   (358-367)   if Wg != NULL
+ * gate_out (may be NULL) receives z (attentions["gate"], mac_cell.py:365).
+ * --------------------------------------------------------------------------------------------- */
+int mac_write_fwd(const float* memory, const float* info, const float* self_smry, const float* control,
+                  const float* Ww, const float* bw, const float* Wg, const float* bg, float gate_bias,
+                  float* new_memory, float* gate_out,
+                  void* workspace, size_t workspace_bytes, int B, int d, mac_stream_t stream);
+size_t mac_write_workspace_bytes(int B, int d);
+
+/* ------------------------------------------------------------------------------------------------
+ * Elementwise helpers used by the Python-composed (non-fused) flag combinations and by state init.
+ * --------------------------------------------------------------------------------------------- */
+/* out[b,n,:] = (x[b,n,:] + mul_bias) * (v[b,:] + mul_bias)     ops.mul MUL (ops.py:694-703); x may equal out */
+int mac_bcast_mul(const float* x, const float* v, float mul_bias, float* out, int B, int N, int d, mac_stream_t stream);
+/* out = act(x) elementwise */
+int mac_activation(const float* x, int act, float* out, long long n, mac_stream_t stream);
+/* variational / plain dropout: out = x / keep * [u >= 1-keep]  with u from mac_dropout_uniform(seed, site, step) */
+int mac_dropout_fwd(const float* x, float keep, uint64_t seed, int site, int step, float* out, long long n,
+                    mac_stream_t stream);
+/* the uniforms the kernels draw, materialised (tests feed them to the oracle): u[i] in [0,1), 24 bits */
+int mac_dropout_uniform(uint64_t seed, int site, int step, float* u, long long n, mac_stream_t stream);
+/* fp32 -> bf16 (round-to-nearest-even), plain row-major; used once per forward for KB and per weight update */
+int mac_cast_bf16(const float* x, void* out_bf16, long long n, mac_stream_t stream);
+
+/* dropout sites (the `site` word of the Philox counter) */
+enum { MAC_SITE_MEM_VAR = 0, MAC_SITE_READ_KB = 1, MAC_SITE_READ_MEM = 2, MAC_SITE_READ_INTER = 3,
+       MAC_SITE_WRITE_INFO = 4, MAC_SITE_MEM_PLAIN = 5 };
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAC_B200_H_ */

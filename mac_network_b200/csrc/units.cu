@@ -1,0 +1,319 @@
+// C-ABI entry points of the three MAC units (fp32 projection path) and the elementwise helpers.
+#include "common.cuh"
+#include "sgemm.cuh"
+#include "tc_gemm.cuh"
+
+using namespace mac;
+
+namespace mac {
+constexpr size_t WS_HEADER = 4096;   // split-K tile counters live here; zero on entry and on exit of every call
+
+__global__ void bcast_mul_kernel(const float4* __restrict__ x, const float4* __restrict__ v, float mb,
+                                 float4* __restrict__ out, long long total4, int N, int d4) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  const long long row = i / d4;
+  const int k4 = (int)(i - row * d4);
+  const float4 a = x[i];
+  const float4 y = __ldg(v + (row / N) * d4 + k4);
+  out[i] = make_float4((a.x + mb) * (y.x + mb), (a.y + mb) * (y.y + mb), (a.z + mb) * (y.z + mb), (a.w + mb) * (y.w + mb));
+}
+
+__global__ void activation_kernel(const float* __restrict__ x, int act, float* __restrict__ out, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = apply_act(act, x[i]);
+}
+
+__global__ void dropout_kernel(const float* __restrict__ x, uint32_t thresh, float scale, uint64_t seed, int site,
+                               int step, float* __restrict__ out, float* __restrict__ u_out, long long n) {
+  const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long base = i4 * 4;
+  if (base >= n) return;
+  const Philox4 r = philox4x32_10(seed, (uint64_t)i4, (uint32_t)site, (uint32_t)step);
+  const uint32_t bits[4] = {r.x >> 8, r.y >> 8, r.z >> 8, r.w >> 8};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    if (base + q < n) {
+      if (u_out) u_out[base + q] = (float)bits[q] * (1.0f / 16777216.0f);
+      if (out) out[base + q] = (bits[q] >= thresh) ? x[base + q] * scale : 0.f;
+    }
+  }
+}
+
+__global__ void cast_bf16_kernel(const float4* __restrict__ x, uint2* __restrict__ out, long long n4) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 v = x[i];
+  __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+  uint2 o;
+  o.x = *reinterpret_cast<uint32_t*>(&lo);
+  o.y = *reinterpret_cast<uint32_t*>(&hi);
+  out[i] = o;
+}
+}  // namespace mac
+
+// ------------------------------------------------------------------------------------------------ misc
+extern "C" int mac_b200_abi_version(void) { return MAC_B200_ABI_VERSION; }
+
+extern "C" const char* mac_b200_strerror(int status) {
+  switch (status) {
+    case MAC_OK: return "ok";
+    case MAC_ERR_INVALID: return "invalid argument (size or null pointer)";
+    case MAC_ERR_ALIGN: return "pointer or stride not 16-byte aligned";
+    case MAC_ERR_UNSUPPORTED: return "flag/shape combination outside the fused path";
+    case MAC_ERR_WORKSPACE: return "workspace too small";
+    case MAC_ERR_ARCH: return "device is not sm_100 or the tensor-map driver entry point is missing";
+    default: return status > 0 ? cudaGetErrorString((cudaError_t)status) : "unknown mac_b200 status";
+  }
+}
+
+extern "C" int mac_b200_device_ok(void) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  int major = 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+  return major == 10 ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------------ linear
+extern "C" size_t mac_linear_workspace_bytes(int M, int K, int n_out) {
+  return WS_HEADER + sgemm_workspace_bytes(M, n_out, K);
+}
+
+extern "C" int mac_linear_fwd(const float* const* x_segs, const int* k_segs, const int* ldx, int nseg, const float* W,
+                              const float* b, float bias_const, int act, float* y, int ldy, int M, int n_out,
+                              void* workspace, size_t workspace_bytes, mac_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!x_segs || !k_segs || !ldx || nseg < 1 || nseg > 4 || !W || !y || M <= 0 || n_out <= 0) return MAC_ERR_INVALID;
+  SgemmParams p{};
+  p.a_mode = A_SEGS;
+  p.nseg = nseg;
+  int K = 0;
+  for (int i = 0; i < nseg; ++i) {
+    if (!x_segs[i] || k_segs[i] <= 0 || (k_segs[i] & 3) || (ldx[i] & 3)) return MAC_ERR_INVALID;
+    if (!mac_aligned16(x_segs[i])) return MAC_ERR_ALIGN;
+    p.a[i] = x_segs[i];
+    p.ak[i] = k_segs[i];
+    p.lda[i] = ldx[i];
+    K += k_segs[i];
+  }
+  if (!mac_aligned16(W) || !mac_aligned16(y) || (ldy & 3) || (n_out & 3)) return MAC_ERR_ALIGN;
+  p.W = W; p.ldw = n_out; p.M = M; p.N = n_out; p.K = K;
+  p.epi = EPI_BIAS_ACT; p.bias = b; p.bias_const = bias_const; p.act = act; p.Y = y; p.ldy = ldy;
+  char* ws = reinterpret_cast<char*>(workspace);
+  const bool have_ws = ws != nullptr && workspace_bytes > WS_HEADER;
+  return sgemm_launch(p, have_ws ? reinterpret_cast<unsigned int*>(ws) : nullptr,
+                      have_ws ? reinterpret_cast<float*>(ws + WS_HEADER) : nullptr,
+                      have_ws ? workspace_bytes - WS_HEADER : 0, stream);
+}
+
+// ------------------------------------------------------------------------------------------------ read unit
+// workspace layout: [header 4 KB | md [B,d] | y [B,d] | P [BN,d] | H [BN,d] | logit parts [BN, d/128.. <=8] | split-K]
+static size_t read_ws_layout(int B, int N, int d, size_t* off_md, size_t* off_y, size_t* off_P, size_t* off_H,
+                             size_t* off_parts, size_t* off_splitk) {
+  size_t o = WS_HEADER;
+  auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 255) & ~(size_t)255; return r; };
+  *off_md = take((size_t)B * d * 4);
+  *off_y = take((size_t)B * d * 4);
+  *off_P = take((size_t)B * N * d * 4);
+  *off_H = take((size_t)B * N * d * 4);
+  *off_parts = take((size_t)B * N * 16 * 4);
+  *off_splitk = o;
+  o += sgemm_workspace_bytes(B, d, d);
+  return o;
+}
+
+extern "C" size_t mac_read_workspace_bytes(int B, int N, int d, int prec) {
+  size_t a, b, c, e, f, g;
+  size_t fp32 = read_ws_layout(B, N, d, &a, &b, &c, &e, &f, &g);
+  if (prec == MAC_PREC_BF16) return fp32 + tc_read_extra_workspace_bytes(B, N, d);
+  return fp32;
+}
+
+extern "C" int mac_read_fwd(const float* kb, const void* kb_bf16, const float* memory_in, const float* control,
+                            const mac_read_weights* w, float keep_read, uint64_t seed, int step, int prec, float* info,
+                            float* att, float* save, void* workspace, size_t workspace_bytes, int B, int N, int d,
+                            mac_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!kb || !memory_in || !control || !w || !info || !att || !workspace) return MAC_ERR_INVALID;
+  if (B <= 0 || N <= 0 || d <= 0 || (d & 3)) return MAC_ERR_INVALID;
+  if (!(keep_read > 0.f && keep_read <= 1.f)) return MAC_ERR_INVALID;
+  if (!mac_aligned16(kb) || !mac_aligned16(memory_in) || !mac_aligned16(control) || !mac_aligned16(workspace))
+    return MAC_ERR_ALIGN;
+  if (workspace_bytes < mac_read_workspace_bytes(B, N, d, prec)) return MAC_ERR_WORKSPACE;
+  size_t o_md, o_y, o_P, o_H, o_parts, o_sk;
+  const size_t fp32_total = read_ws_layout(B, N, d, &o_md, &o_y, &o_P, &o_H, &o_parts, &o_sk);
+  char* ws = reinterpret_cast<char*>(workspace);
+  float* md = reinterpret_cast<float*>(ws + o_md);
+  const int M = B * N;
+  // saved activations for backward live in the caller's `save` when given: [P | H | I1 | y]
+  float* P = save ? save : reinterpret_cast<float*>(ws + o_P);
+  float* H = save ? save + (size_t)M * d : reinterpret_cast<float*>(ws + o_H);
+  float* I1 = save ? save + (size_t)2 * M * d : nullptr;
+  float* y = save ? save + (size_t)3 * M * d : reinterpret_cast<float*>(ws + o_y);
+  float* parts = reinterpret_cast<float*>(ws + o_parts);
+  const bool drop = keep_read < 1.f;
+  const uint32_t thr = drop ? keep_threshold(keep_read) : 0u;
+  const float scale = drop ? 1.f / keep_read : 1.f;
+
+  // md = dropout(memory_in, keep_read)   (ops.py:679)
+  const float* mem = memory_in;
+  if (drop) {
+    const long long n = (long long)B * d;
+    dropout_kernel<<<(unsigned)(((n + 3) / 4 + 255) / 256), 256, 0, stream>>>(memory_in, thr, scale, seed,
+                                                                            MAC_SITE_READ_MEM, step, md, nullptr, n);
+    MAC_LAUNCH_CHECK();
+    mem = md;
+  }
+  // y = md @ Wy + by   (ops.py:689)
+  {
+    SgemmParams p{};
+    p.a_mode = A_SEGS; p.nseg = 1; p.a[0] = mem; p.ak[0] = d; p.lda[0] = d;
+    p.W = w->Wy; p.ldw = d; p.M = B; p.N = d; p.K = d;
+    p.epi = EPI_BIAS_ACT; p.bias = w->by; p.act = MAC_ACT_NON; p.Y = y; p.ldy = d;
+    int st = sgemm_launch(p, reinterpret_cast<unsigned int*>(ws), reinterpret_cast<float*>(ws + o_sk),
+                          fp32_total - o_sk, stream);
+    if (st != MAC_OK) return st;
+  }
+  int nparts = 0;
+  if (prec == MAC_PREC_BF16) {
+    int st = tc_read_chain(kb_bf16, y, control, w, thr, scale, seed, step, P, H, I1, parts, &nparts,
+                           ws + fp32_total, workspace_bytes - fp32_total, B, N, d, save != nullptr, stream);
+    if (st != MAC_OK) return st;
+  } else {
+    // P = dropout(KB) @ Wx + bx   (ops.py:678, 688)
+    {
+      SgemmParams p{};
+      p.a_mode = drop ? A_DROPOUT : A_SEGS; p.nseg = 1; p.a[0] = kb; p.ak[0] = d; p.lda[0] = d;
+      p.a_thresh = thr; p.a_scale = scale; p.seed = seed; p.a_site = MAC_SITE_READ_KB; p.step = step;
+      p.W = w->Wx; p.ldw = d; p.M = M; p.N = d; p.K = d;
+      p.epi = EPI_BIAS_ACT; p.bias = w->bx; p.act = MAC_ACT_NON; p.Y = P; p.ldy = d;
+      int st = sgemm_launch(p, nullptr, nullptr, 0, stream, false);
+      if (st != MAC_OK) return st;
+    }
+    // H = ELU([P*y, P] @ Wm + bm)   (ops.py:694-719, mac_cell.py:236-238)
+    {
+      SgemmParams p{};
+      p.a_mode = A_ROWSCALE_CONCAT; p.nseg = 1; p.a[0] = P; p.lda[0] = d; p.rowvec = y; p.rows_per_batch = N;
+      p.W = w->Wm; p.ldw = d; p.M = M; p.N = d; p.K = 2 * d;
+      p.epi = EPI_BIAS_ACT; p.bias = w->bm; p.act = MAC_ACT_ELU; p.Y = H; p.ldy = d;
+      int st = sgemm_launch(p, nullptr, nullptr, 0, stream, false);
+      if (st != MAC_OK) return st;
+    }
+    // I1 = H @ Wm2 + bm2 ; I2 = ELU(I1 * control) ; logits = dropout(I2) . wr   (ops.py:325-328, mac_cell.py:248-266)
+    {
+      SgemmParams p{};
+      p.a_mode = A_SEGS; p.nseg = 1; p.a[0] = H; p.ak[0] = d; p.lda[0] = d;
+      p.W = w->Wm2; p.ldw = d; p.M = M; p.N = d; p.K = d; p.rows_per_batch = N;
+      p.epi = EPI_READ_LOGITS; p.bias = w->bm2; p.Y = I1; p.ldy = d;
+      p.ctrl = control; p.wr = w->wr; p.logit_parts = parts;
+      p.e_thresh = thr; p.e_scale = scale; p.e_site = MAC_SITE_READ_INTER; p.seed = seed; p.step = step;
+      int st = sgemm_launch(p, nullptr, nullptr, 0, stream, false);
+      if (st != MAC_OK) return st;
+      nparts = (M >= 512) ? (d + 127) / 128 : (d + 63) / 64;
+    }
+  }
+  if (nparts > 16) return MAC_ERR_UNSUPPORTED;
+  // att = softmax(logits); info = sum_n att * KB   (original, un-dropped KB: mac_cell.py:271-275)
+  if (prec == MAC_PREC_BF16 && kb_bf16 != nullptr)
+    return mac_kb_attend_fwd(parts, nparts, w->br, kb_bf16, 1, att, info, B, N, d, stream_);
+  return mac_kb_attend_fwd(parts, nparts, w->br, kb, 0, att, info, B, N, d, stream_);
+}
+
+// ------------------------------------------------------------------------------------------------ write unit
+extern "C" size_t mac_write_workspace_bytes(int B, int d) {
+  return WS_HEADER + (size_t)B * d * 4 + 256 + sgemm_workspace_bytes(B, d, 3 * d);
+}
+
+extern "C" int mac_write_fwd(const float* memory, const float* info, const float* self_smry, const float* control,
+                             const float* Ww, const float* bw, const float* Wg, const float* bg, float gate_bias,
+                             float* new_memory, float* gate_out, void* workspace, size_t workspace_bytes, int B, int d,
+                             mac_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!memory || !info || !Ww || !new_memory || !workspace || B <= 0 || d <= 0 || (d & 3)) return MAC_ERR_INVALID;
+  if (Wg && !control) return MAC_ERR_INVALID;
+  if (workspace_bytes < mac_write_workspace_bytes(B, d)) return MAC_ERR_WORKSPACE;
+  char* ws = reinterpret_cast<char*>(workspace);
+  float* tmp = reinterpret_cast<float*>(ws + WS_HEADER);
+  const size_t o_sk = WS_HEADER + (((size_t)B * d * 4 + 255) & ~(size_t)255);
+  // m' = [memory, info(, self_smry)] @ Ww + bw   (mac_cell.py:339-352), concat never materialised
+  SgemmParams p{};
+  p.a_mode = A_SEGS;
+  p.a[0] = memory; p.ak[0] = d; p.lda[0] = d;
+  p.a[1] = info; p.ak[1] = d; p.lda[1] = d;
+  p.nseg = 2;
+  if (self_smry) { p.a[2] = self_smry; p.ak[2] = d; p.lda[2] = d; p.nseg = 3; }
+  p.W = Ww; p.ldw = d; p.M = B; p.N = d; p.K = p.nseg * d;
+  p.epi = EPI_BIAS_ACT; p.bias = bw; p.act = MAC_ACT_NON;
+  p.Y = Wg ? tmp : new_memory; p.ldy = d;
+  {
+    int st = sgemm_launch(p, reinterpret_cast<unsigned int*>(ws), reinterpret_cast<float*>(ws + o_sk),
+                          workspace_bytes - o_sk, stream);
+    if (st != MAC_OK) return st;
+  }
+  if (Wg) {
+    // z = sigmoid(control @ Wg + bg + gate_bias); m' = m'*z + memory*(1-z)   (mac_cell.py:358-367)
+    SgemmParams g{};
+    g.a_mode = A_SEGS; g.nseg = 1; g.a[0] = control; g.ak[0] = d; g.lda[0] = d;
+    g.W = Wg; g.ldw = d; g.M = B; g.N = d; g.K = d;
+    g.epi = EPI_GATE; g.bias = bg; g.bias_const = gate_bias; g.Y = new_memory; g.ldy = d;
+    g.gnew = tmp; g.gold = memory; g.gate_z = gate_out;
+    int st = sgemm_launch(g, reinterpret_cast<unsigned int*>(ws), reinterpret_cast<float*>(ws + o_sk),
+                          workspace_bytes - o_sk, stream);
+    if (st != MAC_OK) return st;
+  }
+  return MAC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ elementwise
+extern "C" int mac_bcast_mul(const float* x, const float* v, float mul_bias, float* out, int B, int N, int d,
+                             mac_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!x || !v || !out || B <= 0 || N <= 0 || d <= 0 || (d & 3)) return MAC_ERR_INVALID;
+  if (!mac_aligned16(x) || !mac_aligned16(v) || !mac_aligned16(out)) return MAC_ERR_ALIGN;
+  const long long total4 = (long long)B * N * d / 4;
+  bcast_mul_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, stream>>>(
+      reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(v), mul_bias, reinterpret_cast<float4*>(out),
+      total4, N, d / 4);
+  MAC_LAUNCH_CHECK();
+  return MAC_OK;
+}
+
+extern "C" int mac_activation(const float* x, int act, float* out, long long n, mac_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!x || !out || n <= 0) return MAC_ERR_INVALID;
+  activation_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(x, act, out, n);
+  MAC_LAUNCH_CHECK();
+  return MAC_OK;
+}
+
+extern "C" int mac_dropout_fwd(const float* x, float keep, uint64_t seed, int site, int step, float* out, long long n,
+                               mac_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!x || !out || n <= 0 || !(keep > 0.f && keep <= 1.f)) return MAC_ERR_INVALID;
+  const uint32_t thr = keep < 1.f ? keep_threshold(keep) : 0u;
+  const float scale = keep < 1.f ? 1.f / keep : 1.f;
+  dropout_kernel<<<(unsigned)(((n + 3) / 4 + 255) / 256), 256, 0, stream>>>(x, thr, scale, seed, site, step, out,
+                                                                            nullptr, n);
+  MAC_LAUNCH_CHECK();
+  return MAC_OK;
+}
+
+extern "C" int mac_dropout_uniform(uint64_t seed, int site, int step, float* u, long long n, mac_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!u || n <= 0) return MAC_ERR_INVALID;
+  dropout_kernel<<<(unsigned)(((n + 3) / 4 + 255) / 256), 256, 0, stream>>>(nullptr, 0u, 1.f, seed, site, step, nullptr,
+                                                                            u, n);
+  MAC_LAUNCH_CHECK();
+  return MAC_OK;
+}
+
+extern "C" int mac_cast_bf16(const float* x, void* out_bf16, long long n, mac_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!x || !out_bf16 || n <= 0 || (n & 3)) return MAC_ERR_INVALID;
+  if (!mac_aligned16(x) || (reinterpret_cast<uintptr_t>(out_bf16) & 7)) return MAC_ERR_ALIGN;
+  cast_bf16_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const float4*>(x),
+                                                                       reinterpret_cast<uint2*>(out_bf16), n / 4);
+  MAC_LAUNCH_CHECK();
+  return MAC_OK;
+}

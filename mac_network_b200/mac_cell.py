@@ -1,0 +1,433 @@
+"""Host-side mirror of the reference's MAC cell over the sm_100a kernels in libmac_b200.so.
+
+Same call surface as `/root/reference/mac_cell.py`:
+
+    cell = MACCell(vecQuestions, questionWords, questionCntxWords, questionLengths, knowledgeBase,
+                   memoryDropout, readDropout, writeDropout, batchSize, train, reuse=None)   # mac_cell.py:59-61
+    state = cell.zero_state(batchSize)                                                      # mac_cell.py:539-592
+    for i in range(config.netLength):                                                       # model.py:453-458
+        cell.iteration = i
+        _, state = cell(none, state)                                                        # mac_cell.py:420-480
+    cell.attentions["kb" | "question" | "self" | "gate"][step]                              # model.py:740
+
+plus the three units with the reference signatures (`control` 133-187, `read` 209-277, `write`
+305-375).  Differences that the PyTorch/CUDA setting forces:
+  * the reference reads a module-global `config` and pulls weights out of TF variable scopes; here
+    they are the keyword-only arguments `config=` (a `MACConfig`) and `params=` (a `MACParams`, keyed by
+    the reference's variable names), defaulting to the module globals set with `set_defaults`.
+  * tensors are CUDA float32 `torch.Tensor`s; every arithmetic op is a kernel of libmac_b200.so --
+    there is no PyTorch/CPU fallback, and a missing library raises at construction.
+"""
+import collections
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import ACT, PREC, ReadWeights, check, ptr, stream_ptr
+from .config import MACConfig
+from .params import PREFIX, init_params, param_specs
+
+MACCellTuple = collections.namedtuple("MACCellTuple", ("control", "memory"))   # mac_cell.py:8
+
+_defaults = {"config": None, "params": None}
+
+
+def set_defaults(config=None, params=None):
+    """The analogue of the reference's global `config` (config.py:92) and of the enclosing variable scope."""
+    if config is not None:
+        _defaults["config"] = config
+    if params is not None:
+        _defaults["params"] = params
+
+
+class MACParams(object):
+    """Cell parameters on the device, keyed by the reference's TF variable names."""
+
+    def __init__(self, cfg, netLength=None, values=None, seed=0, device="cuda"):
+        self.cfg = cfg
+        self.L = cfg.netLength if netLength is None else netLength
+        self.specs = param_specs(cfg, self.L)
+        if values is None:
+            values = init_params(cfg, self.L, seed=seed)
+        missing = set(self.specs) - set(values)
+        if missing:
+            raise KeyError("missing parameters: %s" % sorted(missing)[:4])
+        self.device = torch.device(device)
+        self.t = collections.OrderedDict()
+        for name, (shape, _) in self.specs.items():
+            v = np.asarray(values[name], dtype=np.float32)
+            assert tuple(v.shape) == tuple(shape), (name, v.shape, shape)
+            self.t[name] = torch.from_numpy(np.ascontiguousarray(v)).to(self.device)
+        self.version = 0
+        self._derived = {}
+
+    def __getitem__(self, name):
+        return self.t[PREFIX + name]
+
+    def has(self, name):
+        return (PREFIX + name) in self.t
+
+    def lin(self, scope, name):
+        sc = scope + "linearLayer" + name + "/"
+        return self[sc + "weights/weight"], self[sc + "biases/bias"]
+
+    def numpy(self):
+        return collections.OrderedDict((k, v.detach().cpu().numpy()) for k, v in self.t.items())
+
+    def touch(self):
+        """Call after updating parameter values in place (optimizer step): drops packed/bf16 copies."""
+        self.version += 1
+        self._derived.clear()
+
+    def derived(self, key, fn):
+        if key not in self._derived:
+            self._derived[key] = fn()
+        return self._derived[key]
+
+    def scalar(self, name):
+        """0-d bias of an outDim == 1 linear (ops.py:304-305) as a python float (read once, cached)."""
+        return self.derived(("scalar", name), lambda: float(self[name].item()))
+
+
+class _Workspaces(object):
+    """Device scratch, allocated once per (B, N, d, precision); the first 4 KB of each stays zero (split-K counters)."""
+
+    def __init__(self, lib, B, N, d, prec, device):
+        self.read_bytes = int(lib.mac_read_workspace_bytes(B, N, d, prec))
+        self.write_bytes = int(lib.mac_write_workspace_bytes(B, d))
+        self.lin_bytes = int(lib.mac_linear_workspace_bytes(max(B, 64), 3 * d, max(d, 64) * 16))
+        self.read = torch.zeros(self.read_bytes, dtype=torch.uint8, device=device)
+        self.write = torch.zeros(self.write_bytes, dtype=torch.uint8, device=device)
+        self.lin = torch.zeros(self.lin_bytes, dtype=torch.uint8, device=device)
+
+
+class MACCell(object):
+    """The MAC recurrent cell (stateful, like the reference: mac_cell.py:32-34)."""
+
+    def __init__(self, vecQuestions, questionWords, questionCntxWords, questionLengths, knowledgeBase,
+                 memoryDropout, readDropout, writeDropout, batchSize, train, reuse=None, *,
+                 config=None, params=None, prec="fp32", seed=0):
+        self.lib = _lib.load()
+        self.cfg = config if config is not None else _defaults["config"]
+        self.params = params if params is not None else _defaults["params"]
+        if self.cfg is None or self.params is None:
+            raise ValueError("MACCell needs config= and params= (or set_defaults(...))")
+        if not isinstance(self.cfg, MACConfig):
+            raise TypeError("config must be a MACConfig")
+        self.cfg.validate()
+        if not self.cfg.is_fast_path:
+            raise NotImplementedError(
+                "this flag set is outside the fused sm_100a path (shipped args*.txt family); see DESIGN.md section 6")
+        c = self.cfg
+        unsupported = [k for k in ("controlConcatWords", "controlProj", "controlInWordsProj", "controlOutWordsProj",
+                                   "unsharedCells", "writeInfoProj", "writeMergeCtrl", "writeConcatMul")
+                       if getattr(c, k)]
+        if unsupported or c.writeInputs != "BOTH" or c.writeInfoAct != "NON" or c.writeMemAct != "NON" \
+                or not c.writeMemProj:
+            raise NotImplementedError("flags outside the fused path: %s" % unsupported)
+        for t in (vecQuestions, questionCntxWords, knowledgeBase):
+            if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+                raise ValueError("inputs must be contiguous CUDA float32 tensors")
+        self.vecQuestions = vecQuestions
+        self.questionWords = questionWords
+        self.questionCntxWords = questionCntxWords
+        self.questionLengths = questionLengths.to(torch.int32).contiguous()
+        self.knowledgeBase = knowledgeBase
+        self.dropouts = {"memory": float(memoryDropout), "read": float(readDropout), "write": float(writeDropout)}
+        self.batchSize = int(batchSize)
+        self.train = bool(train)
+        self.reuse = reuse
+        self.prec = PREC[prec]
+        self.seed = int(seed)
+        self.device = knowledgeBase.device
+        B, N, d = knowledgeBase.shape
+        self.B, self.N, self.d = B, N, d
+        assert B == self.batchSize and d == c.memDim == c.ctrlDim
+        self.none = torch.zeros((B, 1), dtype=torch.float32, device=self.device)     # mac_cell.py:75
+        self.iteration = 0
+        self.L = self.params.L
+        self.ws = _Workspaces(self.lib, B, N, d, self.prec, self.device)
+        self._hoist = not (c.controlFeedPrev or c.controlWholeQ or c.controlContinuous)
+        self._rw = {}
+        self.kb_bf16 = None
+
+    # ------------------------------------------------------------------ reference properties
+    @property
+    def state_size(self):
+        return MACCellTuple(self.cfg.ctrlDim, self.cfg.memDim)      # mac_cell.py:84-86
+
+    @property
+    def output_size(self):
+        return 1                                                     # mac_cell.py:91-93
+
+    # ------------------------------------------------------------------ thin wrappers over the C ABI
+    def _linear(self, xs, W, b, out, act="NON", bias_const=0.0):
+        """ops.linear (ops.py:298-333) on [M, sum k] segments; `xs` is a list of 2-D row-major views."""
+        n = len(xs)
+        M = xs[0].shape[0]
+        arr_p = (ctypes.c_void_p * n)(*[x.data_ptr() for x in xs])
+        arr_k = (ctypes.c_int * n)(*[x.shape[1] for x in xs])
+        arr_ld = (ctypes.c_int * n)(*[x.stride(0) for x in xs])
+        code = ACT["ELU"] if (act == "RELU" and self.cfg.relu == "ELU") else ACT["RELU_STD"] if act == "RELU" else ACT[act]
+        check(self.lib.mac_linear_fwd(arr_p, arr_k, arr_ld, n, ptr(W), ptr(b), float(bias_const), code, ptr(out),
+                                      out.stride(0), M, W.shape[1], ptr(self.ws.lin), self.ws.lin_bytes, stream_ptr()),
+              "mac_linear_fwd")
+        return out
+
+    def _attend(self, cc, cc_t, cc_b, inw, in_b, in_r, outw, out_b, out_r, lengths, w, b, att, out, nsteps, S):
+        check(self.lib.mac_control_attend_fwd(ptr(cc), cc_t, cc_b, ptr(inw), in_b, in_r, ptr(outw), out_b, out_r,
+                                              ptr(lengths), ptr(w), float(b), ptr(att), ptr(out), nsteps, self.B, S,
+                                              self.d, stream_ptr()), "mac_control_attend_fwd")
+
+    def _dropout(self, x, keep, site, step, out):
+        check(self.lib.mac_dropout_fwd(ptr(x), float(keep), self.seed, site, step, ptr(out), x.numel(), stream_ptr()),
+              "mac_dropout_fwd")
+        return out
+
+    def _new(self, *shape):
+        return torch.empty(shape, dtype=torch.float32, device=self.device)
+
+    # ------------------------------------------------------------------ state init (mac_cell.py:496-505, 539-592)
+    def initState(self, name, dim, initType, batchSize, out):
+        if initType == "PRM":
+            out.copy_(self.params[name].unsqueeze(0).expand(batchSize, dim))
+        elif initType == "ZERO":
+            out.zero_()
+        else:  # "Q"
+            out.copy_(self.vecQuestions)
+        return out
+
+    def zero_state(self, batchSize=None, dtype=None):
+        c, B, d, L = self.cfg, self.B, self.d, self.L
+        self.attentions = {"kb": [], "question": [], "self": [], "gate": []}        # mac_cell.py:541
+        # step-major histories [L+1, B, d]; the reference's [B, i+1, d] tensors are permuted views of these
+        self._hc = self._new(L + 1, B, d)
+        self._hm = self._new(L + 1, B, d)
+        self._hi = self._new(L + 1, B, d)
+        c0 = self.initState("initCtrl", c.ctrlDim, c.initCtrl, B, self._hc[0])
+        m0 = self.initState("initMem", c.memDim, c.initMem, B, self._hm[0])
+        self._hi[0].copy_(m0)                                                          # mac_cell.py:551
+        self._set_histories(0)
+        self.contControl = c0                                                          # mac_cell.py:553
+        words = self.questionCntxWords if c.controlContextual else self.questionWords  # mac_cell.py:570
+        self.inWords = self.outWords = words
+        self._att_q = self._new(L, B, words.shape[1])
+        self._att_kb = self._new(L, B, self.N)
+        self._gate = self._new(L, B, d) if c.writeGate else None
+        if self.prec == PREC["bf16"]:
+            self.kb_bf16 = torch.empty(self.knowledgeBase.shape, dtype=torch.bfloat16, device=self.device)
+            check(self.lib.mac_cast_bf16(ptr(self.knowledgeBase), ptr(self.kb_bf16), self.knowledgeBase.numel(),
+                                         stream_ptr()), "mac_cast_bf16")
+        self._mem_in = self._new(B, d)
+        if self._hoist:
+            self._control_all_steps()
+        return MACCellTuple(c0, m0)
+
+    def _set_histories(self, i):
+        self.controls = self._hc[:i + 1].permute(1, 0, 2)      # [B, i+1, d] like mac_cell.py:549, 472
+        self.memories = self._hm[:i + 1].permute(1, 0, 2)
+        self.infos = self._hi[:i + 1].permute(1, 0, 2)
+
+    # ------------------------------------------------------------------ control unit
+    def _question_input(self):
+        """u = act(linear_qInput(vecQuestions)) (mac_cell.py:442-445): weights shared over steps => once per forward."""
+        W, b = self.params.lin("MACCell/", "qInput")
+        u = self._linear([self.vecQuestions], W, b, self._new(self.B, self.d), act=self.cfg.controlInputAct)
+        return u
+
+    def _control_all_steps(self):
+        """With controlFeedPrev off the control chain does not depend on memory (mac_cell.py:141-151): compute
+        ci_i = linear_qInput{i}(u) for every step with ONE GEMM against the packed [d, L*d] weight, then ONE
+        attention launch that streams each batch row's words once for all L steps."""
+        c, B, d, L = self.cfg, self.B, self.d, self.L
+        u = self._question_input()
+        if c.controlInputUnshared:
+            def pack():
+                Ws = [self.params.lin("MACCell/", "qInput%d" % i) for i in range(L)]
+                return (torch.cat([w for w, _ in Ws], dim=1).contiguous(), torch.cat([b for _, b in Ws]).contiguous())
+            Wc, bc = self.params.derived("qInputCat", pack)
+            self._ci = self._linear([u], Wc, bc, self._new(B, L * d))              # [B, L*d]: ci_i = [:, i*d:(i+1)*d]
+            cc_t, cc_b = d, L * d
+        else:
+            W, b = self.params.lin("MACCell/", "qInputU")
+            self._ci = self._linear([u], W, b, self._new(B, d))
+            cc_t, cc_b = 0, d                                                       # same query for every step
+        sc = "MACCell/control/inter2logits/linearLayerlogits/"
+        w = self.params[sc + "weights/weight"]
+        bl = self.params.scalar(sc + "biases/bias")
+        S = self.inWords.shape[1]
+        self._attend(self._ci, cc_t, cc_b, self.inWords, S * d, d, self.outWords, S * d, d, self.questionLengths,
+                     w, bl, self._att_q, self._hc[1:], L, S)
+
+    def control(self, controlInput, inWords, outWords, questionLengths, control, contControl=None, name="",
+                reuse=None, _att_out=None, _out=None):
+        """mac_cell.py:133-187 (returns newControl, newContControl)."""
+        c, B, d = self.cfg, self.B, self.d
+        sc = "MACCell/control" + name + "/"
+        newContControl = controlInput
+        if c.controlFeedPrev:
+            prev = control if c.controlFeedPrevAtt else contControl
+            xs = [prev, controlInput] if c.controlFeedInputs else [prev]
+            W, b = self.params.lin(sc, "contControl")
+            newContControl = self._linear(xs, W, b, self._new(B, d), act=c.controlContAct)
+            if c.controlContAct != "NON":                                            # nested "_2" layer, ops.py:325-328
+                W2, b2 = self.params.lin(sc + "linearLayercontControl/", "contControl_2")
+                newContControl = self._linear([newContControl], W2, b2, self._new(B, d))
+        S = inWords.shape[1]
+        att = _att_out if _att_out is not None else self._new(B, S)
+        out = _out if _out is not None else self._new(B, d)
+        lsc = sc + "inter2logits/linearLayerlogits/"
+        self._attend(newContControl, 0, d, inWords, S * d, d, outWords, S * d, d, questionLengths,
+                     self.params[lsc + "weights/weight"], self.params.scalar(lsc + "biases/bias"), att, out, 1, S)
+        self.attentions["question"].append(att)
+        newControl = out
+        if c.controlContinuous:
+            newControl = newContControl
+        return newControl, newContControl
+
+    # ------------------------------------------------------------------ read unit
+    def _read_weights(self, name):
+        if name in self._rw:
+            return self._rw[name]
+        p, sc = self.params, "MACCell/read" + name + "/"
+        Wx, bx = p.lin(sc + "mulmemInter/", "projX")
+        Wy, by = p.lin(sc + "mulmemInter/", "projY")
+        Wm, bm = p.lin(sc, "memKbProj")
+        Wm2, bm2 = p.lin(sc + "linearLayermemKbProj/", "memKbProj_2")
+        lsc = sc + "inter2att/inter2logits/linearLayerlogits/"
+        rw = ReadWeights(Wx.data_ptr(), bx.data_ptr(), Wy.data_ptr(), by.data_ptr(), Wm.data_ptr(), bm.data_ptr(),
+                         Wm2.data_ptr(), bm2.data_ptr(), p[lsc + "weights/weight"].data_ptr(),
+                         p.scalar(lsc + "biases/bias"), None, None, None)
+        if self.prec == PREC["bf16"]:
+            def cast(t):
+                o = torch.empty(t.shape, dtype=torch.bfloat16, device=t.device)
+                check(self.lib.mac_cast_bf16(ptr(t), ptr(o), t.numel(), stream_ptr()), "mac_cast_bf16")
+                return o
+            keep = p.derived(("bf16", sc), lambda: (cast(Wx), cast(Wm), cast(Wm2)))
+            rw.Wx_bf16, rw.Wm_bf16, rw.Wm2_bf16 = (t.data_ptr() for t in keep)
+        self._rw[name] = rw
+        return rw
+
+    def read(self, knowledgeBase, memory, control, name="", reuse=None, _att_out=None, _out=None, _save=None):
+        """mac_cell.py:209-277 (returns the retrieved information [B, memDim])."""
+        c, B, N, d = self.cfg, self.B, self.N, self.d
+        i = self.iteration
+        keep_m = self.dropouts["memory"]
+        if keep_m < 1.0:
+            if c.memoryVariationalDropout:     # one mask per forward (mac_cell.py:589-590): site MEM_VAR, step 0
+                memory = self._dropout(memory, keep_m, _lib.SITE_MEM_VAR, 0, self._mem_in)
+            else:
+                memory = self._dropout(memory, keep_m, _lib.SITE_MEM_PLAIN, i, self._mem_in)
+        att = _att_out if _att_out is not None else self._new(B, N)
+        info = _out if _out is not None else self._new(B, d)
+        rw = self._read_weights(name)
+        check(self.lib.mac_read_fwd(ptr(knowledgeBase), ptr(self.kb_bf16), ptr(memory), ptr(control),
+                                    ctypes.byref(rw), float(self.dropouts["read"]), self.seed, i, self.prec,
+                                    ptr(info), ptr(att), ptr(_save), ptr(self.ws.read), self.ws.read_bytes, B, N, d,
+                                    stream_ptr()), "mac_read_fwd")
+        self.attentions["kb"].append(att)
+        return info
+
+    # ------------------------------------------------------------------ write unit
+    def write(self, memory, info, control, contControl=None, name="", reuse=None, _out=None, _gate_out=None):
+        """mac_cell.py:305-375 (returns the new memory [B, memDim])."""
+        c, B, d = self.cfg, self.B, self.d
+        sc = "MACCell/write" + name + "/"
+        i = self.iteration
+        selfSmry = None
+        if c.writeSelfAtt:
+            selfControl = contControl if c.writeSelfAttMod == "CONT" else control
+            W, b = self.params.lin(sc, "ctrlProj")
+            selfControl = self._linear([selfControl], W, b, self._new(B, d))
+            lsc = sc + "inter2attselfAttention/inter2logits/linearLayerlogits/"
+            att = self._new(B, i + 1)
+            selfSmry = self._new(B, d)
+            # interactions = controls * selfControl; attention over the i+1 history rows; summary of memories
+            self._attend(selfControl, 0, selfControl.stride(0), self._hc, d, B * d, self._hm, d, B * d, None,
+                         self.params[lsc + "weights/weight"], self.params.scalar(lsc + "biases/bias"), att, selfSmry,
+                         1, i + 1)
+            self.attentions["self"].append(att)
+        Ww, bw = self.params.lin(sc, "newMemory")
+        Wg = bg = None
+        gate = None
+        if c.writeGate:
+            Wg, bg = self.params.lin(sc, "gate")
+            gate = _gate_out if _gate_out is not None else self._new(B, d)
+        out = _out if _out is not None else self._new(B, d)
+        check(self.lib.mac_write_fwd(ptr(memory), ptr(info), ptr(selfSmry), ptr(control), ptr(Ww), ptr(bw), ptr(Wg),
+                                     ptr(bg), float(c.writeGateBias), ptr(out), ptr(gate), ptr(self.ws.write),
+                                     self.ws.write_bytes, B, d, stream_ptr()), "mac_write_fwd")
+        if c.writeGate:
+            self.attentions["gate"].append(gate)
+        return out
+
+    # ------------------------------------------------------------------ one reasoning step (mac_cell.py:420-480)
+    def __call__(self, inputs, state, scope=None):
+        c, B, d = self.cfg, self.B, self.d
+        i = self.iteration
+        if i >= self.L:
+            raise IndexError("iteration %d >= netLength %d the parameters were built for" % (i, self.L))
+        control, memory = state.control, state.memory
+        if self._hoist:
+            newControl = self._hc[i + 1]
+            self.contControl = self._ci[:, i * d:(i + 1) * d] if c.controlInputUnshared else self._ci
+            self.attentions["question"].append(self._att_q[i])
+        else:
+            u = self._question_input() if i == 0 else self._u
+            self._u = u
+            nameU = ("qInput%d" % i) if c.controlInputUnshared else "qInputU"
+            W, b = self.params.lin("MACCell/", nameU)
+            ci = self._linear([u], W, b, self._new(B, d))
+            newControl, self.contControl = self.control(ci, self.inWords, self.outWords, self.questionLengths,
+                                                        control, self.contControl, _att_out=self._att_q[i],
+                                                        _out=self._hc[i + 1])
+            if c.controlContinuous:
+                self._hc[i + 1].copy_(newControl)
+                newControl = self._hc[i + 1]
+        if c.controlWholeQ:                                                            # mac_cell.py:455-456
+            self._hc[i + 1].copy_(self.vecQuestions)
+            newControl = self._hc[i + 1]
+        info = self.read(self.knowledgeBase, memory, newControl, _att_out=self._att_kb[i], _out=self._hi[i + 1])
+        if c.writeDropout < 1.0 and self.dropouts["write"] < 1.0:                      # mac_cell.py:461-463
+            info = self._dropout(info, self.dropouts["write"], _lib.SITE_WRITE_INFO, i, self._hi[i + 1])
+        newMemory = self.write(memory, info, newControl, self.contControl, _out=self._hm[i + 1],
+                               _gate_out=None if self._gate is None else self._gate[i])
+        self._set_histories(i + 1)                                                     # mac_cell.py:472-474
+        return self.none, MACCellTuple(newControl, newMemory)
+
+    # ------------------------------------------------------------------ test support
+    def dropout_uniforms(self):
+        """The uniforms the kernels draw for this forward, in the reference's call order (zero_state mask, then per
+        step KB / memory / interactions / write) -- tests hand them to the oracle."""
+        c, B, N, d, L = self.cfg, self.B, self.N, self.d, self.L
+        out = []
+
+        def draw(site, step, shape):
+            u = torch.empty(shape, dtype=torch.float32, device=self.device)
+            check(self.lib.mac_dropout_uniform(self.seed, site, step, ptr(u), u.numel(), stream_ptr()), "uniform")
+            return u.cpu().numpy().astype(np.float64)
+        km, kr, kw = self.dropouts["memory"], self.dropouts["read"], self.dropouts["write"]
+        if c.memoryVariationalDropout and km < 1.0:
+            out.append(draw(_lib.SITE_MEM_VAR, 0, (B, d)))
+        for i in range(L):
+            if not c.memoryVariationalDropout and km < 1.0:
+                out.append(draw(_lib.SITE_MEM_PLAIN, i, (B, d)))
+            if kr < 1.0:
+                out.append(draw(_lib.SITE_READ_KB, i, (B, N, d)))
+                out.append(draw(_lib.SITE_READ_MEM, i, (B, d)))
+                out.append(draw(_lib.SITE_READ_INTER, i, (B, N, d)))
+            if c.writeDropout < 1.0 and kw < 1.0:
+                out.append(draw(_lib.SITE_WRITE_INFO, i, (B, d)))
+        return out
+
+
+def mac_network(cell, netLength):
+    """The caller of the cell, `MACnet.MACnetwork` (model.py:447-458, 486-487): zero_state + static unroll."""
+    state = cell.zero_state(cell.batchSize)
+    none = cell.none
+    for i in range(netLength):
+        cell.iteration = i
+        _, state = cell(none, state)
+    return state.control, state.memory

@@ -1,0 +1,164 @@
+"""GPU parity: the sm_100a kernels (through the C ABI / MACCell host mirror) against the fp64 oracle and
+against the golden fixtures produced by the unmodified reference.  Tolerance (BASELINE.json north_star):
+fp32 projections within 1e-4 relative (max |x - ref| / max |ref| per tensor), probabilities with a 1e-6
+absolute floor."""
+import numpy as np
+import pytest
+import torch
+
+from oracle.mac_oracle import MACOracle
+from mac_network_b200.config import MACConfig
+from mac_network_b200.params import init_params, perturb_biases
+from mac_network_b200.synthetic import make_inputs
+from tests._util import golden_cases, load_golden, rebuild, max_rel
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4
+FAST_FIXTURES = [c for c in golden_cases() if not c.startswith("p2_") and not c.startswith("novardp")] + \
+                ["novardp_train_small"]
+
+
+def _to_dev(inputs):
+    out = {}
+    for k, v in inputs.items():
+        out[k] = torch.from_numpy(np.ascontiguousarray(v)).cuda()
+    return out
+
+
+def run_gpu(cfg, params_np, inputs_np, L, dropouts=(1.0, 1.0, 1.0), train=False, prec="fp32", seed=0):
+    from mac_network_b200.mac_cell import MACCell, MACParams
+    p32 = {k: np.asarray(v, np.float32) for k, v in params_np.items()}
+    params = MACParams(cfg, L, values=p32)
+    x = _to_dev({k: (np.asarray(v, np.float32) if v.dtype != np.int32 else v) for k, v in inputs_np.items()})
+    cell = MACCell(x["vecQuestions"], x["questionWords"], x["questionCntxWords"], x["questionLengths"],
+                   x["knowledgeBase"], dropouts[0], dropouts[1], dropouts[2], x["knowledgeBase"].shape[0], train,
+                   config=cfg, params=params, prec=prec, seed=seed)
+    state = cell.zero_state(cell.batchSize)
+    trace = []
+    for i in range(L):
+        cell.iteration = i
+        _, state = cell(cell.none, state)
+        trace.append((state.control, state.memory, cell.contControl))
+    torch.cuda.synchronize()
+    out = {
+        "control": np.stack([t[0].cpu().numpy() for t in trace]),
+        "memory": np.stack([t[1].cpu().numpy() for t in trace]),
+        "contControl": np.stack([t[2].cpu().numpy() for t in trace]),
+        "info": cell.infos.permute(1, 0, 2)[1:].cpu().numpy(),
+        "att_question": np.stack([a.cpu().numpy() for a in cell.attentions["question"]]),
+        "att_kb": np.stack([a.cpu().numpy() for a in cell.attentions["kb"]]),
+    }
+    if cell.attentions["gate"]:
+        out["att_gate"] = np.stack([a.cpu().numpy() for a in cell.attentions["gate"]])
+    for i, a in enumerate(cell.attentions["self"]):
+        out["att_self_%d" % i] = a.cpu().numpy()
+    return out, cell
+
+
+def run_oracle(cfg, params_np, inputs_np, L, dropouts=(1.0, 1.0, 1.0), uniforms=None):
+    orc = MACOracle(cfg, params_np, dtype=np.float64)
+    orc.run(L, inputs_np["vecQuestions"], inputs_np["questionWords"], inputs_np["questionCntxWords"],
+            inputs_np["questionLengths"], inputs_np["knowledgeBase"], memoryDropout=dropouts[0],
+            readDropout=dropouts[1], writeDropout=dropouts[2], uniforms=uniforms)
+    return orc.outputs()
+
+
+def compare(got, ref, tol=TOL, what=""):
+    assert set(got) == set(ref), (sorted(got), sorted(ref))
+    worst = {}
+    for k in ref:
+        err = max_rel(got[k], ref[k])
+        worst[k] = err
+        if k.startswith("att_") and k != "att_gate":
+            assert np.max(np.abs(got[k] - ref[k])) < max(tol * np.max(np.abs(ref[k])), 1e-6), (what, k, err)
+        else:
+            assert err < tol, (what, k, err)
+    return worst
+
+
+def test_library_is_native_and_device_ok():
+    from mac_network_b200 import _lib
+    lib = _lib.load()
+    assert lib.mac_b200_device_ok() == 1
+
+
+@pytest.mark.parametrize("case", [c for c in FAST_FIXTURES if "train" not in c])
+def test_eval_matches_reference_fixture(case):
+    """Kernels vs the outputs of the unmodified reference cell (fixture) -- eval mode."""
+    meta, gold = load_golden(case)
+    cfg, inputs, params = rebuild(meta, np.float64)
+    L = meta["shape"]["L"]
+    got, _ = run_gpu(cfg, params, inputs, L)
+    ref = {k: v.astype(np.float64) for k, v in gold.items() if not k.startswith(("uniform_", "final_"))}
+    compare(got, ref, what=case)
+
+
+@pytest.mark.parametrize("variant,shape", [
+    ("args", (32, 20, 196, 512, 4)),      # BASELINE configs[1]
+    ("args3", (16, 20, 196, 512, 4)),
+    ("args4", (16, 20, 196, 512, 4)),
+    ("args1", (16, 20, 196, 512, 4)),
+    ("gqa", (64, 30, 49, 512, 6)),        # BASELINE configs[4]
+    ("args", (5, 9, 50, 64, 3)),          # ragged: B*N not a tile multiple, d = 64
+    ("gqa", (3, 1, 1, 128, 2)),           # degenerate: one word, one KB cell
+])
+def test_eval_matches_oracle(variant, shape):
+    B, S, N, d, L = shape
+    cfg = MACConfig.args(variant, netLength=L, memDim=d, ctrlDim=d, attDim=d)
+    inputs = make_inputs(B, S, N, d, seed=11, dtype=np.float64)
+    params = perturb_biases(init_params(cfg, L, seed=12, dtype=np.float64), seed=13)
+    got, _ = run_gpu(cfg, params, inputs, L)
+    ref = run_oracle(cfg, params, inputs, L)
+    compare(got, ref, what="%s%s" % (variant, shape))
+    # properties the domain offers, at full size
+    qa = got["att_question"]
+    assert np.allclose(qa.sum(-1), 1.0, atol=1e-5)
+    for b, n in enumerate(inputs["questionLengths"]):
+        assert np.all(qa[:, b, n:] == 0.0)
+    assert np.allclose(got["att_kb"].sum(-1), 1.0, atol=1e-5)
+
+
+@pytest.mark.parametrize("variant,shape,dp", [
+    ("args", (8, 12, 196, 512, 3), (0.85, 0.85, 1.0)),
+    ("gqa", (8, 10, 49, 128, 4), (0.85, 0.85, 0.9)),
+    ("args1", (4, 6, 20, 64, 3), (0.7, 0.6, 1.0)),
+])
+def test_train_mode_matches_oracle_with_same_masks(variant, shape, dp):
+    """Training-mode forward: the kernels draw Philox masks in-kernel; the oracle is fed the same uniforms
+    (materialised by mac_dropout_uniform) in the reference's call order."""
+    B, S, N, d, L = shape
+    over = dict(netLength=L, memDim=d, ctrlDim=d, attDim=d)
+    if dp[2] < 1.0:
+        over["writeDropout"] = dp[2]
+    cfg = MACConfig.args(variant, **over)
+    inputs = make_inputs(B, S, N, d, seed=21, dtype=np.float64)
+    params = perturb_biases(init_params(cfg, L, seed=22, dtype=np.float64), seed=23)
+    got, cell = run_gpu(cfg, params, inputs, L, dropouts=dp, train=True, seed=1234567)
+    ref = run_oracle(cfg, params, inputs, L, dropouts=dp, uniforms=cell.dropout_uniforms())
+    compare(got, ref, what="train-%s" % variant)
+
+
+def test_novardp_fixture_train_semantics():
+    """Non-variational memory dropout draws a fresh [B,d] mask every step (mac_cell.py:217)."""
+    B, S, N, d, L = 4, 6, 20, 64, 3
+    flags = ["--relu=ELU", "--controlContextual", "--readProjInputs", "--readMemConcatKB", "--readMemConcatProj",
+             "--readMemProj", "--readCtrl", "--writeMemProj", "--initCtrl=Q", "--controlInputUnshared"]
+    cfg = MACConfig.from_flags(flags, netLength=L, memDim=d, ctrlDim=d, attDim=d)
+    inputs = make_inputs(B, S, N, d, seed=31, dtype=np.float64)
+    params = perturb_biases(init_params(cfg, L, seed=32, dtype=np.float64), seed=33)
+    dp = (0.8, 0.9, 1.0)
+    got, cell = run_gpu(cfg, params, inputs, L, dropouts=dp, train=True, seed=99)
+    ref = run_oracle(cfg, params, inputs, L, dropouts=dp, uniforms=cell.dropout_uniforms())
+    compare(got, ref, what="novardp")
+
+
+def test_inputs_are_not_modified():
+    B, S, N, d, L = 4, 6, 20, 64, 2
+    cfg = MACConfig.args("gqa", netLength=L, memDim=d, ctrlDim=d, attDim=d)
+    inputs = make_inputs(B, S, N, d, seed=5, dtype=np.float64)
+    params = init_params(cfg, L, seed=6, dtype=np.float64)
+    _, cell = run_gpu(cfg, params, inputs, L)
+    assert np.array_equal(cell.knowledgeBase.cpu().numpy(), inputs["knowledgeBase"].astype(np.float32))
+    assert np.array_equal(cell.questionCntxWords.cpu().numpy(), inputs["questionCntxWords"].astype(np.float32))
+    assert np.array_equal(cell.vecQuestions.cpu().numpy(), inputs["vecQuestions"].astype(np.float32))
