@@ -1,0 +1,402 @@
+#!/usr/bin/env python
+"""bench.py -- MAC reasoning steps/sec on synthetic CLEVR-shaped batches (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--prec bf16|fp32] [--impl ours|reference]
+
+A bench "step" is one full pass of the hot path over one batch: the netLength-step unroll of the MAC cell
+(model.py:447-458) on B=64 questions -- 12 reasoning steps at the headline configuration (BASELINE.json
+configs[2]: B=64, S=40, 14x14 KB, d=512, netLength=12).  `value` = reasoning steps/s = K * netLength * N / t.
+
+  value   inputs resident in HBM when the timed region starts; the K timed passes rotate over 8 resident
+          batches (8 x 31 MB > 126 MB L2) so the knowledge base comes from HBM every pass.
+  e2e     the same metric through the public API with HOST (pinned) buffers: per pass the H2D copy of the batch
+          (KB, words, question vector, lengths) and the D2H read of the final state + attention maps are inside the
+          timed region (double-buffered against compute on a copy stream).
+  roofline / roofline_kb_attend   per-kernel, measured live with CUDA events around single launches (cold L2).
+  cpu_baseline   the oracle's fp32 PyTorch-CPU port (oracle/mac_torch_cpu.py) timed on this box's host cores.
+
+`--impl reference` times that CPU port alone (TensorFlow-1 cannot be installed offline).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from mac_network_b200.config import MACConfig  # noqa: E402
+from mac_network_b200.params import init_params, perturb_biases  # noqa: E402
+from mac_network_b200.synthetic import SHAPES, make_inputs  # noqa: E402
+
+METRIC = "mac_reasoning_steps_per_sec"
+UNIT = "reasoning-steps/s"
+WORKLOAD = "headline"            # BASELINE.json configs[2]
+NSLOTS = 8
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm": p["hbm_gbs"], "tensor_burst": p["bf16_tflops"], "tensor_sustained": p["bf16_tflops_sustained"],
+                "src": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm": 6650.0, "tensor_burst": 1590.0, "tensor_sustained": 1400.0, "src": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler(object):
+    """nvidia-smi sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+def cpu_reference(cfg, shape, params_np, budget_s=15.0, max_forwards=8):
+    """The oracle's op-by-op fp32 CPU port on all host threads.  Returns reasoning-steps/s and a description."""
+    from oracle.mac_torch_cpu import TorchCPUCell
+    B, S, N, d, L = shape
+    torch.set_num_threads(os.cpu_count() or 1)
+    inp = make_inputs(B, S, N, d, seed=1234)
+    cell = TorchCPUCell(cfg, params_np, L)
+    args = (torch.from_numpy(inp["vecQuestions"]), torch.from_numpy(inp["questionCntxWords"]),
+            torch.from_numpy(inp["questionLengths"]).long(), torch.from_numpy(inp["knowledgeBase"]))
+    t0 = time.perf_counter()
+    cell.forward(*args)                                 # warm-up (also sizes the sample)
+    t1 = time.perf_counter() - t0
+    n = int(max(1, min(max_forwards, budget_s / max(t1, 1e-3))))
+    t0 = time.perf_counter()
+    for _ in range(n):
+        cell.forward(*args)
+    dt = (time.perf_counter() - t0) / n
+    return {"value": L / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "%d full forward passes (B=%d, netLength=%d) of the fp32 PyTorch-CPU port after 1 warm-up; "
+                      "%.3f s per pass" % (n, B, L, dt)}, dt
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+class Slot(object):
+    """One resident batch + its cell + the captured CUDA graph of the netLength unroll."""
+
+    def __init__(self, cfg, params, shape, seed, prec, use_graph, host_inputs=None):
+        from mac_network_b200.mac_cell import MACCell, mac_network
+        B, S, N, d, L = shape
+        inp = host_inputs if host_inputs is not None else make_inputs(B, S, N, d, seed=seed)
+        self.x = {k: torch.from_numpy(v).cuda() for k, v in inp.items()}
+        x = self.x
+        self.cell = MACCell(x["vecQuestions"], x["questionWords"], x["questionCntxWords"], x["questionLengths"],
+                            x["knowledgeBase"], 1.0, 1.0, 1.0, B, False, config=cfg, params=params, prec=prec)
+        self.L = L
+        self.graph = None
+        self._net = mac_network
+        self.run()                                        # warm-up: fills caches (packed weights, scalars, attrs)
+        torch.cuda.synchronize()
+        from mac_network_b200 import _lib
+        n0 = _lib.load().mac_b200_launch_count()
+        self.run()                                        # steady-state pass: count the kernels it launches
+        torch.cuda.synchronize()
+        self.launches = _lib.load().mac_b200_launch_count() - n0
+        if use_graph:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._net(self.cell, self.L)
+            self.graph = g
+
+    def run(self):
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._net(self.cell, self.L)
+
+    def outputs(self):
+        c = self.cell
+        return [c._hc[self.L], c._hm[self.L], c._att_kb, c._att_q]
+
+
+def time_kernel(fn, flush, iters=20):
+    """Average duration (s) of single launches, each after an L2 flush, CUDA events on the launching stream."""
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+    for _ in range(3):
+        fn()
+    for a, b in ev:
+        flush.zero_()
+        a.record()
+        fn()
+        b.record()
+    torch.cuda.synchronize()
+    return float(np.mean([a.elapsed_time(b) for a, b in ev])) * 1e-3
+
+
+def kernel_rooflines(shape, prec, pk):
+    """Per-kernel rooflines measured live: K3 (KB attention, HBM-bound) and the dominant projection GEMM."""
+    from mac_network_b200 import _lib as L
+    lib = L.load()
+    B, S, N, d, _ = shape
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    out = {}
+    # ---- K3: softmax over the KB + weighted sum.  Algorithmic bytes: KB once + logits in + att out + info out
+    for name, bf16 in (("fp32_kb", 0), ("bf16_kb", 1)):
+        kb = torch.randn(B, N, d, device="cuda")
+        kbx = kb.to(torch.bfloat16) if bf16 else kb
+        parts = torch.randn(B, N, 4, device="cuda")
+        att = torch.empty(B, N, device="cuda")
+        info = torch.empty(B, d, device="cuda")
+
+        def k3():
+            L.check(lib.mac_kb_attend_fwd(L.ptr(parts), 4, 0.0, L.ptr(kbx), bf16, L.ptr(att), L.ptr(info), B, N, d,
+                                          L.stream_ptr()))
+        t = time_kernel(k3, flush)
+        nbytes = B * N * d * (2 if bf16 else 4) + B * N * 4 * 4 + B * N * 4 + B * d * 4
+        out["kb_attend_" + name] = {"bound": "hbm", "achieved": nbytes / t / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                                    "frac": nbytes / t / 1e9 / pk["hbm"], "traffic": None, "us": t * 1e6,
+                                    "algorithmic_bytes": nbytes, "l2": "flushed before every launch"}
+    # ---- dominant projection GEMM: memKbProj, [B*N, 2d] x [2d, d] (49.6 % of the step's FLOPs)
+    M, K = B * N, 2 * d
+    x = torch.randn(M, K, device="cuda")
+    W = torch.randn(K, d, device="cuda") / K ** 0.5
+    bias = torch.zeros(d, device="cuda")
+    y = torch.empty(M, d, device="cuda")
+    import ctypes
+    arr_p = (ctypes.c_void_p * 1)(x.data_ptr())
+    arr_k = (ctypes.c_int * 1)(K)
+
+    def gemm():
+        L.check(lib.mac_linear_fwd(arr_p, arr_k, arr_k, 1, L.ptr(W), L.ptr(bias), 0.0, 3, L.ptr(y), d, M, d, None, 0,
+                                   L.stream_ptr()))
+    t = time_kernel(gemm, flush, iters=10)
+    flops = 2.0 * M * K * d
+    out["memKbProj_gemm_fp32"] = {"bound": "tensor", "achieved": flops / t / 1e12, "peak": pk["tensor_burst"],
+                                  "unit": "TFLOP/s", "frac": flops / t / 1e12 / pk["tensor_burst"], "traffic": None,
+                                  "us": t * 1e6, "note": "fp32 FMA-pipe kernel (parity path) against the bf16 tensor peak"}
+    return out
+
+
+def run_ours(args):
+    from mac_network_b200 import _lib
+    from mac_network_b200.mac_cell import MACParams
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = _lib.load()
+    shape = SHAPES[WORKLOAD]
+    B, S, N, d, L = shape
+    cfg = MACConfig.args("args", netLength=L)
+    pv = perturb_biases(init_params(cfg, L, seed=100), seed=101)
+    params = MACParams(cfg, L, values=pv)
+    pk = peaks()
+    use_graph = not args.no_graph
+
+    # ---- resident-input arm
+    slots = [Slot(cfg, params, shape, 1234 + 1000 * rank + s, args.prec, use_graph) for s in range(NSLOTS)]
+    launches_per_pass = slots[0].launches
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for w in range(args.warmup):
+        slots[w % NSLOTS].run()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(args.steps):
+        slots[k % NSLOTS].run()
+    e1.record()
+    barrier()
+    t_dev = e0.elapsed_time(e1) * 1e-3
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end-to-end arm: host (pinned) buffers, H2D + compute + D2H per pass, double-buffered
+    host = []
+    for s in range(4):
+        inp = make_inputs(B, S, N, d, seed=777 + 1000 * rank + s)
+        host.append({k: torch.from_numpy(v).pin_memory() for k, v in inp.items()})
+    dev = [Slot(cfg, params, shape, 0, args.prec, use_graph, host_inputs={k: v.numpy() for k, v in host[0].items()})
+           for _ in range(2)]
+    outs_host = [[torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in dv.outputs()] for dv in dev]
+    h2d_bytes = sum(v.numel() * v.element_size() for k, v in host[0].items() if k != "questionWords")
+    d2h_bytes = sum(t.numel() * t.element_size() for t in outs_host[0])
+    copy_stream = torch.cuda.Stream()
+    main = torch.cuda.current_stream()
+    ev_in = [torch.cuda.Event() for _ in range(2)]
+    ev_done = [torch.cuda.Event() for _ in range(2)]
+
+    def e2e_pass(k):
+        sl = k % 2
+        hb = host[k % len(host)]
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(ev_done[sl])            # slot's previous compute + D2H finished
+            for key, t in dev[sl].x.items():
+                if key != "questionWords":                 # unused when controlContextual (mac_cell.py:570)
+                    t.copy_(hb[key], non_blocking=True)
+            ev_in[sl].record(copy_stream)
+        main.wait_event(ev_in[sl])
+        dev[sl].run()
+        for src, dst in zip(dev[sl].outputs(), outs_host[sl]):
+            dst.copy_(src, non_blocking=True)
+        ev_done[sl].record(main)
+
+    for sl in range(2):
+        ev_done[sl].record(main)
+    for k in range(max(args.warmup, 2)):
+        e2e_pass(k)
+    barrier()
+    e0.record()
+    for k in range(args.steps):
+        e2e_pass(k)
+    e1.record()
+    barrier()
+    t_e2e = e0.elapsed_time(e1) * 1e-3
+
+    # ---- max over ranks
+    if dist is not None:
+        tt = torch.tensor([t_dev, t_e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_dev, t_e2e = float(tt[0]), float(tt[1])
+
+    if rank == 0:
+        roofs = kernel_rooflines(shape, args.prec, pk)
+        cpu, _ = cpu_reference(cfg, shape, pv) if not args.skip_cpu else ({"value": None, "unit": UNIT, "cores": 0,
+                                                                           "kind": "port", "sample": "skipped"}, 0)
+        value = args.steps * L * world / t_dev
+        dom = "memKbProj_gemm_fp32" if args.prec == "fp32" else "read_chain_tc"
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.prec == "fp32" else "bf16",
+            "data": "synthetic",
+            "config": {"workload": "BASELINE.json configs[2]: args.txt cell, B=%d/GPU, S=%d, KB=14x14 (N=%d), d=%d, "
+                                   "netLength=%d, inference (dropouts=1.0)" % (B, S, N, d, L),
+                       "step": "one netLength-step unroll over one batch (%d reasoning steps)" % L,
+                       "l2": "timed passes rotate over %d resident batches (%.0f MB > 126 MB L2)"
+                             % (NSLOTS, NSLOTS * (B * N * d + B * S * d) * 4 / 1e6),
+                       "cuda_graph": use_graph, "projections": args.prec, "parallelism": "dp%d (replicas, no "
+                       "data-path collective in inference)" % world},
+            "sample_steps_per_sec": value * B,
+            "e2e": {"value": args.steps * L * world / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+                    "d2h_bytes_per_step": d2h_bytes, "ms_per_step": t_e2e / args.steps * 1e3},
+            "gpu_launches": int(launches_per_pass) * args.steps,
+            "clocks": clocks,
+            "roofline": roofs.get(dom, roofs["memKbProj_gemm_fp32"]),
+            "roofline_kb_attend": roofs["kb_attend_bf16_kb" if args.prec == "bf16" else "kb_attend_fp32_kb"],
+            "rooflines_all": roofs,
+            "peaks": pk,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    shape = SHAPES[WORKLOAD]
+    B, S, N, d, L = shape
+    cfg = MACConfig.args("args", netLength=L)
+    pv = perturb_biases(init_params(cfg, L, seed=100), seed=101)
+    from oracle.mac_torch_cpu import TorchCPUCell
+    torch.set_num_threads(os.cpu_count() or 1)
+    inp = make_inputs(B, S, N, d, seed=1234)
+    cell = TorchCPUCell(cfg, pv, L)
+    a = (torch.from_numpy(inp["vecQuestions"]), torch.from_numpy(inp["questionCntxWords"]),
+         torch.from_numpy(inp["questionLengths"]).long(), torch.from_numpy(inp["knowledgeBase"]))
+    steps = min(args.steps, 8)
+    warm = min(args.warmup, 2)
+    for _ in range(warm):
+        cell.forward(*a)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cell.forward(*a)
+    dt = time.perf_counter() - t0
+    v = steps * L / dt
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+            "steps": steps, "warmup": warm, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "BASELINE.json configs[2]: args.txt cell, B=%d, S=%d, N=%d, d=%d, netLength=%d, "
+                                   "inference" % (B, S, N, d, L),
+                       "note": "TensorFlow-1 is not installable offline: this is the oracle's fp32 PyTorch-CPU port at "
+                               "TF-op granularity on all host threads (rank 0 only); steps capped at 8"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": "%d full forward passes, %.3f s each" % (steps, dt / steps)},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--prec", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -57,6 +57,8 @@ int mac_b200_abi_version(void);
 const char* mac_b200_strerror(int status);
 /* 1 if the current device is compute capability 10.x (tcgen05/TMEM/TMA available) */
 int mac_b200_device_ok(void);
+/* number of kernels this library has launched (or recorded into a stream capture) in this process */
+long long mac_b200_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * ops.linear (ops.py:298-333) / ops.multiply (ops.py:50-59)

@@ -34,6 +34,7 @@ PROTOTYPES = {
     "mac_b200_abi_version": (c_int, []),
     "mac_b200_strerror": (ctypes.c_char_p, [c_int]),
     "mac_b200_device_ok": (c_int, []),
+    "mac_b200_launch_count": (c_ll, []),
     "mac_linear_fwd": (c_int, [ctypes.POINTER(c_fp), ctypes.POINTER(c_int), ctypes.POINTER(c_int), c_int, c_fp, c_fp,
                                c_f, c_int, c_fp, c_int, c_int, c_int, c_fp, c_sz, c_fp]),
     "mac_linear_workspace_bytes": (c_sz, [c_int, c_int, c_int]),

@@ -10,8 +10,11 @@
     cudaError_t _e = (expr);                        \
     if (_e != cudaSuccess) return (int)_e;          \
   } while (0)
+// every kernel launch of the library goes through this: counts it (mac_b200_launch_count) and surfaces launch errors
+extern "C" void mac_b200_count_launch_(void);
 #define MAC_LAUNCH_CHECK()                          \
   do {                                              \
+    mac_b200_count_launch_();                       \
     cudaError_t _e = cudaGetLastError();            \
     if (_e != cudaSuccess) return (int)_e;          \
   } while (0)

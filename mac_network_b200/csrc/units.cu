@@ -53,6 +53,10 @@ __global__ void cast_bf16_kernel(const float4* __restrict__ x, uint2* __restrict
 }  // namespace mac
 
 // ------------------------------------------------------------------------------------------------ misc
+#include <atomic>
+static std::atomic<long long> g_launches{0};
+extern "C" void mac_b200_count_launch_(void) { g_launches.fetch_add(1, std::memory_order_relaxed); }
+extern "C" long long mac_b200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 extern "C" int mac_b200_abi_version(void) { return MAC_B200_ABI_VERSION; }
 
 extern "C" const char* mac_b200_strerror(int status) {

@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _declared():
     src = open(os.path.join(ROOT, "include", "mac_b200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return set(re.findall(r"\b(mac_[a-z0-9_]+)\s*\(", src))
+    return set(re.findall(r"\b(mac_[a-z0-9_]+)\s*\(", src)) - {"mac_b200_count_launch_"}
 
 
 def test_header_and_binding_agree():

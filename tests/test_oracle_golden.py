@@ -54,3 +54,25 @@ def test_attention_properties():
     assert np.allclose(gold["att_kb"].sum(-1), 1.0, atol=1e-12)
     g = load_golden("args4_small")[1]["att_gate"]
     assert np.all((g > 0) & (g < 1))
+
+
+@pytest.mark.parametrize("variant", ["args", "gqa"])
+def test_torch_cpu_port_matches_oracle(variant):
+    """The timed CPU baseline (oracle/mac_torch_cpu.py, fp32) against the fp64 numpy oracle."""
+    import torch
+    from oracle.mac_torch_cpu import TorchCPUCell
+    from mac_network_b200.config import MACConfig
+    from mac_network_b200.params import init_params, perturb_biases
+    from mac_network_b200.synthetic import make_inputs
+    B, S, N, d, L = 4, 7, 12, 64, 3
+    cfg = MACConfig.args(variant, netLength=L, memDim=d, ctrlDim=d, attDim=d)
+    inp = make_inputs(B, S, N, d, seed=1, dtype=np.float64)
+    params = perturb_biases(init_params(cfg, L, seed=2, dtype=np.float64), seed=3)
+    ref = MACOracle(cfg, params).run(L, inp["vecQuestions"], inp["questionWords"], inp["questionCntxWords"],
+                                     inp["questionLengths"], inp["knowledgeBase"])
+    cell = TorchCPUCell(cfg, params, L)
+    c, m, _ = cell.forward(torch.from_numpy(inp["vecQuestions"]).float(),
+                           torch.from_numpy(inp["questionCntxWords"]).float(),
+                           torch.from_numpy(inp["questionLengths"]).long(), torch.from_numpy(inp["knowledgeBase"]).float())
+    assert np.max(np.abs(c.numpy() - ref.control)) / np.max(np.abs(ref.control)) < 1e-5
+    assert np.max(np.abs(m.numpy() - ref.memory)) / np.max(np.abs(ref.memory)) < 1e-5
