@@ -6,6 +6,7 @@
 // Both stage their operand through the TMA engine (cp.async.bulk -> shared memory, mbarrier
 // completion), reduce with warp shuffles, and read every HBM byte exactly once.
 #include "common.cuh"
+#include "tmap.cuh"
 
 namespace mac {
 
@@ -133,40 +134,42 @@ constexpr int K3_THREADS = 256;
 
 template <typename KT, int DS>
 __global__ void __launch_bounds__(K3_THREADS) kb_attend_kernel(
-    const float* __restrict__ logit_parts, int nparts, float br, const KT* __restrict__ kb,
-    float* __restrict__ att, float* __restrict__ info, int B, int N, int d, int rows_per_stage, int nstages, int nbuf) {
+    const float* __restrict__ logit_parts, int nparts, float br, const __grid_constant__ CUtensorMap kb_map,
+    float* __restrict__ att, float* __restrict__ info, int B, int N, int d, int rows_per_stage, int nstages, int nbuf, int buf_elems) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   KT* s_kb = reinterpret_cast<KT*>(smem_raw);                                    // [nstages_resident][rows][DS]
-  float* s_att = reinterpret_cast<float*>(smem_raw + (size_t)nbuf * rows_per_stage * DS * sizeof(KT));  // [N]
+  float* s_att = reinterpret_cast<float*>(smem_raw + (size_t)nbuf * buf_elems * sizeof(KT));  // [N]
   float* s_acc = s_att + ((N + 3) & ~3);                                         // [K3_THREADS / DS groups][DS]
-  __shared__ __align__(8) uint64_t bar[2];
+  constexpr int MAXBUF = 8;
+  __shared__ __align__(8) uint64_t bar[MAXBUF];
   __shared__ float s_red[K3_THREADS / 32];
 
   const int slice = blockIdx.x, b = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NW = K3_THREADS / 32;
   constexpr int GROUPS = K3_THREADS / DS;       // row groups working on the same columns
-  const KT* src = kb + ((size_t)b * N) * d + (size_t)slice * DS;
   constexpr uint32_t ROW_BYTES = DS * sizeof(KT);
 
   if (tid == 0) {
-    mbar_init(&bar[0], 1);
-    mbar_init(&bar[1], 1);
+#pragma unroll
+    for (int i = 0; i < MAXBUF; ++i) mbar_init(&bar[i], 1);
     fence_mbar_init();
   }
   __syncthreads();
-  // producer: warp 0 issues the row copies of a stage (each row slice is ROW_BYTES contiguous)
+  // producer: ONE tiled TMA request per stage -- box [rows_per_stage x DS] of the [B*N, d] knowledge base at
+  // (row b*N + r0, column slice*DS).  A box that runs past this batch row's N rows just brings rows nobody reads
+  // (out-of-range rows at the very end are zero-filled); the transaction count is always the full box.
   auto issue = [&](int stage) {
-    const int r0 = stage * rows_per_stage;
-    const int nr = min(rows_per_stage, N - r0);
-    KT* dst = s_kb + (size_t)(stage & 1) * rows_per_stage * DS;
-    if (lane == 0) mbar_expect_tx(&bar[stage & 1], (uint32_t)nr * ROW_BYTES);
-    __syncwarp();
-    for (int r = lane; r < nr; r += 32) bulk_g2s(dst + (size_t)r * DS, src + (size_t)(r0 + r) * d, ROW_BYTES, &bar[stage & 1]);
+    if (lane == 0) {
+      const int buf = stage % nbuf;
+      KT* dst = s_kb + (size_t)buf * buf_elems;        // 128-byte aligned (TMA destination)
+      mbar_expect_tx(&bar[buf], (uint32_t)rows_per_stage * ROW_BYTES);
+      tma_load_2d(dst, &kb_map, slice * DS, b * N + stage * rows_per_stage, &bar[buf]);
+    }
   };
   if (warp == 0) {
-    issue(0);
-    if (nstages > 1) issue(1);
+    // every resident buffer is requested up-front: all of this CTA's bytes are in flight before the softmax starts
+    for (int s = 0; s < nstages && s < nbuf; ++s) issue(s);
   }
 
   // softmax over the N logits of this batch row while the KB slab is in flight
@@ -209,15 +212,15 @@ __global__ void __launch_bounds__(K3_THREADS) kb_attend_kernel(
   const int c = tid % DS, g = tid / DS;
   float acc = 0.f;
   for (int stage = 0; stage < nstages; ++stage) {
-    mbar_wait(&bar[stage & 1], (stage >> 1) & 1);
-    const KT* buf = s_kb + (size_t)(stage & 1) * rows_per_stage * DS;
+    mbar_wait(&bar[stage % nbuf], (stage / nbuf) & 1);
+    const KT* buf = s_kb + (size_t)(stage % nbuf) * buf_elems;
     const int r0 = stage * rows_per_stage;
     const int nr = min(rows_per_stage, N - r0);
 #pragma unroll 4
     for (int r = g; r < nr; r += GROUPS) acc = fmaf(s_att[r0 + r], (float)buf[(size_t)r * DS + c], acc);
-    if (stage + 2 < nstages) {          // refill this buffer (only taken when N exceeds two stages)
+    if (stage + nbuf < nstages) {       // refill this buffer (only when the slab does not fit the resident buffers)
       __syncthreads();
-      if (warp == 0) issue(stage + 2);
+      if (warp == 0) issue(stage + nbuf);
     }
   }
   s_acc[g * DS + c] = acc;
@@ -233,22 +236,33 @@ __global__ void __launch_bounds__(K3_THREADS) kb_attend_kernel(
 template <typename KT, int DS>
 static int launch_kb_attend(const float* logit_parts, int nparts, float br, const KT* kb, float* att, float* info,
                             int B, int N, int d, cudaStream_t stream) {
-  // stage sizing: whole slab resident when it fits (<= ~100 KB so two CTAs share an SM), else 2-stage ring
+  // stage sizing: the [N x DS] slab is cut into <= 8 boxes that are all requested up-front and consumed as they
+  // land (the weighted sum of box i overlaps the flight of boxes i+1..); when the slab exceeds ~100 KB (two CTAs
+  // per SM) the boxes are recycled as a ring
   const size_t row_bytes = (size_t)DS * sizeof(KT);
-  int rows_per_stage = N;
-  int nstages = 1;
-  const size_t budget = 96 * 1024;
-  if ((size_t)N * row_bytes > budget) {
-    rows_per_stage = (int)(budget / 2 / row_bytes);
+  const size_t budget = 100 * 1024;
+  int nstages = N >= 64 ? 4 : 1;
+  int rows_per_stage = (N + nstages - 1) / nstages;
+  int nbuf = nstages;
+  if (rows_per_stage > 256 || (size_t)rows_per_stage * nstages * row_bytes > budget) {
+    nbuf = 4;
+    rows_per_stage = (int)(budget / nbuf / row_bytes);
+    if (rows_per_stage > 256) rows_per_stage = 256;
     nstages = (N + rows_per_stage - 1) / rows_per_stage;
+    if (nstages < nbuf) nbuf = nstages;
   }
-  const int nbuf = nstages > 1 ? 2 : 1;
-  const size_t smem = (size_t)nbuf * rows_per_stage * row_bytes + (size_t)((N + 3) & ~3) * sizeof(float) +
+  CUtensorMap map;
+  int st = make_tmap_2d(&map, kb, sizeof(KT) == 4 ? 0 : 1, (uint64_t)B * N, (uint64_t)d, (uint64_t)d * sizeof(KT),
+                        (uint32_t)rows_per_stage, (uint32_t)DS, 0);
+  if (st != MAC_OK) return st;
+  const size_t buf_bytes = ((size_t)rows_per_stage * row_bytes + 127) & ~(size_t)127;
+  const size_t smem = (size_t)nbuf * buf_bytes + (size_t)((N + 3) & ~3) * sizeof(float) +
                       (size_t)K3_THREADS * sizeof(float) + 16;
   auto kern = kb_attend_kernel<KT, DS>;
   MAC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(d / DS, B);
-  kern<<<grid, K3_THREADS, smem, stream>>>(logit_parts, nparts, br, kb, att, info, B, N, d, rows_per_stage, nstages, nbuf);
+  kern<<<grid, K3_THREADS, smem, stream>>>(logit_parts, nparts, br, map, att, info, B, N, d, rows_per_stage, nstages, nbuf,
+                                           (int)(buf_bytes / sizeof(KT)));
   MAC_LAUNCH_CHECK();
   return MAC_OK;
 }
