@@ -113,7 +113,7 @@ typedef struct mac_read_weights {
   const float* Wm;  const float* bm;   /* read/linearLayermemKbProj                    [2d,d],[d] */
   const float* Wm2; const float* bm2;  /* read/linearLayermemKbProj/linearLayermemKbProj_2 [d,d],[d] */
   const float* wr;  float br;          /* read/inter2att/inter2logits/linearLayerlogits [d], []   */
-  /* bf16 copies of Wx, Wm, Wm2 in the tcgen05 operand layout (mac_pack_weight_bf16); NULL for MAC_PREC_FP32 */
+  /* bf16 [out,in] copies of Wx, Wm, Wm2 (mac_pack_weight_bf16); NULL for MAC_PREC_FP32 */
   const void* Wx_bf16; const void* Wm_bf16; const void* Wm2_bf16;
 } mac_read_weights;
 
@@ -156,6 +156,17 @@ int mac_dropout_fwd(const float* x, float keep, uint64_t seed, int site, int ste
 int mac_dropout_uniform(uint64_t seed, int site, int step, float* u, long long n, mac_stream_t stream);
 /* fp32 -> bf16 (round-to-nearest-even), plain row-major; used once per forward for KB and per weight update */
 int mac_cast_bf16(const float* x, void* out_bf16, long long n, mac_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Tensor-core (MAC_PREC_BF16) helpers.
+ * mac_pack_weight_bf16: fp32 W[K, n_out] (the reference's [in, out] layout, ops.py:304) -> bf16 Wt[n_out, K], the
+ *   K-major B operand tcgen05.mma consumes; call once per weight update.
+ * mac_linear_tc_fwd: y[M,n_out] = act(x[M,K] @ W + b) with x bf16 row-major and W given as the packed Wt;
+ *   fp32 accumulation in TMEM, fp32 output.  Requires K % 64 == 0 and n_out % 256 == 0.
+ * --------------------------------------------------------------------------------------------- */
+int mac_pack_weight_bf16(const float* W, void* Wt_bf16, int K, int n_out, mac_stream_t stream);
+int mac_linear_tc_fwd(const void* x_bf16, const void* wt_bf16, const float* b, int act, float* y,
+                      int M, int K, int n_out, mac_stream_t stream);
 
 /* dropout sites (the `site` word of the Philox counter) */
 enum { MAC_SITE_MEM_VAR = 0, MAC_SITE_READ_KB = 1, MAC_SITE_READ_MEM = 2, MAC_SITE_READ_INTER = 3,

@@ -52,6 +52,8 @@ PROTOTYPES = {
     "mac_dropout_fwd": (c_int, [c_fp, c_f, c_u64, c_int, c_int, c_fp, c_ll, c_fp]),
     "mac_dropout_uniform": (c_int, [c_u64, c_int, c_int, c_fp, c_ll, c_fp]),
     "mac_cast_bf16": (c_int, [c_fp, c_fp, c_ll, c_fp]),
+    "mac_pack_weight_bf16": (c_int, [c_fp, c_fp, c_int, c_int, c_fp]),
+    "mac_linear_tc_fwd": (c_int, [c_fp, c_fp, c_fp, c_int, c_fp, c_int, c_int, c_int, c_fp]),
 }
 
 _lib = None

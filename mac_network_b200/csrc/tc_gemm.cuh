@@ -1,10 +1,432 @@
-// bf16 tcgen05/TMEM read-unit chain (MAC_PREC_BF16).  Placeholder until the tensor-core path lands.
+// bf16 tensor-core GEMM for sm_100a: tcgen05.mma (UMMA 128 x BN x 16, cta_group::1) with fp32 accumulators in
+// TMEM, operands staged by TMA (cp.async.bulk.tensor, 128-byte swizzle) through a 4-stage mbarrier ring, and the
+// read unit's elementwise work fused into the TMEM->register epilogue.
+//
+//   C[M,N] = epilogue( A[M,K] @ Wt[N,K]^T )      A, Wt bf16 row-major with K contiguous ("K-major" both)
+//
+// Warp roles (192 threads, persistent over output tiles, one CTA per SM):
+//   warp 0      TMA producer          (one elected lane issues the A and B boxes of each k-block)
+//   warp 1      TMEM allocator + MMA issuer (one elected lane issues tcgen05.mma / tcgen05.commit)
+//   warps 2..5  epilogue              (tcgen05.ld 32 lanes x 32 columns per instruction; thread == output row)
+// Two accumulator buffers (2 x BN TMEM columns) let the epilogue of tile i overlap the MMAs of tile i+1.
+//
+// Epilogues (the read-unit chain of mac_cell.py:230-266 / ops.py:668-725, see mac_b200.h):
+//   TC_EPI_P       P = acc + bx            -> bf16 P and bf16 P*y[b]            (ops.py:688, 694-703)
+//   TC_EPI_ACT     act(acc + b)            -> bf16                               (mac_cell.py:236-238)
+//   TC_EPI_LOGITS  I1 = acc + bm2; t = ELU(I1 * control[b]); (dropout); parts[m, ntile] = sum_n t * wr[n]
+//                                                                                (ops.py:325-328, mac_cell.py:248-266)
+//   TC_EPI_F32     act(acc + b)            -> fp32                               (generic ops.linear)
 #pragma once
 #include "common.cuh"
+#include "tmap.cuh"
+
 namespace mac {
-inline size_t tc_read_extra_workspace_bytes(int, int, int) { return 0; }
-inline int tc_read_chain(const void*, const float*, const float*, const mac_read_weights*, uint32_t, float, uint64_t,
-                         int, float*, float*, float*, float*, int*, void*, size_t, int, int, int, bool, cudaStream_t) {
-  return MAC_ERR_UNSUPPORTED;
+
+enum { TC_EPI_P = 0, TC_EPI_ACT = 1, TC_EPI_LOGITS = 2, TC_EPI_F32 = 3 };
+
+struct TcGemmParams {
+  int M, N, K;
+  int kblocks0;            // k-blocks (of 64) served by tensor map a0; the rest come from a1 (concat along K)
+  int epi, act;
+  const float* bias;       // [N] or NULL
+  __nv_bfloat16* out0;     // bf16 output 0 (P / act / I1-save), may be NULL for TC_EPI_LOGITS
+  __nv_bfloat16* out1;     // bf16 output 1 (P*y)
+  float* outf;             // fp32 output (TC_EPI_F32)
+  int ldo;
+  const float* y;          // [B, N] row scale for TC_EPI_P
+  const float* ctrl;       // [B, N] for TC_EPI_LOGITS
+  const float* wr;         // [N]
+  float* parts;            // [M, gridN]
+  int rows_per_batch;
+  uint32_t e_thresh;       // dropout on the logits' input (0 = none)
+  float e_scale;
+  uint64_t seed;
+  int e_site, step;
+};
+
+// ------------------------------------------------------------------ tcgen05 PTX wrappers
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]; single-thread issue
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// mbarrier arrive when all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor) for a K-major tile stored as rows of 128 bytes with
+// the 128-byte swizzle (what TMA SWIZZLE_128B writes for a [rows x 64 bf16] box):
+//   start address >> 4 | LBO (ignored for swizzled K-major; 1) | SBO = 1024 B between 8-row groups | version 1 |
+//   layout type 2 (SWIZZLE_128B).  The tile base must be 1024-byte aligned (base_offset 0).
+__device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);   // bits [0,14)
+  d |= (uint64_t)1 << 16;                        // leading byte offset (16-B units), bits [16,30)
+  d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset, bits [32,46)
+  d |= (uint64_t)1 << 46;                        // version = 1 (Blackwell), bits [46,48)
+  d |= (uint64_t)2 << 61;                        // layout type SWIZZLE_128B, bits [61,64)
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B bf16, both K-major, dense, M x N
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;                 // 64 bf16 = 128 B = one swizzle atom row
+constexpr int TC_THREADS = 192;
+
+template <int BN>
+struct TcCfg {
+  static constexpr int STAGES = BN == 256 ? 4 : 6;
+  static constexpr int A_BYTES = TC_BM * TC_BK * 2;        // 16 KB
+  static constexpr int B_BYTES = BN * TC_BK * 2;           // 32 KB (BN = 256)
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int TMEM_COLS = 2 * BN;                 // two accumulator buffers; power of two >= 32
+};
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
+               const __grid_constant__ CUtensorMap map_b, const TcGemmParams p) {
+  using C = TcCfg<BN>;
+  extern __shared__ unsigned char smem_dyn[];
+  // 1024-byte aligned operand ring
+  const uint32_t base_u32 = smem_u32(smem_dyn);
+  const uint32_t pad = (1024u - (base_u32 & 1023u)) & 1023u;
+  unsigned char* tiles = smem_dyn + pad;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + C::STAGES * C::STAGE_BYTES);
+  uint64_t* full = bars;                       // [STAGES]  TMA -> MMA
+  uint64_t* empty = bars + C::STAGES;          // [STAGES]  MMA -> TMA
+  uint64_t* tfull = bars + 2 * C::STAGES;      // [2]       MMA -> epilogue
+  uint64_t* tempty = tfull + 2;                // [2]       epilogue -> MMA
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tiles = (p.M + TC_BM - 1) / TC_BM;
+  const int n_tiles = p.N / BN;
+  const int num_tiles = m_tiles * n_tiles;
+  const int kblocks = p.K / TC_BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a0);
+    tma_prefetch_desc(&map_a1);
+    tma_prefetch_desc(&map_b);
+#pragma unroll
+    for (int i = 0; i < C::STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(&tfull[0], 1);
+    mbar_init(&tfull[1], 1);
+    mbar_init(&tempty[0], 4);
+    mbar_init(&tempty[1], 4);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, C::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int mt = t / n_tiles, nt = t % n_tiles;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          unsigned char* sa = tiles + stage * C::STAGE_BYTES;
+          unsigned char* sb = sa + C::A_BYTES;
+          mbar_expect_tx(&full[stage], C::STAGE_BYTES);
+          if (kb < p.kblocks0)
+            tma_load_2d(sa, &map_a0, kb * TC_BK, mt * TC_BM, &full[stage]);
+          else
+            tma_load_2d(sa, &map_a1, (kb - p.kblocks0) * TC_BK, mt * TC_BM, &full[stage]);
+          tma_load_2d(sb, &map_b, kb * TC_BK, nt * BN, &full[stage]);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    constexpr uint32_t idesc = make_idesc_bf16(TC_BM, BN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tempty[acc], acc_phase ^ 1);        // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * BN;
+      for (int kb = 0; kb < kblocks; ++kb) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = smem_u32(tiles + stage * C::STAGE_BYTES);
+          const uint64_t adesc = make_sw128_kmajor_desc(sa);
+          const uint64_t bdesc = make_sw128_kmajor_desc(sa + C::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle atom: +2 in the 16-B address field
+            umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);                // frees the smem slot when these MMAs retire
+          if (kb == kblocks - 1) umma_commit(&tfull[acc]);
+        }
+        __syncwarp();
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================================================== epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1)
+    const int q = warp & 3;
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int mt = t / n_tiles, nt = t % n_tiles;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const int row = mt * TC_BM + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      const int bidx = row_ok ? row / p.rows_per_batch : 0;
+      const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
+      float part = 0.f;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(taddr + c0, r);
+        tmem_ld_wait();
+        const int n0 = nt * BN + c0;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + n0 + j) : 0.f);
+        if (p.epi == TC_EPI_P) {
+          if (row_ok) {
+            const float* yb = p.y + (size_t)bidx * p.N + n0;
+            uint4* o0 = reinterpret_cast<uint4*>(p.out0 + (size_t)row * p.ldo + n0);
+            uint4* o1 = reinterpret_cast<uint4*>(p.out1 + (size_t)row * p.ldo + n0);
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint32_t a[4], b[4];
+#pragma unroll
+              for (int h = 0; h < 4; ++h) {
+                const float x0 = v[j + 2 * h], x1 = v[j + 2 * h + 1];
+                __nv_bfloat162 t0 = __floats2bfloat162_rn(x0, x1);
+                __nv_bfloat162 t1 = __floats2bfloat162_rn(x0 * __ldg(yb + j + 2 * h), x1 * __ldg(yb + j + 2 * h + 1));
+                a[h] = *reinterpret_cast<uint32_t*>(&t0);
+                b[h] = *reinterpret_cast<uint32_t*>(&t1);
+              }
+              o0[j / 8] = make_uint4(a[0], a[1], a[2], a[3]);
+              o1[j / 8] = make_uint4(b[0], b[1], b[2], b[3]);
+            }
+          }
+        } else if (p.epi == TC_EPI_ACT) {
+          if (row_ok) {
+            uint4* o0 = reinterpret_cast<uint4*>(p.out0 + (size_t)row * p.ldo + n0);
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint32_t a[4];
+#pragma unroll
+              for (int h = 0; h < 4; ++h) {
+                __nv_bfloat162 t0 = __floats2bfloat162_rn(apply_act(p.act, v[j + 2 * h]), apply_act(p.act, v[j + 2 * h + 1]));
+                a[h] = *reinterpret_cast<uint32_t*>(&t0);
+              }
+              o0[j / 8] = make_uint4(a[0], a[1], a[2], a[3]);
+            }
+          }
+        } else if (p.epi == TC_EPI_F32) {
+          if (row_ok) {
+            float4* o = reinterpret_cast<float4*>(p.outf + (size_t)row * p.ldo + n0);
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              o[j / 4] = make_float4(apply_act(p.act, v[j]), apply_act(p.act, v[j + 1]), apply_act(p.act, v[j + 2]),
+                                     apply_act(p.act, v[j + 3]));
+          }
+        } else {  // TC_EPI_LOGITS
+          if (row_ok) {
+            if (p.out0) {
+              uint4* o0 = reinterpret_cast<uint4*>(p.out0 + (size_t)row * p.ldo + n0);
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                uint32_t a[4];
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                  __nv_bfloat162 t0 = __floats2bfloat162_rn(v[j + 2 * h], v[j + 2 * h + 1]);
+                  a[h] = *reinterpret_cast<uint32_t*>(&t0);
+                }
+                o0[j / 8] = make_uint4(a[0], a[1], a[2], a[3]);
+              }
+            }
+            const float* cb = p.ctrl + (size_t)bidx * p.N + n0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              uint32_t bits[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+              if (p.e_thresh) {
+                const uint64_t e = (uint64_t)row * (uint64_t)p.N + (uint64_t)(n0 + j);
+                const Philox4 rr = philox4x32_10(p.seed, e >> 2, (uint32_t)p.e_site, (uint32_t)p.step);
+                bits[0] = rr.x; bits[1] = rr.y; bits[2] = rr.z; bits[3] = rr.w;
+              }
+#pragma unroll
+              for (int h = 0; h < 4; ++h) {
+                float tt = elu_f(v[j + h] * __ldg(cb + j + h));
+                tt = ((bits[h] >> 8) >= p.e_thresh) ? tt * p.e_scale : 0.f;
+                part = fmaf(tt, __ldg(p.wr + n0 + j + h), part);
+              }
+            }
+          }
+        }
+      }
+      if (p.epi == TC_EPI_LOGITS && row_ok) p.parts[(size_t)row * n_tiles + nt] = part;
+      // release the accumulator buffer to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+    }
+  }
+
+  // ---- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+inline int tc_num_sms() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return sms;
+}
+
+// A = [a0 (K0 cols) | a1 (K1 cols)] bf16 row-major (ld = own K), Wt bf16 [N, K0+K1]
+inline int tc_gemm_launch(const void* a0, int K0, const void* a1, int K1, const void* wt, TcGemmParams p,
+                          cudaStream_t stream) {
+  constexpr int BN = 256;
+  if (p.M <= 0 || p.N <= 0 || (p.N % BN) || (K0 % TC_BK) || (K1 % TC_BK) || K0 <= 0) return MAC_ERR_UNSUPPORTED;
+  if (!mac_aligned16(a0) || !mac_aligned16(wt)) return MAC_ERR_ALIGN;
+  p.K = K0 + K1;
+  p.kblocks0 = K0 / TC_BK;
+  CUtensorMap ma0, ma1, mb;
+  int st = make_tmap_2d(&ma0, a0, 1, (uint64_t)p.M, (uint64_t)K0, (uint64_t)K0 * 2, TC_BM, TC_BK, 1);
+  if (st != MAC_OK) return st;
+  if (K1 > 0) {
+    st = make_tmap_2d(&ma1, a1, 1, (uint64_t)p.M, (uint64_t)K1, (uint64_t)K1 * 2, TC_BM, TC_BK, 1);
+    if (st != MAC_OK) return st;
+  } else {
+    ma1 = ma0;
+  }
+  st = make_tmap_2d(&mb, wt, 1, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)p.K * 2, BN, TC_BK, 1);
+  if (st != MAC_OK) return st;
+  auto kern = tc_gemm_kernel<BN>;
+  MAC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM_BYTES));
+  const int tiles = ((p.M + TC_BM - 1) / TC_BM) * (p.N / BN);
+  const int grid = tiles < tc_num_sms() ? tiles : tc_num_sms();
+  kern<<<grid, TC_THREADS, TcCfg<BN>::SMEM_BYTES, stream>>>(ma0, ma1, mb, p);
+  MAC_LAUNCH_CHECK();
+  return MAC_OK;
+}
+
+// fp32 [K, N] (in, out) weight -> bf16 [N, K] (out, in): the K-major B operand of the forward GEMMs
+__global__ void pack_weight_bf16_kernel(const float* __restrict__ W, __nv_bfloat16* __restrict__ Wt, int K, int N) {
+  __shared__ float tile[32][33];
+  const int k0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int k = k0 + i, n = n0 + threadIdx.x;
+    tile[i][threadIdx.x] = (k < K && n < N) ? W[(size_t)k * N + n] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int n = n0 + i, k = k0 + threadIdx.x;
+    if (n < N && k < K) Wt[(size_t)n * K + k] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+  }
+}
+
+// extra workspace of the bf16 read chain: P, P*y, H (+ I1 when saving for backward), each [B*N, d] bf16
+inline size_t tc_read_extra_workspace_bytes(int B, int N, int d) {
+  return (size_t)4 * (((size_t)B * N * d * 2 + 1023) & ~(size_t)1023) + 1024;
+}
+
+// The read unit's three projections on tensor cores (see mac_read_fwd in mac_b200.h).
+inline int tc_read_chain(const void* kb_bf16, const float* y, const float* control, const mac_read_weights* w,
+                         uint32_t thr, float scale, uint64_t seed, int step, float* /*P_f32*/, float* /*H_f32*/,
+                         float* /*I1_f32*/, float* parts, int* nparts, void* ws, size_t ws_bytes, int B, int N, int d,
+                         bool save, cudaStream_t stream) {
+  if (!kb_bf16 || !w->Wx_bf16 || !w->Wm_bf16 || !w->Wm2_bf16) return MAC_ERR_INVALID;
+  if (d % 256) return MAC_ERR_UNSUPPORTED;
+  if (thr != 0) return MAC_ERR_UNSUPPORTED;      // training-mode dropout on the tensor-core path: not yet
+  if (ws_bytes < tc_read_extra_workspace_bytes(B, N, d)) return MAC_ERR_WORKSPACE;
+  const int M = B * N;
+  const size_t slab = (((size_t)M * d * 2 + 1023) & ~(size_t)1023);
+  char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~(uintptr_t)1023);
+  __nv_bfloat16* P = reinterpret_cast<__nv_bfloat16*>(base);
+  __nv_bfloat16* PY = reinterpret_cast<__nv_bfloat16*>(base + slab);
+  __nv_bfloat16* H = reinterpret_cast<__nv_bfloat16*>(base + 2 * slab);
+  __nv_bfloat16* I1 = save ? reinterpret_cast<__nv_bfloat16*>(base + 3 * slab) : nullptr;
+  TcGemmParams p{};
+  p.M = M; p.N = d; p.rows_per_batch = N; p.ldo = d; p.seed = seed; p.step = step;
+  // P = KB @ Wx + bx ; also P*y
+  p.epi = TC_EPI_P; p.bias = w->bx; p.out0 = P; p.out1 = PY; p.y = y;
+  int st = tc_gemm_launch(kb_bf16, d, nullptr, 0, w->Wx_bf16, p, stream);
+  if (st != MAC_OK) return st;
+  // H = ELU([P*y, P] @ Wm + bm)
+  p.epi = TC_EPI_ACT; p.act = MAC_ACT_ELU; p.bias = w->bm; p.out0 = H; p.out1 = nullptr;
+  st = tc_gemm_launch(PY, d, P, d, w->Wm_bf16, p, stream);
+  if (st != MAC_OK) return st;
+  // logits parts = sum_n ELU((H @ Wm2 + bm2) * control) * wr
+  p.epi = TC_EPI_LOGITS; p.bias = w->bm2; p.out0 = I1; p.ctrl = control; p.wr = w->wr; p.parts = parts;
+  p.e_thresh = thr; p.e_scale = scale; p.e_site = MAC_SITE_READ_INTER;
+  st = tc_gemm_launch(H, d, nullptr, 0, w->Wm2_bf16, p, stream);
+  if (st != MAC_OK) return st;
+  *nparts = d / 256;
+  return MAC_OK;
+}
+
 }  // namespace mac

@@ -321,3 +321,23 @@ extern "C" int mac_cast_bf16(const float* x, void* out_bf16, long long n, mac_st
   MAC_LAUNCH_CHECK();
   return MAC_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ tensor-core helpers
+extern "C" int mac_pack_weight_bf16(const float* W, void* Wt_bf16, int K, int N, mac_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!W || !Wt_bf16 || K <= 0 || N <= 0) return MAC_ERR_INVALID;
+  dim3 grid((N + 31) / 32, (K + 31) / 32), block(32, 8);
+  pack_weight_bf16_kernel<<<grid, block, 0, stream>>>(W, reinterpret_cast<__nv_bfloat16*>(Wt_bf16), K, N);
+  MAC_LAUNCH_CHECK();
+  return MAC_OK;
+}
+
+extern "C" int mac_linear_tc_fwd(const void* x_bf16, const void* wt_bf16, const float* b, int act, float* y, int M,
+                                 int K, int n_out, mac_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!x_bf16 || !wt_bf16 || !y || M <= 0) return MAC_ERR_INVALID;
+  if (!mac_b200_device_ok()) return MAC_ERR_ARCH;
+  TcGemmParams p{};
+  p.M = M; p.N = n_out; p.epi = TC_EPI_F32; p.act = act; p.bias = b; p.outf = y; p.ldo = n_out; p.rows_per_batch = 1;
+  return tc_gemm_launch(x_bf16, K, nullptr, 0, wt_bf16, p, stream);
+}

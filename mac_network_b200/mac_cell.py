@@ -301,11 +301,11 @@ class MACCell(object):
                          Wm2.data_ptr(), bm2.data_ptr(), p[lsc + "weights/weight"].data_ptr(),
                          p.scalar(lsc + "biases/bias"), None, None, None)
         if self.prec == PREC["bf16"]:
-            def cast(t):
-                o = torch.empty(t.shape, dtype=torch.bfloat16, device=t.device)
-                check(self.lib.mac_cast_bf16(ptr(t), ptr(o), t.numel(), stream_ptr()), "mac_cast_bf16")
+            def pack(t):       # fp32 [in, out] -> bf16 [out, in] (K-major B operand of tcgen05.mma)
+                o = torch.empty((t.shape[1], t.shape[0]), dtype=torch.bfloat16, device=t.device)
+                check(self.lib.mac_pack_weight_bf16(ptr(t), ptr(o), t.shape[0], t.shape[1], stream_ptr()), "pack")
                 return o
-            keep = p.derived(("bf16", sc), lambda: (cast(Wx), cast(Wm), cast(Wm2)))
+            keep = p.derived(("bf16", sc), lambda: (pack(Wx), pack(Wm), pack(Wm2)))
             rw.Wx_bf16, rw.Wm_bf16, rw.Wm2_bf16 = (t.data_ptr() for t in keep)
         self._rw[name] = rw
         return rw

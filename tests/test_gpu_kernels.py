@@ -125,3 +125,24 @@ def test_dropout_rng_matches_independent_philox():
         mask = np.floor(keep + ref)
         assert np.allclose(o.cpu().numpy(), mask / np.float32(keep), rtol=1e-6)
     assert 0.8 < mask.mean() < 0.9
+
+
+@pytest.mark.parametrize("M,K,N,act", [(12544, 512, 512, "NON"), (300, 1024, 256, "ELU"), (128, 64, 256, "NON"),
+                                       (3136, 512, 512, "TANH")])
+def test_linear_tensor_core(M, K, N, act):
+    """tcgen05/TMEM GEMM (bf16 operands, fp32 accumulate) against an fp64 product of the same bf16-rounded operands."""
+    L, lib = _lib()
+    rng = np.random.RandomState(3)
+    x = torch.from_numpy(rng.standard_normal((M, K)).astype(np.float32)).cuda().to(torch.bfloat16)
+    W = torch.from_numpy((rng.standard_normal((K, N)) / np.sqrt(K)).astype(np.float32)).cuda()
+    b = torch.from_numpy(rng.standard_normal((N,)).astype(np.float32)).cuda()
+    Wt = torch.empty(N, K, dtype=torch.bfloat16, device="cuda")
+    L.check(lib.mac_pack_weight_bf16(L.ptr(W), L.ptr(Wt), K, N, L.stream_ptr()))
+    torch.cuda.synchronize()
+    assert torch.equal(Wt, W.t().contiguous().to(torch.bfloat16))
+    y = torch.zeros(M, N, device="cuda")
+    L.check(lib.mac_linear_tc_fwd(L.ptr(x), L.ptr(Wt), L.ptr(b), L.ACT[act], L.ptr(y), M, K, N, L.stream_ptr()))
+    torch.cuda.synchronize()
+    z = x.float().cpu().numpy().astype(np.float64) @ Wt.float().cpu().numpy().astype(np.float64).T + b.cpu().numpy()
+    ref = {"NON": z, "ELU": O.elu(z), "TANH": np.tanh(z)}[act]
+    assert max_rel(y.cpu().numpy(), ref) < 1e-4
