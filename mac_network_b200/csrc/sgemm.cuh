@@ -7,6 +7,7 @@
 // deterministic.
 #pragma once
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace mac {
 
@@ -319,10 +320,14 @@ inline size_t sgemm_workspace_bytes(int M, int N, int K) {
   return (size_t)splitk * M * N * sizeof(float) + 256;
 }
 
+inline bool skinny_ok(const SgemmParams& p);
+inline int skinny_launch(const SgemmParams& p, cudaStream_t stream);
+
 inline int sgemm_launch(SgemmParams p, unsigned int* counters, float* partial, size_t partial_bytes,
                         cudaStream_t stream, bool allow_splitk = true) {
   if (p.M <= 0 || p.N <= 0 || p.K <= 0) return MAC_ERR_INVALID;
   if ((p.N & 3) || (p.K & 3)) return MAC_ERR_INVALID;
+  if (allow_splitk && skinny_ok(p) && !getenv("MAC_NO_SKINNY")) return skinny_launch(p, stream);   // M <= 64: cluster/DSMEM split-K kernel
   const bool big = (p.M >= 512);
   const int BM = big ? 128 : 64, BN = big ? 128 : 64;
   dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, 1);

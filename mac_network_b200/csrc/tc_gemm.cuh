@@ -7,7 +7,8 @@
 // Warp roles (192 threads, persistent over output tiles, one CTA per SM):
 //   warp 0      TMA producer          (one elected lane issues the A and B boxes of each k-block)
 //   warp 1      TMEM allocator + MMA issuer (one elected lane issues tcgen05.mma / tcgen05.commit)
-//   warps 2..5  epilogue              (tcgen05.ld 32 lanes x 32 columns per instruction; thread == output row)
+//   warps 2..9  epilogue              (tcgen05.ld 32 lanes x 32 columns per instruction; thread == output row;
+//                                      two warps per TMEM lane quarter, each takes half of the tile's columns)
 // Two accumulator buffers (2 x BN TMEM columns) let the epilogue of tile i overlap the MMAs of tile i+1.
 //
 // Epilogues (the read-unit chain of mac_cell.py:230-266 / ops.py:668-725, see mac_b200.h):
@@ -19,6 +20,7 @@
 #pragma once
 #include "common.cuh"
 #include "tmap.cuh"
+#include <stdlib.h>
 
 namespace mac {
 
@@ -42,6 +44,7 @@ struct TcGemmParams {
   float e_scale;
   uint64_t seed;
   int e_site, step;
+  int debug;               // MAC_TC_DEBUG (profiling experiments only): 1 skip epilogue math/stores, 2 skip MMA, 4 skip TMA
 };
 
 // ------------------------------------------------------------------ tcgen05 PTX wrappers
@@ -110,7 +113,9 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;                 // 64 bf16 = 128 B = one swizzle atom row
-constexpr int TC_THREADS = 192;
+constexpr int TC_MAX_VEC = 4;              // a 128-row tile spans at most this many samples on the smem-parameter path
+constexpr int TC_EPI_WARPS = 8;            // two per TMEM lane quarter: each handles half of the tile's columns
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 
 template <int BN>
 struct TcCfg {
@@ -118,11 +123,31 @@ struct TcCfg {
   static constexpr int A_BYTES = TC_BM * TC_BK * 2;        // 16 KB
   static constexpr int B_BYTES = BN * TC_BK * 2;           // 32 KB (BN = 256)
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int STG_WORDS = 32 * 16;                // per epilogue warp: 32 rows x 16 words, XOR-swizzled
+  static constexpr int PAR_ROWS = 2 + TC_MAX_VEC;          // bias, wr, and up to TC_MAX_VEC per-sample rows (y / control)
+  static constexpr int PAR_WORDS = 2 * PAR_ROWS * BN;      // double-buffered with the accumulators
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ +
+                                    TC_EPI_WARPS * STG_WORDS * 4 + PAR_WORDS * 4;
   static constexpr int TMEM_COLS = 2 * BN;                 // two accumulator buffers; power of two >= 32
 };
 
-template <int BN>
+// fast ELU for the tensor-core path: x > 0 ? x : exp(x) - 1 with the SFU exponential (abs error ~1e-7 near 0,
+// far below the bf16 rounding of the stored activations)
+__device__ __forceinline__ float elu_fast(float x) { return x > 0.f ? x : __expf(x) - 1.f; }
+template <int ACT>
+__device__ __forceinline__ float act_ct(float x) {
+  if constexpr (ACT == MAC_ACT_TANH) return tanhf(x);
+  else if constexpr (ACT == MAC_ACT_SIGMOID) return 1.f / (1.f + __expf(-x));
+  else if constexpr (ACT == MAC_ACT_ELU) return elu_fast(x);
+  else if constexpr (ACT == MAC_ACT_RELU) return fmaxf(x, 0.f);
+  else return x;
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+template <int BN, int EPI, int ACT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                const __grid_constant__ CUtensorMap map_b, const TcGemmParams p) {
@@ -138,6 +163,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   uint64_t* tfull = bars + 2 * C::STAGES;      // [2]       MMA -> epilogue
   uint64_t* tempty = tfull + 2;                // [2]       epilogue -> MMA
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint32_t* stg_all = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(bars) + 256);
+  float* par_all = reinterpret_cast<float*>(stg_all + TC_EPI_WARPS * C::STG_WORDS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = (p.M + TC_BM - 1) / TC_BM;
@@ -156,8 +183,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     }
     mbar_init(&tfull[0], 1);
     mbar_init(&tfull[1], 1);
-    mbar_init(&tempty[0], 4);
-    mbar_init(&tempty[1], 4);
+    mbar_init(&tempty[0], TC_EPI_WARPS);
+    mbar_init(&tempty[1], TC_EPI_WARPS);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr, C::TMEM_COLS);
@@ -177,6 +204,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           mbar_wait(&empty[stage], phase ^ 1);
           unsigned char* sa = tiles + stage * C::STAGE_BYTES;
           unsigned char* sb = sa + C::A_BYTES;
+          if (p.debug & 4) {
+            mbar_arrive(&full[stage]);
+            if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
           mbar_expect_tx(&full[stage], C::STAGE_BYTES);
           if (kb < p.kblocks0)
             tma_load_2d(sa, &map_a0, kb * TC_BK, mt * TC_BM, &full[stage]);
@@ -209,7 +241,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k) {
             // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle atom: +2 in the 16-B address field
-            umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+            if (!(p.debug & 2)) umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
           }
           umma_commit(&empty[stage]);                // frees the smem slot when these MMAs retire
           if (kb == kblocks - 1) umma_commit(&tfull[acc]);
@@ -220,105 +252,163 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     }
   } else {
     // ===================================================== epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1)
+    // thread == one output row of the tile; 32 fp32 columns per tcgen05.ld
     const int q = warp & 3;
+    uint32_t* stg = stg_all + (warp - 2) * C::STG_WORDS;
+    const int chalf = (warp - 2) >> 2;              // which half of the tile's columns this warp drains
+    // Row-per-thread registers -> coalesced 128-bit global stores.  The warp's 32-row chunk goes through a private
+    // shared-memory patch whose 16-byte groups are XOR-swizzled with the row (conflict-free both ways): thread == row
+    // writes 16-B groups, then lane l reads group (l % G) of row (i*32/G + l / G) and stores 16 B to global, so one
+    // store instruction covers 32/G whole row segments (G = 4: 64-B bf16 rows; G = 8: 128-B fp32 rows).
+    auto store_bf16_chunk = [&](const uint32_t (&w)[16], __nv_bfloat16* out, int row0, int col0) {
+      __syncwarp();
+      uint4* s4 = reinterpret_cast<uint4*>(stg);
+#pragma unroll
+      for (int g = 0; g < 4; ++g) s4[lane * 4 + (g ^ (lane & 3))] = make_uint4(w[4 * g], w[4 * g + 1], w[4 * g + 2], w[4 * g + 3]);
+      __syncwarp();
+      const int g = lane & 3;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int rr = i * 8 + (lane >> 2);
+        const uint4 v = s4[rr * 4 + (g ^ (rr & 3))];
+        if (row0 + rr < p.M) *reinterpret_cast<uint4*>(out + (size_t)(row0 + rr) * p.ldo + col0 + 8 * g) = v;
+      }
+    };
+    auto store_f32_chunk = [&](const float (&w)[32], float* out, int row0, int col0) {
+      float4* s4 = reinterpret_cast<float4*>(stg);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {            // two 16-column halves through the 2 KB patch
+        __syncwarp();
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          s4[lane * 4 + (g ^ (lane & 3))] = make_float4(w[16 * h + 4 * g], w[16 * h + 4 * g + 1], w[16 * h + 4 * g + 2], w[16 * h + 4 * g + 3]);
+        __syncwarp();
+        const int g = lane & 3;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int rr = i * 8 + (lane >> 2);
+          const float4 v = s4[rr * 4 + (g ^ (rr & 3))];
+          if (row0 + rr < p.M) *reinterpret_cast<float4*>(out + (size_t)(row0 + rr) * p.ldo + col0 + 16 * h + 4 * g) = v;
+        }
+      }
+    };
+    const int etid = threadIdx.x - 64;              // 0..255 among the epilogue threads
+    const float* vec_src = (EPI == TC_EPI_P) ? p.y : (EPI == TC_EPI_LOGITS ? p.ctrl : nullptr);
     int it = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       const int mt = t / n_tiles, nt = t % n_tiles;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
+      // ---- stage this tile's parameters in shared memory while the MMAs of the tile are still running:
+      //      row 0 bias[BN], row 1 wr[BN], rows 2.. the y / control vectors of the samples this tile touches
+      float* par = par_all + acc * (C::PAR_ROWS * BN);
+      const int b_lo = (mt * TC_BM) / p.rows_per_batch;
+      const int last_row = min(p.M, (mt + 1) * TC_BM) - 1;
+      const int nvec = vec_src ? (last_row / p.rows_per_batch - b_lo + 1) : 0;
+      const bool vec_smem = nvec <= TC_MAX_VEC;
+      {
+        const int nb = nt * BN;
+        for (int i = etid; i < BN; i += 32 * TC_EPI_WARPS) {
+          par[i] = p.bias ? __ldg(p.bias + nb + i) : 0.f;
+          if constexpr (EPI == TC_EPI_LOGITS) par[BN + i] = __ldg(p.wr + nb + i);
+        }
+        if (vec_src && vec_smem)
+          for (int i = etid; i < nvec * BN; i += 32 * TC_EPI_WARPS)
+            par[2 * BN + i] = __ldg(vec_src + (size_t)(b_lo + i / BN) * p.N + nb + (i % BN));
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
+      }
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      const int row = mt * TC_BM + q * 32 + lane;
+      const int row0 = mt * TC_BM + q * 32;
+      const int row = row0 + lane;
       const bool row_ok = row < p.M;
-      const int bidx = row_ok ? row / p.rows_per_batch : 0;
+      const int bidx = row_ok ? row / p.rows_per_batch : b_lo;
+      const float* vrow = vec_smem ? par + (2 + bidx - b_lo) * BN : nullptr;   // this row's y / control vector (tile-local)
       const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
       float part = 0.f;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = chalf * (BN / 2); c0 < (chalf + 1) * (BN / 2); c0 += 32) {
+        if (p.debug & 1) break;
         uint32_t r[32];
-        tmem_ld32(taddr + c0, r);
-        tmem_ld_wait();
+        if (p.debug & 8) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = (uint32_t)(c0 + j);
+        } else {
+          tmem_ld32(taddr + c0, r);
+          tmem_ld_wait();
+        }
         const int n0 = nt * BN + c0;
-        float v[32];
+        const float4* bias4 = reinterpret_cast<const float4*>(par + c0);
+        if constexpr (EPI == TC_EPI_P) {
+          const float4* y4 = vec_smem ? reinterpret_cast<const float4*>(vrow + c0)
+                                      : reinterpret_cast<const float4*>(p.y + (size_t)bidx * p.N + n0);
+          uint32_t w0[16], w1[16];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + n0 + j) : 0.f);
-        if (p.epi == TC_EPI_P) {
-          if (row_ok) {
-            const float* yb = p.y + (size_t)bidx * p.N + n0;
-            uint4* o0 = reinterpret_cast<uint4*>(p.out0 + (size_t)row * p.ldo + n0);
-            uint4* o1 = reinterpret_cast<uint4*>(p.out1 + (size_t)row * p.ldo + n0);
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint32_t a[4], b[4];
-#pragma unroll
-              for (int h = 0; h < 4; ++h) {
-                const float x0 = v[j + 2 * h], x1 = v[j + 2 * h + 1];
-                __nv_bfloat162 t0 = __floats2bfloat162_rn(x0, x1);
-                __nv_bfloat162 t1 = __floats2bfloat162_rn(x0 * __ldg(yb + j + 2 * h), x1 * __ldg(yb + j + 2 * h + 1));
-                a[h] = *reinterpret_cast<uint32_t*>(&t0);
-                b[h] = *reinterpret_cast<uint32_t*>(&t1);
-              }
-              o0[j / 8] = make_uint4(a[0], a[1], a[2], a[3]);
-              o1[j / 8] = make_uint4(b[0], b[1], b[2], b[3]);
-            }
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b0 = bias4[j / 4], y0 = y4[j / 4];
+            const float x0 = __uint_as_float(r[j]) + b0.x, x1 = __uint_as_float(r[j + 1]) + b0.y;
+            const float x2 = __uint_as_float(r[j + 2]) + b0.z, x3 = __uint_as_float(r[j + 3]) + b0.w;
+            w0[j / 2] = pack_bf16(x0, x1);
+            w0[j / 2 + 1] = pack_bf16(x2, x3);
+            w1[j / 2] = pack_bf16(x0 * y0.x, x1 * y0.y);
+            w1[j / 2 + 1] = pack_bf16(x2 * y0.z, x3 * y0.w);
           }
-        } else if (p.epi == TC_EPI_ACT) {
-          if (row_ok) {
-            uint4* o0 = reinterpret_cast<uint4*>(p.out0 + (size_t)row * p.ldo + n0);
+          store_bf16_chunk(w0, p.out0, row0, n0);
+          store_bf16_chunk(w1, p.out1, row0, n0);
+        } else if constexpr (EPI == TC_EPI_ACT) {
+          uint32_t w0[16];
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint32_t a[4];
-#pragma unroll
-              for (int h = 0; h < 4; ++h) {
-                __nv_bfloat162 t0 = __floats2bfloat162_rn(apply_act(p.act, v[j + 2 * h]), apply_act(p.act, v[j + 2 * h + 1]));
-                a[h] = *reinterpret_cast<uint32_t*>(&t0);
-              }
-              o0[j / 8] = make_uint4(a[0], a[1], a[2], a[3]);
-            }
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b0 = bias4[j / 4];
+            w0[j / 2] = pack_bf16(act_ct<ACT>(__uint_as_float(r[j]) + b0.x), act_ct<ACT>(__uint_as_float(r[j + 1]) + b0.y));
+            w0[j / 2 + 1] = pack_bf16(act_ct<ACT>(__uint_as_float(r[j + 2]) + b0.z), act_ct<ACT>(__uint_as_float(r[j + 3]) + b0.w));
           }
-        } else if (p.epi == TC_EPI_F32) {
-          if (row_ok) {
-            float4* o = reinterpret_cast<float4*>(p.outf + (size_t)row * p.ldo + n0);
+          store_bf16_chunk(w0, p.out0, row0, n0);
+        } else if constexpr (EPI == TC_EPI_F32) {
+          float w0[32];
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              o[j / 4] = make_float4(apply_act(p.act, v[j]), apply_act(p.act, v[j + 1]), apply_act(p.act, v[j + 2]),
-                                     apply_act(p.act, v[j + 3]));
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b0 = bias4[j / 4];
+            w0[j] = act_ct<ACT>(__uint_as_float(r[j]) + b0.x);
+            w0[j + 1] = act_ct<ACT>(__uint_as_float(r[j + 1]) + b0.y);
+            w0[j + 2] = act_ct<ACT>(__uint_as_float(r[j + 2]) + b0.z);
+            w0[j + 3] = act_ct<ACT>(__uint_as_float(r[j + 3]) + b0.w);
           }
+          if (!(p.debug & 32)) store_f32_chunk(w0, p.outf, row0, n0);
+          else if (w0[lane] == 123.456f) p.outf[0] = 1.f;
         } else {  // TC_EPI_LOGITS
-          if (row_ok) {
-            if (p.out0) {
-              uint4* o0 = reinterpret_cast<uint4*>(p.out0 + (size_t)row * p.ldo + n0);
+          const float4* c4 = vec_smem ? reinterpret_cast<const float4*>(vrow + c0)
+                                      : reinterpret_cast<const float4*>(p.ctrl + (size_t)bidx * p.N + n0);
+          const float4* w4 = reinterpret_cast<const float4*>(par + BN + c0);
+          uint32_t w0[16];
 #pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                uint32_t a[4];
-#pragma unroll
-                for (int h = 0; h < 4; ++h) {
-                  __nv_bfloat162 t0 = __floats2bfloat162_rn(v[j + 2 * h], v[j + 2 * h + 1]);
-                  a[h] = *reinterpret_cast<uint32_t*>(&t0);
-                }
-                o0[j / 8] = make_uint4(a[0], a[1], a[2], a[3]);
-              }
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b0 = bias4[j / 4], cc = c4[j / 4], ww = w4[j / 4];
+            const float i0 = __uint_as_float(r[j]) + b0.x, i1 = __uint_as_float(r[j + 1]) + b0.y;
+            const float i2 = __uint_as_float(r[j + 2]) + b0.z, i3 = __uint_as_float(r[j + 3]) + b0.w;
+            w0[j / 2] = pack_bf16(i0, i1);
+            w0[j / 2 + 1] = pack_bf16(i2, i3);
+            float t0 = elu_fast(i0 * cc.x), t1 = elu_fast(i1 * cc.y), t2 = elu_fast(i2 * cc.z), t3 = elu_fast(i3 * cc.w);
+            if (p.e_thresh) {
+              const uint64_t e = (uint64_t)row * (uint64_t)p.N + (uint64_t)(n0 + j);
+              const Philox4 rr = philox4x32_10(p.seed, e >> 2, (uint32_t)p.e_site, (uint32_t)p.step);
+              t0 = ((rr.x >> 8) >= p.e_thresh) ? t0 * p.e_scale : 0.f;
+              t1 = ((rr.y >> 8) >= p.e_thresh) ? t1 * p.e_scale : 0.f;
+              t2 = ((rr.z >> 8) >= p.e_thresh) ? t2 * p.e_scale : 0.f;
+              t3 = ((rr.w >> 8) >= p.e_thresh) ? t3 * p.e_scale : 0.f;
             }
-            const float* cb = p.ctrl + (size_t)bidx * p.N + n0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              uint32_t bits[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
-              if (p.e_thresh) {
-                const uint64_t e = (uint64_t)row * (uint64_t)p.N + (uint64_t)(n0 + j);
-                const Philox4 rr = philox4x32_10(p.seed, e >> 2, (uint32_t)p.e_site, (uint32_t)p.step);
-                bits[0] = rr.x; bits[1] = rr.y; bits[2] = rr.z; bits[3] = rr.w;
-              }
-#pragma unroll
-              for (int h = 0; h < 4; ++h) {
-                float tt = elu_f(v[j + h] * __ldg(cb + j + h));
-                tt = ((bits[h] >> 8) >= p.e_thresh) ? tt * p.e_scale : 0.f;
-                part = fmaf(tt, __ldg(p.wr + n0 + j + h), part);
-              }
-            }
+            part = fmaf(t0, ww.x, part);
+            part = fmaf(t1, ww.y, part);
+            part = fmaf(t2, ww.z, part);
+            part = fmaf(t3, ww.w, part);
           }
+          if (p.out0) store_bf16_chunk(w0, p.out0, row0, n0);       // I1 kept for backward
         }
       }
-      if (p.epi == TC_EPI_LOGITS && row_ok) p.parts[(size_t)row * n_tiles + nt] = part;
+      if constexpr (EPI == TC_EPI_LOGITS) {
+        // two partial sums per (row, n-tile): one per column half
+        if (row_ok) p.parts[((size_t)row * n_tiles + nt) * 2 + chalf] = part;
+      }
       // release the accumulator buffer to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -346,12 +436,60 @@ inline int tc_num_sms() {
   return sms;
 }
 
+template <int BN, int EPI, int ACT>
+inline int tc_gemm_launch_t(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtensorMap& mb,
+                            const TcGemmParams& p, cudaStream_t stream) {
+  auto kern = tc_gemm_kernel<BN, EPI, ACT>;
+  MAC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM_BYTES));
+  const int tiles = ((p.M + TC_BM - 1) / TC_BM) * (p.N / BN);
+  const int grid = tiles < tc_num_sms() ? tiles : tc_num_sms();
+  kern<<<grid, TC_THREADS, TcCfg<BN>::SMEM_BYTES, stream>>>(ma0, ma1, mb, p);
+  MAC_LAUNCH_CHECK();
+  return MAC_OK;
+}
+
+template <int BN>
+inline int tc_gemm_dispatch(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtensorMap& mb,
+                            const TcGemmParams& p, cudaStream_t stream) {
+  switch (p.epi) {
+    case TC_EPI_P: return tc_gemm_launch_t<BN, TC_EPI_P, MAC_ACT_NON>(ma0, ma1, mb, p, stream);
+    case TC_EPI_LOGITS: return tc_gemm_launch_t<BN, TC_EPI_LOGITS, MAC_ACT_NON>(ma0, ma1, mb, p, stream);
+    case TC_EPI_ACT:
+      if (p.act == MAC_ACT_ELU) return tc_gemm_launch_t<BN, TC_EPI_ACT, MAC_ACT_ELU>(ma0, ma1, mb, p, stream);
+      if (p.act == MAC_ACT_NON) return tc_gemm_launch_t<BN, TC_EPI_ACT, MAC_ACT_NON>(ma0, ma1, mb, p, stream);
+      return MAC_ERR_UNSUPPORTED;
+    case TC_EPI_F32:
+      switch (p.act) {
+        case MAC_ACT_NON: return tc_gemm_launch_t<BN, TC_EPI_F32, MAC_ACT_NON>(ma0, ma1, mb, p, stream);
+        case MAC_ACT_TANH: return tc_gemm_launch_t<BN, TC_EPI_F32, MAC_ACT_TANH>(ma0, ma1, mb, p, stream);
+        case MAC_ACT_SIGMOID: return tc_gemm_launch_t<BN, TC_EPI_F32, MAC_ACT_SIGMOID>(ma0, ma1, mb, p, stream);
+        case MAC_ACT_ELU: return tc_gemm_launch_t<BN, TC_EPI_F32, MAC_ACT_ELU>(ma0, ma1, mb, p, stream);
+        case MAC_ACT_RELU: return tc_gemm_launch_t<BN, TC_EPI_F32, MAC_ACT_RELU>(ma0, ma1, mb, p, stream);
+      }
+      return MAC_ERR_UNSUPPORTED;
+  }
+  return MAC_ERR_UNSUPPORTED;
+}
+
+// tile width: the one that minimises (rounds over the SMs) x (tile width) -- 392 tiles of 128 x 128 finish in 3
+// rounds of half-size tiles where 196 tiles of 128 x 256 need 2 full rounds
+inline int tc_pick_bn(int M, int N) {
+  if (N % 256) return 128;
+  const int sms = tc_num_sms();
+  const int mt = (M + TC_BM - 1) / TC_BM;
+  const int r256 = (mt * (N / 256) + sms - 1) / sms, r128 = (mt * (N / 128) + sms - 1) / sms;
+  return (r128 * 128 < r256 * 256) ? 128 : 256;
+}
+
 // A = [a0 (K0 cols) | a1 (K1 cols)] bf16 row-major (ld = own K), Wt bf16 [N, K0+K1]
 inline int tc_gemm_launch(const void* a0, int K0, const void* a1, int K1, const void* wt, TcGemmParams p,
-                          cudaStream_t stream) {
-  constexpr int BN = 256;
-  if (p.M <= 0 || p.N <= 0 || (p.N % BN) || (K0 % TC_BK) || (K1 % TC_BK) || K0 <= 0) return MAC_ERR_UNSUPPORTED;
+                          cudaStream_t stream, int* bn_used = nullptr) {
+  if (p.M <= 0 || p.N <= 0 || (p.N % 128) || (K0 % TC_BK) || (K1 % TC_BK) || K0 <= 0) return MAC_ERR_UNSUPPORTED;
   if (!mac_aligned16(a0) || !mac_aligned16(wt)) return MAC_ERR_ALIGN;
+  int BN = tc_pick_bn(p.M, p.N);
+  if (const char* e = getenv("MAC_TC_BN")) { const int v = atoi(e); if ((v == 128 || v == 256) && p.N % v == 0) BN = v; }
+  if (const char* e = getenv("MAC_TC_DEBUG")) p.debug = atoi(e);
+  if (bn_used) *bn_used = BN;
   p.K = K0 + K1;
   p.kblocks0 = K0 / TC_BK;
   CUtensorMap ma0, ma1, mb;
@@ -363,15 +501,9 @@ inline int tc_gemm_launch(const void* a0, int K0, const void* a1, int K1, const 
   } else {
     ma1 = ma0;
   }
-  st = make_tmap_2d(&mb, wt, 1, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)p.K * 2, BN, TC_BK, 1);
+  st = make_tmap_2d(&mb, wt, 1, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)p.K * 2, (uint32_t)BN, TC_BK, 1);
   if (st != MAC_OK) return st;
-  auto kern = tc_gemm_kernel<BN>;
-  MAC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM_BYTES));
-  const int tiles = ((p.M + TC_BM - 1) / TC_BM) * (p.N / BN);
-  const int grid = tiles < tc_num_sms() ? tiles : tc_num_sms();
-  kern<<<grid, TC_THREADS, TcCfg<BN>::SMEM_BYTES, stream>>>(ma0, ma1, mb, p);
-  MAC_LAUNCH_CHECK();
-  return MAC_OK;
+  return BN == 256 ? tc_gemm_dispatch<256>(ma0, ma1, mb, p, stream) : tc_gemm_dispatch<128>(ma0, ma1, mb, p, stream);
 }
 
 // fp32 [K, N] (in, out) weight -> bf16 [N, K] (out, in): the K-major B operand of the forward GEMMs
@@ -400,7 +532,7 @@ inline int tc_read_chain(const void* kb_bf16, const float* y, const float* contr
                          float* /*I1_f32*/, float* parts, int* nparts, void* ws, size_t ws_bytes, int B, int N, int d,
                          bool save, cudaStream_t stream) {
   if (!kb_bf16 || !w->Wx_bf16 || !w->Wm_bf16 || !w->Wm2_bf16) return MAC_ERR_INVALID;
-  if (d % 256) return MAC_ERR_UNSUPPORTED;
+  if (d % 128) return MAC_ERR_UNSUPPORTED;
   if (thr != 0) return MAC_ERR_UNSUPPORTED;      // training-mode dropout on the tensor-core path: not yet
   if (ws_bytes < tc_read_extra_workspace_bytes(B, N, d)) return MAC_ERR_WORKSPACE;
   const int M = B * N;
@@ -423,9 +555,10 @@ inline int tc_read_chain(const void* kb_bf16, const float* y, const float* contr
   // logits parts = sum_n ELU((H @ Wm2 + bm2) * control) * wr
   p.epi = TC_EPI_LOGITS; p.bias = w->bm2; p.out0 = I1; p.ctrl = control; p.wr = w->wr; p.parts = parts;
   p.e_thresh = thr; p.e_scale = scale; p.e_site = MAC_SITE_READ_INTER;
-  st = tc_gemm_launch(H, d, nullptr, 0, w->Wm2_bf16, p, stream);
+  int bn = 256;
+  st = tc_gemm_launch(H, d, nullptr, 0, w->Wm2_bf16, p, stream, &bn);
   if (st != MAC_OK) return st;
-  *nparts = d / 256;
+  *nparts = 2 * (d / bn);
   return MAC_OK;
 }
 

@@ -1,6 +1,7 @@
 // C-ABI entry points of the three MAC units (fp32 projection path) and the elementwise helpers.
 #include "common.cuh"
 #include "sgemm.cuh"
+#include "skinny.cuh"
 #include "tc_gemm.cuh"
 
 using namespace mac;
