@@ -168,6 +168,45 @@ int mac_pack_weight_bf16(const float* W, void* Wt_bf16, int K, int n_out, mac_st
 int mac_linear_tc_fwd(const void* x_bf16, const void* wt_bf16, const float* b, int act, float* y,
                       int M, int K, int n_out, mac_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Backward (fp32 path).  The reference differentiates the graph with TF autodiff (model.py:626-636); each forward
+ * entry point above has a counterpart here (math: SURVEY.md Appendix E).  "+=" outputs accumulate (zero them once per
+ * backward pass).  `*_part` outputs are per-sample partial sums [B, d] (or [B]) to be reduced over B with mac_colsum
+ * at the end of the pass -- every reduction has a fixed order, so gradients are deterministic.
+ * --------------------------------------------------------------------------------------------- */
+/* y = concat(x_s) @ W + b:  dx_s (+)= dy @ W[k-range of s, :]^T (Wt = W^T [n_out, K] row-major); dW += x^T dy; db += colsum(dy) */
+int mac_linear_bwd(const float* const* x_segs, const int* k_segs, const int* ldx, int nseg, const float* Wt,
+                   const float* dy, int ldy, float* const* dx_segs, const int* ld_dx, const int* dx_accum,
+                   float* dW, float* db, int M, int n_out, void* workspace, size_t workspace_bytes, mac_stream_t stream);
+/* backward of mac_control_attend_fwd (control unit attention and write-unit self-attention); d_in_words/d_out_words += (they
+ * may be the same buffer), dq = gradient w.r.t. cc (optionally accumulated), dw_part [B,d] +=, db_part [B] += */
+int mac_control_attend_bwd(const float* cc, long long cc_tstride, long long cc_bstride,
+                           const float* in_words, long long in_bstride, long long in_rstride,
+                           const float* out_words, long long out_bstride, long long out_rstride,
+                           const float* w_logit, const float* att, const float* g_out, long long g_tstride, long long g_bstride,
+                           float* d_in_words, float* d_out_words, float* dq, long long dq_tstride, long long dq_bstride,
+                           int dq_accumulate, float* dw_part, float* db_part, int nsteps, int B, int S, int d, mac_stream_t stream);
+/* backward of mac_kb_attend_fwd: dkl [B,N] = softmax-backward of the logits; dkb [B,N,d] += att (x) dinfo (dkb may be NULL) */
+int mac_kb_attend_bwd(const float* kb, const float* att, const float* dinfo, float* dka_scratch, float* dkl,
+                      float* dkb, float* dbr_part, int B, int N, int d, mac_stream_t stream);
+/* backward of mac_read_fwd (MAC_PREC_FP32); `save` is what the forward wrote; W*_t are the transposed weights */
+int mac_read_bwd(const float* kb, const float* memory_in, const float* control, const mac_read_weights* w,
+                 const float* Wx_t, const float* Wy_t, const float* Wm_t, const float* Wm2_t,
+                 const float* att, const float* save, const float* dinfo, float keep_read, uint64_t seed, int step,
+                 float* dkb, float* dmem_in, float* dcontrol, float* dWx, float* dbx_part, float* dWy, float* dby,
+                 float* dWm, float* dbm_part, float* dWm2, float* dbm2_part, float* dwr_part, float* dbr_part,
+                 void* workspace, size_t workspace_bytes, int B, int N, int d, mac_stream_t stream);
+size_t mac_read_bwd_workspace_bytes(int B, int N, int d);
+/* write gate (mac_cell.py:358-367): dmnew = g*z; dmprev += g*(1-z); dpre = g*(mnew-mprev)*z*(1-z) */
+int mac_gate_bwd(const float* g, const float* z, const float* mnew, const float* mprev, float* dmnew, float* dmprev,
+                 float* dpre, long long n, mac_stream_t stream);
+/* dx = dy * act'(.) given the saved activation OUTPUT y */
+int mac_activation_bwd(const float* y, const float* dy, int act, float* dx, long long n, mac_stream_t stream);
+/* out[b,k] (+)= sum_n x[b,n,k] */
+int mac_colsum(const float* x, float* out, int B, int N, int d, int accumulate, mac_stream_t stream);
+/* dst += alpha * src */
+int mac_axpy(float* dst, const float* src, float alpha, long long n, mac_stream_t stream);
+
 /* dropout sites (the `site` word of the Philox counter) */
 enum { MAC_SITE_MEM_VAR = 0, MAC_SITE_READ_KB = 1, MAC_SITE_READ_MEM = 2, MAC_SITE_READ_INTER = 3,
        MAC_SITE_WRITE_INFO = 4, MAC_SITE_MEM_PLAIN = 5 };

@@ -52,6 +52,19 @@ PROTOTYPES = {
     "mac_dropout_fwd": (c_int, [c_fp, c_f, c_u64, c_int, c_int, c_fp, c_ll, c_fp]),
     "mac_dropout_uniform": (c_int, [c_u64, c_int, c_int, c_fp, c_ll, c_fp]),
     "mac_cast_bf16": (c_int, [c_fp, c_fp, c_ll, c_fp]),
+    "mac_linear_bwd": (c_int, [ctypes.POINTER(c_fp), ctypes.POINTER(c_int), ctypes.POINTER(c_int), c_int, c_fp, c_fp, c_int,
+                               ctypes.POINTER(c_fp), ctypes.POINTER(c_int), ctypes.POINTER(c_int), c_fp, c_fp, c_int, c_int,
+                               c_fp, c_sz, c_fp]),
+    "mac_control_attend_bwd": (c_int, [c_fp, c_ll, c_ll, c_fp, c_ll, c_ll, c_fp, c_ll, c_ll, c_fp, c_fp, c_fp, c_ll, c_ll,
+                                       c_fp, c_fp, c_fp, c_ll, c_ll, c_int, c_fp, c_fp, c_int, c_int, c_int, c_int, c_fp]),
+    "mac_kb_attend_bwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_fp]),
+    "mac_read_bwd": (c_int, [c_fp, c_fp, c_fp, ctypes.POINTER(ReadWeights), c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_f,
+                             c_u64, c_int] + [c_fp] * 13 + [c_fp, c_sz, c_int, c_int, c_int, c_fp]),
+    "mac_read_bwd_workspace_bytes": (c_sz, [c_int, c_int, c_int]),
+    "mac_gate_bwd": (c_int, [c_fp] * 7 + [c_ll, c_fp]),
+    "mac_activation_bwd": (c_int, [c_fp, c_fp, c_int, c_fp, c_ll, c_fp]),
+    "mac_colsum": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_int, c_fp]),
+    "mac_axpy": (c_int, [c_fp, c_fp, c_f, c_ll, c_fp]),
     "mac_pack_weight_bf16": (c_int, [c_fp, c_fp, c_int, c_int, c_fp]),
     "mac_linear_tc_fwd": (c_int, [c_fp, c_fp, c_fp, c_int, c_fp, c_int, c_int, c_int, c_fp]),
 }

@@ -1,0 +1,519 @@
+// Backward of the MAC cell (fp32 path).  The reference obtains it from TF autodiff (`optimizer.compute_gradients`,
+// model.py:626-636); here each forward entry point of mac_b200.h has a hand-written counterpart.  Math: SURVEY.md
+// Appendix E.  Reductions are per-sample partial sums (one CTA owns a (sample, column-slice)), reduced over the batch
+// at the end of the backward pass, so gradients are deterministic (no atomics anywhere).
+#include "common.cuh"
+#include "sgemm.cuh"
+#include "skinny.cuh"
+
+using namespace mac;
+
+namespace mac {
+constexpr size_t BW_HEADER = 4096;
+
+// ------------------------------------------------------------------------------------------------ small helpers
+__global__ void axpy_kernel(float* __restrict__ dst, const float* __restrict__ src, float alpha, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] += alpha * src[i];
+}
+
+// dx = dy * act'(.) expressed through the saved OUTPUT y (tanh: 1-y^2; sigmoid: y(1-y); elu: y>0?1:y+1; relu: y>0)
+__global__ void act_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dy, int act,
+                               float* __restrict__ dx, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = y[i];
+  float g = 1.f;
+  if (act == MAC_ACT_TANH) g = 1.f - v * v;
+  else if (act == MAC_ACT_SIGMOID) g = v * (1.f - v);
+  else if (act == MAC_ACT_ELU) g = v > 0.f ? 1.f : v + 1.f;
+  else if (act == MAC_ACT_RELU) g = v > 0.f ? 1.f : 0.f;
+  dx[i] = dy[i] * g;
+}
+
+// out[b, k] (+)= sum_n x[b, n, k]     grid (ceil(d/128), B), 128 threads
+__global__ void colsum_kernel(const float* __restrict__ x, float* __restrict__ out, int N, int d, int accumulate) {
+  const int k = blockIdx.x * 128 + threadIdx.x, b = blockIdx.y;
+  if (k >= d) return;
+  const float* p = x + (size_t)b * N * d + k;
+  float s = 0.f;
+  for (int n = 0; n < N; ++n) s += p[(size_t)n * d];
+  float* o = out + (size_t)b * d + k;
+  *o = accumulate ? *o + s : s;
+}
+
+// write gate backward (mac_cell.py:358-367): m = m'*z + mprev*(1-z), z = sigmoid(pre)
+//   dm' = g*z ; dmprev += g*(1-z) ; dpre = g*(m' - mprev)*z*(1-z)
+__global__ void gate_bwd_kernel(const float* __restrict__ g, const float* __restrict__ z, const float* __restrict__ mnew,
+                                const float* __restrict__ mprev, float* __restrict__ dmnew, float* __restrict__ dmprev,
+                                float* __restrict__ dpre, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float gi = g[i], zi = z[i];
+  dmnew[i] = gi * zi;
+  dmprev[i] += gi * (1.f - zi);
+  dpre[i] = gi * (mnew[i] - mprev[i]) * zi * (1.f - zi);
+}
+
+// ------------------------------------------------------------------------------------------------ attention backward
+// Backward of mac_control_attend_fwd for ONE batch row per CTA, all `nsteps` query vectors in turn:
+//   d_out_words[s,:] += att_s * g ; datt_s = out_words[s,:] . g ; dlogit = att * (datt - sum att*datt)
+//   d_in_words[s,k] += dlogit_s * q_k * w_k ; dq_k = w_k * sum_s dlogit_s * in[s,k]
+//   dw_part[b,k] += q_k * sum_s dlogit_s * in[s,k] ; db_part[b] += sum_s dlogit_s
+constexpr int AB_THREADS = 256;
+__global__ void __launch_bounds__(AB_THREADS) control_attend_bwd_kernel(
+    const float* __restrict__ cc, long long cc_t, long long cc_b, const float* __restrict__ in_words, long long in_b,
+    long long in_r, const float* __restrict__ out_words, long long out_b, long long out_r,
+    const float* __restrict__ w_logit, const float* __restrict__ att, const float* __restrict__ g_out, long long g_t,
+    long long g_b, float* d_in, float* d_out /* may alias d_in */, float* __restrict__ dq, long long dq_t,
+    long long dq_b, int dq_accum, float* __restrict__ dw_part, float* __restrict__ db_part, int nsteps, int B, int S,
+    int d) {
+  extern __shared__ __align__(16) float ab_smem[];
+  float* s_datt = ab_smem;            // [S]
+  float* s_dl = s_datt + S;           // [S]
+  float* s_att = s_dl + S;            // [S]
+  __shared__ float s_red[AB_THREADS / 32];
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = AB_THREADS / 32;
+  const float* inw = in_words + (size_t)b * in_b;
+  const float* outw = out_words + (size_t)b * out_b;
+  float* din = d_in + (size_t)b * in_b;
+  float* dout = d_out + (size_t)b * out_b;
+  for (int t = 0; t < nsteps; ++t) {
+    const float* q = cc + (size_t)t * cc_t + (size_t)b * cc_b;
+    const float* g = g_out + (size_t)t * g_t + (size_t)b * g_b;
+    const float* a = att + ((size_t)t * B + b) * S;
+    for (int s = tid; s < S; s += AB_THREADS) s_att[s] = a[s];
+    __syncthreads();
+    // datt_s = out_words[s,:] . g     (warp per word row)
+    for (int s = warp; s < S; s += NW) {
+      const float* row = outw + (size_t)s * out_r;
+      float acc = 0.f;
+      for (int k = lane; k < d; k += 32) acc = fmaf(row[k], g[k], acc);
+      acc = warp_sum(acc);
+      if (lane == 0) s_datt[s] = acc;
+    }
+    __syncthreads();
+    float part = 0.f;
+    for (int s = tid; s < S; s += AB_THREADS) part += s_att[s] * s_datt[s];
+    part = warp_sum(part);
+    if (lane == 0) s_red[warp] = part;
+    __syncthreads();
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < NW; ++i) dot += s_red[i];
+    __syncthreads();
+    float dlsum = 0.f;
+    for (int s = tid; s < S; s += AB_THREADS) {
+      const float dl = s_att[s] * (s_datt[s] - dot);
+      s_dl[s] = dl;
+      dlsum += dl;
+    }
+    dlsum = warp_sum(dlsum);
+    if (lane == 0) s_red[warp] = dlsum;
+    __syncthreads();
+    if (tid == 0) {
+      float tsum = 0.f;
+#pragma unroll
+      for (int i = 0; i < NW; ++i) tsum += s_red[i];
+      db_part[b] += tsum;
+    }
+    // column-wise pass: thread per feature k
+    for (int k = tid; k < d; k += AB_THREADS) {
+      const float qk = q[k], wk = __ldg(w_logit + k), gk = g[k];
+      float sx = 0.f;   // sum_s dlogit_s * in[s,k]
+      for (int s = 0; s < S; ++s) {
+        const float dl = s_dl[s];
+        const float x = inw[(size_t)s * in_r + k];
+        sx = fmaf(dl, x, sx);
+        // the two word gradients may alias (control unit: in_words == out_words): update sequentially
+        dout[(size_t)s * out_r + k] += s_att[s] * gk;
+        din[(size_t)s * in_r + k] += dl * qk * wk;
+      }
+      float* o = dq + (size_t)t * dq_t + (size_t)b * dq_b + k;
+      *o = dq_accum ? *o + wk * sx : wk * sx;
+      dw_part[(size_t)b * d + k] += qk * sx;
+    }
+    __syncthreads();
+  }
+}
+
+// dka[b,n] = KB[b,n,:] . dinfo[b,:]        grid (ceil(N/8), B), 256 threads = 8 warps, warp per KB row
+__global__ void __launch_bounds__(256) kb_dot_kernel(const float* __restrict__ kb, const float* __restrict__ dinfo,
+                                                    float* __restrict__ dka, int N, int d) {
+  const int b = blockIdx.y, n = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (n >= N) return;
+  const float4* row = reinterpret_cast<const float4*>(kb + ((size_t)b * N + n) * d);
+  const float4* g = reinterpret_cast<const float4*>(dinfo + (size_t)b * d);
+  float acc = 0.f;
+  for (int k = lane; k < d / 4; k += 32) {
+    const float4 x = __ldg(row + k), y = __ldg(g + k);
+    acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc); acc = fmaf(x.z, y.z, acc); acc = fmaf(x.w, y.w, acc);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) dka[(size_t)b * N + n] = acc;
+}
+
+// softmax backward over the KB + rank-1 KB gradient:  dkl = ka*(dka - sum ka*dka);  dkb[b,n,:] += ka[n]*dinfo[b,:]
+// grid (ceil(N/32), B), 256 threads
+__global__ void __launch_bounds__(256) kb_attend_bwd_kernel(const float* __restrict__ att, const float* __restrict__ dka,
+                                                           const float* __restrict__ dinfo, float* __restrict__ dkl,
+                                                           float* __restrict__ dkb, float* __restrict__ dbr_part, int N,
+                                                           int d) {
+  __shared__ float s_red[8];
+  __shared__ float s_dot;
+  const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* a = att + (size_t)b * N;
+  const float* dk = dka + (size_t)b * N;
+  float part = 0.f;
+  for (int n = tid; n < N; n += 256) part += a[n] * dk[n];
+  part = warp_sum(part);
+  if (lane == 0) s_red[warp] = part;
+  __syncthreads();
+  if (tid == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += s_red[i];
+    s_dot = t;
+  }
+  __syncthreads();
+  const float dot = s_dot;
+  const int n0 = blockIdx.x * 32;
+  if (tid < 32 && n0 + tid < N) dkl[(size_t)b * N + n0 + tid] = a[n0 + tid] * (dk[n0 + tid] - dot);
+  if (blockIdx.x == 0 && dbr_part) {
+    // sum_n dkl = sum ka*dka - dot*sum ka = dot - dot*1 = 0 up to round-off; computed explicitly for fidelity
+    float s = 0.f;
+    for (int n = tid; n < N; n += 256) s += a[n] * (dk[n] - dot);
+    s = warp_sum(s);
+    __syncthreads();
+    if (lane == 0) s_red[warp] = s;
+    __syncthreads();
+    if (tid == 0) {
+      float t = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t += s_red[i];
+      dbr_part[b] += t;
+    }
+  }
+  if (dkb) {
+    const float4* g4 = reinterpret_cast<const float4*>(dinfo + (size_t)b * d);
+    for (int r = 0; r < 32 && n0 + r < N; ++r) {
+      const float an = a[n0 + r];
+      float4* row = reinterpret_cast<float4*>(dkb + ((size_t)b * N + n0 + r) * d);
+      for (int k = tid; k < d / 4; k += 256) {
+        float4 o = row[k];
+        const float4 g = __ldg(g4 + k);
+        o.x = fmaf(an, g.x, o.x); o.y = fmaf(an, g.y, o.y); o.z = fmaf(an, g.z, o.z); o.w = fmaf(an, g.w, o.w);
+        row[k] = o;
+      }
+    }
+  }
+}
+
+// Backward through the logits epilogue of the read unit (mac_cell.py:248-266):
+//   T = I1*c ; I2 = ELU(T) ; I2d = I2*mask*scale ; kl = I2d.wr + br
+//   dI2 = dkl*wr*mask*scale ; dT = dI2*ELU'(T) ; dI1 = dT*c ; dc[b,:] += sum_n dT*I1 ; dwr_part[b,:] += sum_n dkl*I2d
+//   dbm2_part[b,:] += sum_n dI1
+// grid (ceil(d/128), B), 128 threads (column per thread, loop over the sample's N rows)
+__global__ void __launch_bounds__(128) read_bwd_logits_kernel(
+    const float* __restrict__ I1, const float* __restrict__ ctrl, const float* __restrict__ wr,
+    const float* __restrict__ dkl, uint32_t thresh, float scale, uint64_t seed, int step, float* __restrict__ dI1,
+    float* __restrict__ dc, float* __restrict__ dwr_part, float* __restrict__ dbm2_part, int N, int d) {
+  const int k = blockIdx.x * 128 + threadIdx.x, b = blockIdx.y;
+  if (k >= d) return;
+  const float c = ctrl[(size_t)b * d + k], w = __ldg(wr + k);
+  float sdc = 0.f, sdw = 0.f, sdb = 0.f;
+  for (int n = 0; n < N; ++n) {
+    const size_t row = (size_t)b * N + n;
+    const float i1 = I1[row * d + k];
+    const float t = i1 * c;
+    const float i2 = elu_f(t);
+    float m = 1.f;
+    if (thresh) {
+      const uint64_t e = row * (uint64_t)d + (uint64_t)k;
+      const Philox4 r = philox4x32_10(seed, e >> 2, MAC_SITE_READ_INTER, (uint32_t)step);
+      const uint32_t bits = (k & 3) == 0 ? r.x : (k & 3) == 1 ? r.y : (k & 3) == 2 ? r.z : r.w;
+      m = ((bits >> 8) >= thresh) ? scale : 0.f;
+    }
+    const float g = dkl[row];
+    const float dT = g * w * m * (t > 0.f ? 1.f : i2 + 1.f);
+    const float di1 = dT * c;
+    dI1[row * d + k] = di1;
+    sdc = fmaf(dT, i1, sdc);
+    sdw = fmaf(g, i2 * m, sdw);
+    sdb += di1;
+  }
+  dc[(size_t)b * d + k] += sdc;
+  dwr_part[(size_t)b * d + k] += sdw;
+  dbm2_part[(size_t)b * d + k] += sdb;
+}
+
+// dP = dI0[:, :d]*y + dI0[:, d:] ; dy[b,:] = sum_n dI0[:, :d]*P ; dbx_part[b,:] += sum_n dP     (ops.py:694-719)
+__global__ void __launch_bounds__(128) read_bwd_p_kernel(const float* __restrict__ dI0, const float* __restrict__ P,
+                                                        const float* __restrict__ y, float* __restrict__ dP,
+                                                        float* __restrict__ dy, float* __restrict__ dbx_part, int N,
+                                                        int d) {
+  const int k = blockIdx.x * 128 + threadIdx.x, b = blockIdx.y;
+  if (k >= d) return;
+  const float yk = y[(size_t)b * d + k];
+  float sdy = 0.f, sdb = 0.f;
+  for (int n = 0; n < N; ++n) {
+    const size_t row = (size_t)b * N + n;
+    const float top = dI0[row * 2 * d + k], bot = dI0[row * 2 * d + d + k];
+    const float dp = top * yk + bot;
+    dP[row * d + k] = dp;
+    sdy = fmaf(top, P[row * d + k], sdy);
+    sdb += dp;
+  }
+  dy[(size_t)b * d + k] = sdy;
+  dbx_part[(size_t)b * d + k] += sdb;
+}
+
+static int launch_colsum(const float* x, float* out, int B, int N, int d, int accumulate, cudaStream_t stream) {
+  dim3 grid((d + 127) / 128, B);
+  colsum_kernel<<<grid, 128, 0, stream>>>(x, out, N, d, accumulate);
+  MAC_LAUNCH_CHECK();
+  return MAC_OK;
+}
+}  // namespace mac
+
+// ================================================================================================ C ABI
+extern "C" int mac_axpy(float* dst, const float* src, float alpha, long long n, mac_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!dst || !src || n <= 0) return MAC_ERR_INVALID;
+  axpy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(dst, src, alpha, n);
+  MAC_LAUNCH_CHECK();
+  return MAC_OK;
+}
+
+extern "C" int mac_activation_bwd(const float* y, const float* dy, int act, float* dx, long long n, mac_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!y || !dy || !dx || n <= 0) return MAC_ERR_INVALID;
+  act_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(y, dy, act, dx, n);
+  MAC_LAUNCH_CHECK();
+  return MAC_OK;
+}
+
+extern "C" int mac_colsum(const float* x, float* out, int B, int N, int d, int accumulate, mac_stream_t stream_) {
+  if (!x || !out || B <= 0 || N <= 0 || d <= 0) return MAC_ERR_INVALID;
+  return launch_colsum(x, out, B, N, d, accumulate, reinterpret_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int mac_gate_bwd(const float* g, const float* z, const float* mnew, const float* mprev, float* dmnew,
+                            float* dmprev, float* dpre, long long n, mac_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!g || !z || !mnew || !mprev || !dmnew || !dmprev || !dpre || n <= 0) return MAC_ERR_INVALID;
+  gate_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(g, z, mnew, mprev, dmnew, dmprev, dpre, n);
+  MAC_LAUNCH_CHECK();
+  return MAC_OK;
+}
+
+// Backward of ops.linear on concatenated segments (ops.py:298-333):  y = concat(x_s) @ W + b
+//   dx_s (+)= dy @ W[koff_s : koff_s+k_s, :]^T   (needs Wt = W^T [n_out, K], row-major)
+//   dW  += concat(x_s)^T @ dy ;  db += colsum(dy)
+extern "C" int mac_linear_bwd(const float* const* x_segs, const int* k_segs, const int* ldx, int nseg, const float* Wt,
+                              const float* dy, int ldy, float* const* dx_segs, const int* ld_dx, const int* dx_accum,
+                              float* dW, float* db, int M, int n_out, void* workspace, size_t workspace_bytes,
+                              mac_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!x_segs || !k_segs || !dy || nseg < 1 || nseg > 4 || M <= 0 || n_out <= 0) return MAC_ERR_INVALID;
+  char* ws = reinterpret_cast<char*>(workspace);
+  const bool have_ws = ws != nullptr && workspace_bytes > BW_HEADER;
+  unsigned int* counters = have_ws ? reinterpret_cast<unsigned int*>(ws) : nullptr;
+  float* partial = have_ws ? reinterpret_cast<float*>(ws + BW_HEADER) : nullptr;
+  const size_t pbytes = have_ws ? workspace_bytes - BW_HEADER : 0;
+  int K = 0;
+  for (int s = 0; s < nseg; ++s) K += k_segs[s];
+  int koff = 0;
+  for (int s = 0; s < nseg; ++s) {
+    if (dx_segs && dx_segs[s]) {
+      if (!Wt) return MAC_ERR_INVALID;
+      SgemmParams p{};
+      p.a_mode = A_SEGS; p.nseg = 1; p.a[0] = dy; p.ak[0] = n_out; p.lda[0] = ldy;
+      p.W = Wt + koff; p.ldw = K; p.M = M; p.N = k_segs[s]; p.K = n_out;
+      p.epi = EPI_BIAS_ACT; p.act = MAC_ACT_NON; p.Y = dx_segs[s]; p.ldy = ld_dx[s]; p.accumulate = dx_accum ? dx_accum[s] : 0;
+      int st = sgemm_launch(p, counters, partial, pbytes, stream);
+      if (st != MAC_OK) return st;
+    }
+    if (dW) {
+      SgemmParams p{};
+      p.a_mode = A_TRANS; p.nseg = 1; p.a[0] = x_segs[s]; p.lda[0] = ldx[s];
+      p.W = dy; p.ldw = ldy; p.M = k_segs[s]; p.N = n_out; p.K = M;
+      p.epi = EPI_BIAS_ACT; p.act = MAC_ACT_NON; p.Y = dW + (size_t)koff * n_out; p.ldy = n_out; p.accumulate = 1;
+      int st = sgemm_launch(p, counters, partial, pbytes, stream);
+      if (st != MAC_OK) return st;
+    }
+    koff += k_segs[s];
+  }
+  if (db) {
+    if (ldy != n_out) return MAC_ERR_UNSUPPORTED;
+    int st = launch_colsum(dy, db, 1, M, n_out, 1, stream);
+    if (st != MAC_OK) return st;
+  }
+  return MAC_OK;
+}
+
+extern "C" int mac_control_attend_bwd(const float* cc, long long cc_tstride, long long cc_bstride,
+                                      const float* in_words, long long in_bstride, long long in_rstride,
+                                      const float* out_words, long long out_bstride, long long out_rstride,
+                                      const float* w_logit, const float* att, const float* g_out, long long g_tstride,
+                                      long long g_bstride, float* d_in_words, float* d_out_words, float* dq,
+                                      long long dq_tstride, long long dq_bstride, int dq_accumulate, float* dw_part,
+                                      float* db_part, int nsteps, int B, int S, int d, mac_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!cc || !in_words || !out_words || !w_logit || !att || !g_out || !d_in_words || !d_out_words || !dq || !dw_part ||
+      !db_part)
+    return MAC_ERR_INVALID;
+  if (nsteps <= 0 || B <= 0 || S <= 0 || d <= 0) return MAC_ERR_INVALID;
+  const size_t smem = (size_t)3 * S * sizeof(float) + 16;
+  control_attend_bwd_kernel<<<B, AB_THREADS, smem, stream>>>(cc, cc_tstride, cc_bstride, in_words, in_bstride, in_rstride,
+                                                            out_words, out_bstride, out_rstride, w_logit, att, g_out,
+                                                            g_tstride, g_bstride, d_in_words, d_out_words, dq, dq_tstride,
+                                                            dq_bstride, dq_accumulate, dw_part, db_part, nsteps, B, S, d);
+  MAC_LAUNCH_CHECK();
+  return MAC_OK;
+}
+
+extern "C" int mac_kb_attend_bwd(const float* kb, const float* att, const float* dinfo, float* dka_scratch, float* dkl,
+                                 float* dkb, float* dbr_part, int B, int N, int d, mac_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!kb || !att || !dinfo || !dka_scratch || !dkl || B <= 0 || N <= 0 || d <= 0 || (d & 3)) return MAC_ERR_INVALID;
+  kb_dot_kernel<<<dim3((N + 7) / 8, B), 256, 0, stream>>>(kb, dinfo, dka_scratch, N, d);
+  MAC_LAUNCH_CHECK();
+  kb_attend_bwd_kernel<<<dim3((N + 31) / 32, B), 256, 0, stream>>>(att, dka_scratch, dinfo, dkl, dkb, dbr_part, N, d);
+  MAC_LAUNCH_CHECK();
+  return MAC_OK;
+}
+
+// Backward of mac_read_fwd (fp32 path).  `save` = [P | H | I1 | y] from the forward.  Gradients in:
+//   dinfo [B,d].  Gradients out / accumulated:
+//   dkb [B,N,d] += (may be NULL), dmem_in [B,d] = gradient w.r.t. memory_in (the tensor handed to mac_read_fwd),
+//   dcontrol [B,d] +=, parameter gradients += (dWx..dWm2 full; bias / wr gradients as per-sample partials [B,d] that
+//   the caller reduces over B once per backward pass; dbr_part [B]).
+extern "C" size_t mac_read_bwd_workspace_bytes(int B, int N, int d) {
+  const size_t Md = (size_t)B * N * d * 4;
+  return BW_HEADER + 4 * Md /*dI1|dZ, dI0 (2x), dP*/ + (size_t)B * N * 8 + (size_t)4 * B * d * 4 + 4096 +
+         (size_t)32 * 2 * d * d * 4 /*split-K partials of the largest wgrad*/;
+}
+
+extern "C" int mac_read_bwd(const float* kb, const float* memory_in, const float* control, const mac_read_weights* w,
+                            const float* Wx_t, const float* Wy_t, const float* Wm_t, const float* Wm2_t,
+                            const float* att, const float* save, const float* dinfo, float keep_read, uint64_t seed,
+                            int step, float* dkb, float* dmem_in, float* dcontrol, float* dWx, float* dbx_part,
+                            float* dWy, float* dby, float* dWm, float* dbm_part, float* dWm2, float* dbm2_part,
+                            float* dwr_part, float* dbr_part, void* workspace, size_t workspace_bytes, int B, int N,
+                            int d, mac_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!kb || !memory_in || !control || !w || !att || !save || !dinfo || !dmem_in || !dcontrol || !workspace)
+    return MAC_ERR_INVALID;
+  if (workspace_bytes < mac_read_bwd_workspace_bytes(B, N, d)) return MAC_ERR_WORKSPACE;
+  const int M = B * N;
+  const size_t Md = (size_t)M * d;
+  char* ws = reinterpret_cast<char*>(workspace);
+  unsigned int* counters = reinterpret_cast<unsigned int*>(ws);
+  float* f = reinterpret_cast<float*>(ws + BW_HEADER);
+  float* bufA = f;                 // dI1, then dZ (in place is not possible: separate GEMM output) -> dI1 here
+  float* bufB = f + Md;            // dZ
+  float* bufC = f + 2 * Md;        // dI0 [M, 2d]
+  float* dka = f + 4 * Md;         // [B,N]
+  float* dkl = dka + (size_t)B * N;
+  float* dy = dkl + (size_t)B * N; // [B,d]
+  float* md = dy + (size_t)B * d;  // [B,d] recomputed dropped memory
+  float* dmd = md + (size_t)B * d; // [B,d]
+  float* partial = dmd + (size_t)2 * B * d + 1024;
+  const size_t pbytes = workspace_bytes - (reinterpret_cast<char*>(partial) - ws);
+  const float* P = save;
+  const float* H = save + Md;
+  const float* I1 = save + 2 * Md;
+  const float* y = save + 3 * Md;
+  const bool drop = keep_read < 1.f;
+  const uint32_t thr = drop ? keep_threshold(keep_read) : 0u;
+  const float scale = drop ? 1.f / keep_read : 1.f;
+  int st;
+  // (1) info = sum_n att*KB ; att = softmax(kl):  dkl, dKB += att (x) dinfo
+  st = mac_kb_attend_bwd(kb, att, dinfo, dka, dkl, dkb, dbr_part, B, N, d, stream_);
+  if (st != MAC_OK) return st;
+  // (2) logits epilogue backward -> dI1, dcontrol, dwr, dbm2
+  read_bwd_logits_kernel<<<dim3((d + 127) / 128, B), 128, 0, stream>>>(I1, control, w->wr, dkl, thr, scale, seed, step,
+                                                                      bufA, dcontrol, dwr_part, dbm2_part, N, d);
+  MAC_LAUNCH_CHECK();
+  // (3) I1 = H @ Wm2 + bm2:  dWm2 += H^T dI1 ;  dZ = (dI1 @ Wm2^T) * ELU'(Z)
+  if (dWm2) {
+    SgemmParams p{};
+    p.a_mode = A_TRANS; p.nseg = 1; p.a[0] = H; p.lda[0] = d;
+    p.W = bufA; p.ldw = d; p.M = d; p.N = d; p.K = M;
+    p.epi = EPI_BIAS_ACT; p.Y = dWm2; p.ldy = d; p.accumulate = 1;
+    st = sgemm_launch(p, counters, partial, pbytes, stream);
+    if (st != MAC_OK) return st;
+  }
+  {
+    SgemmParams p{};
+    p.a_mode = A_SEGS; p.nseg = 1; p.a[0] = bufA; p.ak[0] = d; p.lda[0] = d;
+    p.W = Wm2_t; p.ldw = d; p.M = M; p.N = d; p.K = d;
+    p.epi = EPI_MUL_ELUGRAD; p.aux = H; p.ldaux = d; p.Y = bufB; p.ldy = d;
+    st = sgemm_launch(p, nullptr, nullptr, 0, stream, false);
+    if (st != MAC_OK) return st;
+  }
+  st = launch_colsum(bufB, dbm_part, B, N, d, 1, stream);
+  if (st != MAC_OK) return st;
+  // (4) Z = [P*y, P] @ Wm + bm:  dWm += I0^T dZ ;  dI0 = dZ @ Wm^T
+  if (dWm) {
+    SgemmParams p{};
+    p.a_mode = A_TRANS_ROWSCALE_CONCAT; p.nseg = 1; p.a[0] = P; p.lda[0] = d; p.rowvec = y; p.rows_per_batch = N;
+    p.W = bufB; p.ldw = d; p.M = 2 * d; p.N = d; p.K = M;
+    p.epi = EPI_BIAS_ACT; p.Y = dWm; p.ldy = d; p.accumulate = 1;
+    st = sgemm_launch(p, counters, partial, pbytes, stream);
+    if (st != MAC_OK) return st;
+  }
+  {
+    SgemmParams p{};
+    p.a_mode = A_SEGS; p.nseg = 1; p.a[0] = bufB; p.ak[0] = d; p.lda[0] = d;
+    p.W = Wm_t; p.ldw = 2 * d; p.M = M; p.N = 2 * d; p.K = d;
+    p.epi = EPI_BIAS_ACT; p.act = MAC_ACT_NON; p.Y = bufC; p.ldy = 2 * d;
+    st = sgemm_launch(p, nullptr, nullptr, 0, stream, false);
+    if (st != MAC_OK) return st;
+  }
+  // (5) I0 = [P*y, P]:  dP, dy, dbx   (dP overwrites bufA)
+  read_bwd_p_kernel<<<dim3((d + 127) / 128, B), 128, 0, stream>>>(bufC, P, y, bufA, dy, dbx_part, N, d);
+  MAC_LAUNCH_CHECK();
+  // (6) P = dropout(KB) @ Wx + bx:  dWx += Kd^T dP ;  dKB += (dP @ Wx^T) * mask/keep
+  if (dWx) {
+    SgemmParams p{};
+    p.a_mode = drop ? A_TRANS_DROPOUT : A_TRANS; p.nseg = 1; p.a[0] = kb; p.lda[0] = d;
+    p.a_thresh = thr; p.a_scale = scale; p.seed = seed; p.a_site = MAC_SITE_READ_KB; p.step = step;
+    p.W = bufA; p.ldw = d; p.M = d; p.N = d; p.K = M;
+    p.epi = EPI_BIAS_ACT; p.Y = dWx; p.ldy = d; p.accumulate = 1;
+    st = sgemm_launch(p, counters, partial, pbytes, stream);
+    if (st != MAC_OK) return st;
+  }
+  if (dkb) {
+    SgemmParams p{};
+    p.a_mode = A_SEGS; p.nseg = 1; p.a[0] = bufA; p.ak[0] = d; p.lda[0] = d;
+    p.W = Wx_t; p.ldw = d; p.M = M; p.N = d; p.K = d;
+    p.epi = EPI_ACCUM_DROPOUT; p.Y = dkb; p.ldy = d;
+    p.e_thresh = thr; p.e_scale = scale; p.e_site = MAC_SITE_READ_KB; p.seed = seed; p.step = step;
+    st = sgemm_launch(p, nullptr, nullptr, 0, stream, false);
+    if (st != MAC_OK) return st;
+  }
+  // (7) y = md @ Wy + by with md = dropout(memory_in):  dWy += md^T dy ; dby += colsum(dy) ; dmem_in = (dy @ Wy^T)*mask/keep
+  const float* mdp = memory_in;
+  if (drop) {
+    st = mac_dropout_fwd(memory_in, keep_read, seed, MAC_SITE_READ_MEM, step, md, (long long)B * d, stream_);
+    if (st != MAC_OK) return st;
+    mdp = md;
+  }
+  {
+    const float* xs[1] = {mdp};
+    const int ks[1] = {d};
+    float* dxs[1] = {drop ? dmd : dmem_in};
+    const int acc0[1] = {0};
+    st = mac_linear_bwd(xs, ks, ks, 1, Wy_t, dy, d, dxs, ks, acc0, dWy, dby, B, d, ws, BW_HEADER + pbytes / 2, stream_);
+    if (st != MAC_OK) return st;
+    if (drop) {
+      st = mac_dropout_fwd(dmd, keep_read, seed, MAC_SITE_READ_MEM, step, dmem_in, (long long)B * d, stream_);
+      if (st != MAC_OK) return st;
+    }
+  }
+  return MAC_OK;
+}

@@ -11,8 +11,12 @@
 
 namespace mac {
 
-enum { A_SEGS = 0, A_ROWSCALE_CONCAT = 1, A_DROPOUT = 2 };
-enum { EPI_BIAS_ACT = 0, EPI_READ_LOGITS = 1, EPI_GATE = 2 };
+enum { A_SEGS = 0, A_ROWSCALE_CONCAT = 1, A_DROPOUT = 2,
+       // transposed views for weight gradients dW[K_in, N] = X^T[K_in, rows] @ dY[rows, N]: A(m, k) = X[k][m]
+       A_TRANS = 3, A_TRANS_ROWSCALE_CONCAT = 4, A_TRANS_DROPOUT = 5 };
+enum { EPI_BIAS_ACT = 0, EPI_READ_LOGITS = 1, EPI_GATE = 2,
+       EPI_MUL_ELUGRAD = 3,     // Y = acc * ELU'(aux) with aux = ELU(z) saved from forward: aux > 0 ? 1 : aux + 1
+       EPI_ACCUM_DROPOUT = 4 }; // Y += acc * keep-mask(m, n) * scale   (gradient through tf.nn.dropout)
 
 struct SgemmParams {
   // ---- A view
@@ -39,6 +43,9 @@ struct SgemmParams {
   int act;
   float* Y;              // EPI_BIAS_ACT / EPI_GATE output; EPI_READ_LOGITS: optional I1 store (may be NULL)
   int ldy;
+  int accumulate;        // EPI_BIAS_ACT: Y += result (parameter-gradient accumulation over the steps)
+  const float* aux;      // EPI_MUL_ELUGRAD: saved activation [M, ldaux]
+  int ldaux;
   // EPI_READ_LOGITS: t = (acc+bias)*ctrl[b]; i2 = elu(t) (dropout) ; parts[m, blockIdx.x] = sum_n i2*wr[n]
   const float* ctrl;
   const float* wr;
@@ -91,6 +98,33 @@ __device__ __forceinline__ float4 sg_load_a(const SgemmParams& p, int m, int k) 
   return v;
 }
 
+// transposed view: four consecutive m (feature index) of row k of X
+__device__ __forceinline__ float4 sg_load_at(const SgemmParams& p, int m, int k) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (m >= p.M || k >= p.K) return v;
+  if (p.a_mode == A_TRANS) {
+    v = __ldg(reinterpret_cast<const float4*>(p.a[0] + (size_t)k * p.lda[0] + m));
+  } else if (p.a_mode == A_TRANS_ROWSCALE_CONCAT) {
+    const int half = p.M >> 1;
+    if (m < half) {
+      v = __ldg(reinterpret_cast<const float4*>(p.a[0] + (size_t)k * p.lda[0] + m));
+      const float4 y = __ldg(reinterpret_cast<const float4*>(p.rowvec + (size_t)(k / p.rows_per_batch) * half + m));
+      v.x *= y.x; v.y *= y.y; v.z *= y.z; v.w *= y.w;
+    } else {
+      v = __ldg(reinterpret_cast<const float4*>(p.a[0] + (size_t)k * p.lda[0] + (m - half)));
+    }
+  } else {  // A_TRANS_DROPOUT
+    v = __ldg(reinterpret_cast<const float4*>(p.a[0] + (size_t)k * p.lda[0] + m));
+    const uint64_t e = (uint64_t)k * (uint64_t)p.M + (uint64_t)m;
+    const Philox4 r = philox4x32_10(p.seed, e >> 2, (uint32_t)p.a_site, (uint32_t)p.step);
+    v.x = ((r.x >> 8) >= p.a_thresh) ? v.x * p.a_scale : 0.f;
+    v.y = ((r.y >> 8) >= p.a_thresh) ? v.y * p.a_scale : 0.f;
+    v.z = ((r.z >> 8) >= p.a_thresh) ? v.z * p.a_scale : 0.f;
+    v.w = ((r.w >> 8) >= p.a_thresh) ? v.w * p.a_scale : 0.f;
+  }
+  return v;
+}
+
 template <int BM, int BN>
 __global__ void __launch_bounds__(256) sgemm_kernel(const SgemmParams p) {
   constexpr int BK = 16;
@@ -125,8 +159,13 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const SgemmParams p) {
 #pragma unroll
     for (int i = 0; i < A_F4; ++i) {
       const int f = tid + i * 256;
-      const int row = f >> 2, kq = f & 3;
-      ra[i] = sg_load_a(p, m0 + row, k0 + kq * 4);
+      if (p.a_mode >= A_TRANS) {
+        const int kr = f / (BM / 4), m4 = f % (BM / 4);
+        ra[i] = sg_load_at(p, m0 + m4 * 4, k0 + kr);
+      } else {
+        const int row = f >> 2, kq = f & 3;
+        ra[i] = sg_load_a(p, m0 + row, k0 + kq * 4);
+      }
     }
 #pragma unroll
     for (int i = 0; i < B_F4; ++i) {
@@ -141,11 +180,16 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const SgemmParams p) {
 #pragma unroll
     for (int i = 0; i < A_F4; ++i) {
       const int f = tid + i * 256;
-      const int row = f >> 2, kq = f & 3;
-      As[buf][kq * 4 + 0][row] = ra[i].x;
-      As[buf][kq * 4 + 1][row] = ra[i].y;
-      As[buf][kq * 4 + 2][row] = ra[i].z;
-      As[buf][kq * 4 + 3][row] = ra[i].w;
+      if (p.a_mode >= A_TRANS) {
+        const int kr = f / (BM / 4), m4 = f % (BM / 4);
+        *reinterpret_cast<float4*>(&As[buf][kr][m4 * 4]) = ra[i];
+      } else {
+        const int row = f >> 2, kq = f & 3;
+        As[buf][kq * 4 + 0][row] = ra[i].x;
+        As[buf][kq * 4 + 1][row] = ra[i].y;
+        As[buf][kq * 4 + 2][row] = ra[i].z;
+        As[buf][kq * 4 + 3][row] = ra[i].w;
+      }
     }
 #pragma unroll
     for (int i = 0; i < B_F4; ++i) {
@@ -254,7 +298,51 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const SgemmParams p) {
           if (p.bias) t += __ldg(p.bias + n + q);
           v[q] = apply_act(p.act, t);
         }
-        *reinterpret_cast<float4*>(p.Y + (size_t)m * p.ldy + n) = make_float4(v[0], v[1], v[2], v[3]);
+        float4* dst = reinterpret_cast<float4*>(p.Y + (size_t)m * p.ldy + n);
+        if (p.accumulate) {
+          const float4 o = *dst;
+          v[0] += o.x; v[1] += o.y; v[2] += o.z; v[3] += o.w;
+        }
+        *dst = make_float4(v[0], v[1], v[2], v[3]);
+      }
+    }
+  } else if (p.epi == EPI_MUL_ELUGRAD) {
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+      const int m = row_of(i);
+      if (m >= p.M) continue;
+#pragma unroll
+      for (int j = 0; j < TN; j += 4) {
+        const int n = col_of(j);
+        if (n >= p.N) continue;
+        const float4 h = __ldg(reinterpret_cast<const float4*>(p.aux + (size_t)m * p.ldaux + n));
+        *reinterpret_cast<float4*>(p.Y + (size_t)m * p.ldy + n) =
+            make_float4(acc[i][j] * (h.x > 0.f ? 1.f : h.x + 1.f), acc[i][j + 1] * (h.y > 0.f ? 1.f : h.y + 1.f),
+                        acc[i][j + 2] * (h.z > 0.f ? 1.f : h.z + 1.f), acc[i][j + 3] * (h.w > 0.f ? 1.f : h.w + 1.f));
+      }
+    }
+  } else if (p.epi == EPI_ACCUM_DROPOUT) {
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+      const int m = row_of(i);
+      if (m >= p.M) continue;
+#pragma unroll
+      for (int j = 0; j < TN; j += 4) {
+        const int n = col_of(j);
+        if (n >= p.N) continue;
+        uint32_t bits[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+        if (p.e_thresh) {
+          const uint64_t e = (uint64_t)m * (uint64_t)p.N + (uint64_t)n;
+          const Philox4 r = philox4x32_10(p.seed, e >> 2, (uint32_t)p.e_site, (uint32_t)p.step);
+          bits[0] = r.x; bits[1] = r.y; bits[2] = r.z; bits[3] = r.w;
+        }
+        float4* dst = reinterpret_cast<float4*>(p.Y + (size_t)m * p.ldy + n);
+        float4 o = *dst;
+        o.x += ((bits[0] >> 8) >= p.e_thresh) ? acc[i][j] * p.e_scale : 0.f;
+        o.y += ((bits[1] >> 8) >= p.e_thresh) ? acc[i][j + 1] * p.e_scale : 0.f;
+        o.z += ((bits[2] >> 8) >= p.e_thresh) ? acc[i][j + 2] * p.e_scale : 0.f;
+        o.w += ((bits[3] >> 8) >= p.e_thresh) ? acc[i][j + 3] * p.e_scale : 0.f;
+        *dst = o;
       }
     }
   } else if (p.epi == EPI_GATE) {
@@ -328,6 +416,7 @@ inline int sgemm_launch(SgemmParams p, unsigned int* counters, float* partial, s
   if (p.M <= 0 || p.N <= 0 || p.K <= 0) return MAC_ERR_INVALID;
   if ((p.N & 3) || (p.K & 3)) return MAC_ERR_INVALID;
   if (allow_splitk && skinny_ok(p) && !getenv("MAC_NO_SKINNY")) return skinny_launch(p, stream);   // M <= 64: cluster/DSMEM split-K kernel
+  if (p.a_mode >= A_TRANS && (p.M & 3)) return MAC_ERR_INVALID;
   const bool big = (p.M >= 512);
   const int BM = big ? 128 : 64, BN = big ? 128 : 64;
   dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, 1);

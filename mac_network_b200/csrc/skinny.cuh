@@ -16,7 +16,7 @@ namespace cg = cooperative_groups;
 constexpr int SK_CLUSTER = 8;
 constexpr int SK_BM = 64, SK_BN = 32, SK_THREADS = 128;
 
-__global__ void __launch_bounds__(SK_THREADS) skinny_gemm_kernel(const SgemmParams p, int ks, int dbg) {
+static __global__ void __launch_bounds__(SK_THREADS) skinny_gemm_kernel(const SgemmParams p, int ks, int dbg) {
   extern __shared__ __align__(16) float sk_smem[];
   constexpr int XLD = SK_BM + 4;                // 16-byte aligned rows of the transposed A slice
   float* ws = sk_smem;                          // [ks][SK_BN]       W slice
@@ -119,7 +119,8 @@ __global__ void __launch_bounds__(SK_THREADS) skinny_gemm_kernel(const SgemmPara
         if (p.gate_z) p.gate_z[o] = z;
         p.Y[o] = p.gnew[o] * z + p.gold[o] * (1.f - z);
       } else {
-        p.Y[o] = apply_act(p.act, t);
+        t = apply_act(p.act, t);
+        p.Y[o] = p.accumulate ? p.Y[o] + t : t;
       }
     }
   }
@@ -128,7 +129,7 @@ __global__ void __launch_bounds__(SK_THREADS) skinny_gemm_kernel(const SgemmPara
 
 // usable when M <= 64, K splits evenly into 8 slices of whole float4s, and the slice fits in shared memory
 inline bool skinny_ok(const SgemmParams& p) {
-  if (p.M > SK_BM || p.epi == EPI_READ_LOGITS || p.a_mode != A_SEGS) return false;
+  if (p.M > SK_BM || (p.epi != EPI_BIAS_ACT && p.epi != EPI_GATE) || p.a_mode != A_SEGS) return false;
   if (p.K % (SK_CLUSTER * 4)) return false;
   const int ks = p.K / SK_CLUSTER;
   if (ks > 256) return false;

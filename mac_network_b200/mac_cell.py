@@ -108,7 +108,7 @@ class MACCell(object):
 
     def __init__(self, vecQuestions, questionWords, questionCntxWords, questionLengths, knowledgeBase,
                  memoryDropout, readDropout, writeDropout, batchSize, train, reuse=None, *,
-                 config=None, params=None, prec="fp32", seed=0):
+                 config=None, params=None, prec="fp32", seed=0, save_for_backward=False):
         self.lib = _lib.load()
         self.cfg = config if config is not None else _defaults["config"]
         self.params = params if params is not None else _defaults["params"]
@@ -152,6 +152,9 @@ class MACCell(object):
         self._hoist = not (c.controlFeedPrev or c.controlWholeQ or c.controlContinuous)
         self._rw = {}
         self.kb_bf16 = None
+        self.save_for_backward = bool(save_for_backward)
+        if self.save_for_backward and self.prec != PREC["fp32"]:
+            raise NotImplementedError("backward is implemented on the fp32 path (DESIGN.md section 9)")
 
     # ------------------------------------------------------------------ reference properties
     @property
@@ -221,6 +224,13 @@ class MACCell(object):
             check(self.lib.mac_cast_bf16(ptr(self.knowledgeBase), ptr(self.kb_bf16), self.knowledgeBase.numel(),
                                          stream_ptr()), "mac_cast_bf16")
         self._mem_in = self._new(B, d)
+        if self.save_for_backward:
+            M = B * self.N
+            self._save = [self._new(3 * M * d + B * d) for _ in range(L)]      # [P | H | I1 | y] per step
+            self._mem_in_hist = self._new(L, B, d)
+            self._mnew = self._new(L, B, d) if c.writeGate else None
+            self._ss = self._new(L, B, d) if c.writeSelfAtt else None
+            self._sc = self._new(L, B, d) if c.writeSelfAtt else None
         if self._hoist:
             self._control_all_steps()
         return MACCellTuple(c0, m0)
@@ -235,6 +245,7 @@ class MACCell(object):
         """u = act(linear_qInput(vecQuestions)) (mac_cell.py:442-445): weights shared over steps => once per forward."""
         W, b = self.params.lin("MACCell/", "qInput")
         u = self._linear([self.vecQuestions], W, b, self._new(self.B, self.d), act=self.cfg.controlInputAct)
+        self._u_saved = u
         return u
 
     def _control_all_steps(self):
@@ -322,6 +333,9 @@ class MACCell(object):
                 memory = self._dropout(memory, keep_m, _lib.SITE_MEM_PLAIN, i, self._mem_in)
         att = _att_out if _att_out is not None else self._new(B, N)
         info = _out if _out is not None else self._new(B, d)
+        if self.save_for_backward and _save is None:
+            _save = self._save[i]
+            self._mem_in_hist[i].copy_(memory)
         rw = self._read_weights(name)
         check(self.lib.mac_read_fwd(ptr(knowledgeBase), ptr(self.kb_bf16), ptr(memory), ptr(control),
                                     ctypes.byref(rw), float(self.dropouts["read"]), self.seed, i, self.prec,
@@ -340,10 +354,11 @@ class MACCell(object):
         if c.writeSelfAtt:
             selfControl = contControl if c.writeSelfAttMod == "CONT" else control
             W, b = self.params.lin(sc, "ctrlProj")
-            selfControl = self._linear([selfControl], W, b, self._new(B, d))
+            keep = self.save_for_backward
+            selfControl = self._linear([selfControl], W, b, self._sc[i] if keep else self._new(B, d))
             lsc = sc + "inter2attselfAttention/inter2logits/linearLayerlogits/"
             att = self._new(B, i + 1)
-            selfSmry = self._new(B, d)
+            selfSmry = self._ss[i] if keep else self._new(B, d)
             # interactions = controls * selfControl; attention over the i+1 history rows; summary of memories
             self._attend(selfControl, 0, selfControl.stride(0), self._hc, d, B * d, self._hm, d, B * d, None,
                          self.params[lsc + "weights/weight"], self.params.scalar(lsc + "biases/bias"), att, selfSmry,
@@ -359,6 +374,9 @@ class MACCell(object):
         check(self.lib.mac_write_fwd(ptr(memory), ptr(info), ptr(selfSmry), ptr(control), ptr(Ww), ptr(bw), ptr(Wg),
                                      ptr(bg), float(c.writeGateBias), ptr(out), ptr(gate), ptr(self.ws.write),
                                      self.ws.write_bytes, B, d, stream_ptr()), "mac_write_fwd")
+        if self.save_for_backward and c.writeGate:
+            # the pre-gate memory m' is the first [B,d] block of the write workspace after its 4 KB header
+            self._mnew[i].copy_(self.ws.write[4096:4096 + B * d * 4].view(torch.float32).view(B, d))
         if c.writeGate:
             self.attentions["gate"].append(gate)
         return out

@@ -76,3 +76,16 @@ def test_torch_cpu_port_matches_oracle(variant):
                            torch.from_numpy(inp["questionLengths"]).long(), torch.from_numpy(inp["knowledgeBase"]).float())
     assert np.max(np.abs(c.numpy() - ref.control)) / np.max(np.abs(ref.control)) < 1e-5
     assert np.max(np.abs(m.numpy() - ref.memory)) / np.max(np.abs(ref.memory)) < 1e-5
+
+
+@pytest.mark.parametrize("case", ["args_train_small", "gqa_train_small", "args4_small"])
+def test_torch_autograd_restatement_matches_reference_fixture(case):
+    """The differentiable fp64 torch restatement (gradient oracle) reproduces the reference fixtures' forward."""
+    from oracle import mac_torch_autograd as TA
+    meta, gold = load_golden(case)
+    cfg, inputs, params = rebuild(meta, np.float64)
+    dp = meta["dropouts"]
+    c, m, _ = TA.run(cfg, params, inputs, meta["shape"]["L"], (dp["memory"], dp["read"], dp["write"]),
+                     uniforms_of(meta, gold))
+    assert np.max(np.abs(m - gold["final_memory"])) < 1e-11
+    assert np.max(np.abs(c - gold["final_control"])) < 1e-11
