@@ -393,7 +393,7 @@ extern "C" int mac_kb_attend_bwd(const float* kb, const float* att, const float*
 //   the caller reduces over B once per backward pass; dbr_part [B]).
 extern "C" size_t mac_read_bwd_workspace_bytes(int B, int N, int d) {
   const size_t Md = (size_t)B * N * d * 4;
-  return BW_HEADER + 4 * Md /*dI1|dZ, dI0 (2x), dP*/ + (size_t)B * N * 8 + (size_t)4 * B * d * 4 + 4096 +
+  return BW_HEADER + 4 * Md /*dI1|dZ, dI0 (2x), dP*/ + ((size_t)B * N + 4) * 8 + (size_t)4 * B * d * 4 + 4096 +
          (size_t)32 * 2 * d * d * 4 /*split-K partials of the largest wgrad*/;
 }
 
@@ -417,8 +417,9 @@ extern "C" int mac_read_bwd(const float* kb, const float* memory_in, const float
   float* bufB = f + Md;            // dZ
   float* bufC = f + 2 * Md;        // dI0 [M, 2d]
   float* dka = f + 4 * Md;         // [B,N]
-  float* dkl = dka + (size_t)B * N;
-  float* dy = dkl + (size_t)B * N; // [B,d]
+  const size_t BNp = ((size_t)B * N + 3) & ~(size_t)3;   // keep the [B,d] buffers behind it 16-byte aligned
+  float* dkl = dka + BNp;
+  float* dy = dkl + BNp;           // [B,d]
   float* md = dy + (size_t)B * d;  // [B,d] recomputed dropped memory
   float* dmd = md + (size_t)B * d; // [B,d]
   float* partial = dmd + (size_t)2 * B * d + 1024;
