@@ -416,6 +416,83 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_train(args):
+    """Data-parallel TRAINING step of the cell (BASELINE.json configs[3]): forward with train-mode dropouts + hand-written
+    backward + NCCL all-reduce of the flat gradient bucket + fused clip/Adam/EMA, B=64 per GPU (weak scaling), fp32 path."""
+    from mac_network_b200 import _lib
+    from mac_network_b200.dp import DPTrainer
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = _lib.load()
+    shape = SHAPES[WORKLOAD]
+    B, S, N, d, L = shape
+    cfg = MACConfig.args("args", netLength=L)
+    pv = perturb_biases(init_params(cfg, L, seed=100), seed=101)
+    tr = DPTrainer(cfg, L, param_values=pv, seed=7, rank=rank, world=world)
+    nslots = 4
+    batches, probes = [], []
+    for s_ in range(nslots):
+        inp = make_inputs(B, S, N, d, seed=1234 + 1000 * rank + s_)
+        batches.append({k: torch.from_numpy(v).cuda() for k, v in inp.items()})
+        g = torch.Generator(device="cuda").manual_seed(99 + 17 * rank + s_)
+        probes.append((torch.randn(B, d, device="cuda", generator=g), torch.randn(B, d, device="cuda", generator=g)))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one(k):
+        sl = k % nslots
+        tr.train_step(sl, batches[sl], probes[sl][0], probes[sl][1], B * world)
+
+    for w in range(args.warmup):
+        one(w)
+    barrier()
+    n0 = lib.mac_b200_launch_count()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(args.steps):
+        one(k)
+    e1.record()
+    barrier()
+    t_dev = e0.elapsed_time(e1) * 1e-3
+    launches = lib.mac_b200_launch_count() - n0
+    clocks = sampler.stop() if rank == 0 else None
+    if dist is not None:
+        tt = torch.tensor([t_dev], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_dev = float(tt[0])
+    if rank == 0:
+        value = args.steps * L * world / t_dev
+        nparam = tr.params.numel
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "BASELINE.json configs[3]: DP training of the args.txt cell, B=%d per GPU (global %d), "
+                                       "S=%d, N=%d, d=%d, netLength=%d; dropouts memory/read/write = %s"
+                                       % (B, B * world, S, N, d, L, str(tr.dropouts)),
+                           "step": "forward + hand-written backward + all-reduce(%d fp32 = %.1f MB) + clip/Adam/EMA; "
+                                   "%d reasoning steps" % (nparam, nparam * 4 / 1e6, L),
+                           "l2": "timed steps rotate over %d resident batches per rank; activations saved for backward "
+                                 "(%.0f MB per step) exceed L2" % (nslots, L * 3 * B * N * d * 4 / 1e6),
+                           "cuda_graph": False, "projections": "fp32", "parallelism": "dp%d, NCCL all-reduce per step" % world},
+                "sample_steps_per_sec": value * B, "gpu_launches": int(launches), "clocks": clocks,
+                "e2e": None, "roofline": None, "cpu_baseline": None}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -461,6 +538,7 @@ def main():
     ap.add_argument("--prec", default="bf16", choices=["fp32", "bf16"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--mode", default="infer", choices=["infer", "train"])
     ap.add_argument("--rooflines-only", action="store_true", help="only the per-kernel measurements (for ncu)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -469,6 +547,8 @@ def main():
         print(json.dumps(kernel_rooflines(SHAPES[WORKLOAD], args.prec, peaks())))
     elif args.impl == "reference":
         run_reference(args)
+    elif args.mode == "train":
+        run_train(args)
     else:
         run_ours(args)
 

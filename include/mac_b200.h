@@ -207,6 +207,17 @@ int mac_colsum(const float* x, float* out, int B, int N, int d, int accumulate, 
 /* dst += alpha * src */
 int mac_axpy(float* dst, const float* src, float alpha, long long n, mac_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Training step on a flat fp32 bucket (the buffer NCCL all-reduces in data-parallel training):
+ *   g' = grads * grad_scale;  norm = ||g'||;  g'' = g' * max_norm / max(norm, max_norm)   (tf.clip_by_global_norm, model.py:645-650)
+ *   Adam with TF's bias-corrected step size (model.py:618);  ema = decay*ema + (1-decay)*p   (model.py:658-667; ema may be NULL)
+ * norm_out[0] = global norm, norm_out[1] = clip factor (device memory, no host sync).  step >= 1.
+ * --------------------------------------------------------------------------------------------- */
+int mac_clip_adam_ema_step(float* params, const float* grads, float* adam_m, float* adam_v, float* ema, long long n,
+                           float grad_scale, float max_norm, float lr, float beta1, float beta2, float eps, int step,
+                           float ema_decay, float* norm_out, void* workspace, size_t workspace_bytes, mac_stream_t stream);
+size_t mac_optimizer_workspace_bytes(void);
+
 /* dropout sites (the `site` word of the Philox counter) */
 enum { MAC_SITE_MEM_VAR = 0, MAC_SITE_READ_KB = 1, MAC_SITE_READ_MEM = 2, MAC_SITE_READ_INTER = 3,
        MAC_SITE_WRITE_INFO = 4, MAC_SITE_MEM_PLAIN = 5 };

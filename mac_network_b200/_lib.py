@@ -65,6 +65,9 @@ PROTOTYPES = {
     "mac_activation_bwd": (c_int, [c_fp, c_fp, c_int, c_fp, c_ll, c_fp]),
     "mac_colsum": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_int, c_fp]),
     "mac_axpy": (c_int, [c_fp, c_fp, c_f, c_ll, c_fp]),
+    "mac_clip_adam_ema_step": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_ll, c_f, c_f, c_f, c_f, c_f, c_f, c_int, c_f, c_fp, c_fp,
+                                       c_sz, c_fp]),
+    "mac_optimizer_workspace_bytes": (c_sz, []),
     "mac_pack_weight_bf16": (c_int, [c_fp, c_fp, c_int, c_int, c_fp]),
     "mac_linear_tc_fwd": (c_int, [c_fp, c_fp, c_fp, c_int, c_fp, c_int, c_int, c_int, c_fp]),
 }

@@ -27,7 +27,7 @@ def _t(params, W, key):
 
 
 class _Bwd(object):
-    def __init__(self, cell):
+    def __init__(self, cell, bucket=None):
         self.cell, self.lib = cell, cell.lib
         self.p = cell.params
         c = cell.cfg
@@ -37,11 +37,20 @@ class _Bwd(object):
         dev = cell.device
         self.z = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)
         self.e = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
-        self.g = collections.OrderedDict((k, torch.zeros_like(v)) for k, v in self.p.t.items())
-        self.ws_bytes = int(self.lib.mac_read_bwd_workspace_bytes(self.B, self.N, self.d))
-        self.ws = torch.zeros(self.ws_bytes, dtype=torch.uint8, device=dev)
-        self.lws_bytes = 4096 + 32 * 1536 * 512 * 4
-        self.lws = torch.zeros(self.lws_bytes, dtype=torch.uint8, device=dev)
+        # parameter gradients are views into ONE flat bucket laid out like MACParams.flat (what NCCL all-reduces)
+        from .mac_cell import views_of
+        self.bucket = bucket if bucket is not None else torch.zeros_like(self.p.flat)
+        if bucket is not None:
+            self.bucket.zero_()
+        self.g = views_of(self.bucket, self.p.specs, self.p.offsets)
+        cache = getattr(cell, "_bwd_ws", None)            # scratch is allocated once per cell and reused every step
+        if cache is None:
+            ws_bytes = int(self.lib.mac_read_bwd_workspace_bytes(self.B, self.N, self.d))
+            lws_bytes = 4096 + 32 * 1536 * 512 * 4
+            cache = (ws_bytes, torch.zeros(ws_bytes, dtype=torch.uint8, device=dev), lws_bytes,
+                     torch.zeros(lws_bytes, dtype=torch.uint8, device=dev))
+            cell._bwd_ws = cache
+        self.ws_bytes, self.ws, self.lws_bytes, self.lws = cache
 
     def G(self, name):
         return self.g[PREFIX + name]
@@ -210,8 +219,8 @@ class _Bwd(object):
         return out
 
 
-def mac_backward(cell, d_control, d_memory):
+def mac_backward(cell, d_control, d_memory, bucket=None):
     """Gradients of sum(d_control * control_L) + sum(d_memory * memory_L) w.r.t. every cell parameter and input."""
     if not getattr(cell, "save_for_backward", False):
         raise RuntimeError("construct the MACCell with save_for_backward=True and run the forward first")
-    return _Bwd(cell).run(d_control, d_memory)
+    return _Bwd(cell, bucket).run(d_control, d_memory)

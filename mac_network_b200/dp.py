@@ -1,0 +1,107 @@
+"""Data-parallel training of the MAC cell: one process per GPU, the batch sharded over ranks, ONE collective per step.
+
+The reference's multi-GPU path is a stub (towers >= 1 are ignored, `model.py:671-679`), so there is nothing to match
+except single-process semantics: the all-reduced gradient of the global-mean loss must equal the 1-process gradient on
+the concatenated batch.  Per step:
+    forward (train-mode dropouts, per-rank Philox streams) -> hand-written backward into the flat gradient bucket ->
+    `all_reduce(SUM)` of the bucket over NCCL/NVLink -> global-norm clip, Adam, EMA fused in one kernel (replicated).
+The loss of this cell-level harness is a linear probe of the final state, sum(memory_L * t_m + control_L * t_c) / B_global,
+standing in for the out-of-scope output unit / classifier (it supplies dL/dmemory and dL/dcontrol exactly as they would).
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, ptr, stream_ptr
+
+
+def shard_rows(global_batch, rank, world):
+    """Rank r takes samples [r*B/world, (r+1)*B/world) of the global batch (mirrors initTowerBatch, model.py:139-149)."""
+    if global_batch % world:
+        raise ValueError("global batch %d is not divisible by world size %d" % (global_batch, world))
+    per = global_batch // world
+    return slice(rank * per, (rank + 1) * per)
+
+
+def allreduce_sum_(bucket, group=None):
+    """The path's only exchange step.  Returns the bucket (summed over ranks in place)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(bucket, op=dist.ReduceOp.SUM, group=group)
+    return bucket
+
+
+class DPTrainer(object):
+    def __init__(self, cfg, netLength, param_values=None, seed=0, rank=0, world=1, lr=1e-4, clip=8.0, ema_decay=0.999,
+                 beta1=0.9, beta2=0.999, eps=1e-8, dropouts=None, device="cuda"):
+        from .mac_cell import MACParams
+        self.cfg, self.L, self.rank, self.world = cfg, netLength, rank, world
+        self.lib = _lib.load()
+        self.params = MACParams(cfg, netLength, values=param_values, seed=seed, device=device)   # replicated
+        n = self.params.numel
+        z = lambda: torch.zeros(n, dtype=torch.float32, device=self.params.device)
+        self.bucket, self.adam_m, self.adam_v = z(), z(), z()
+        self.ema = self.params.flat.clone()
+        self.norm = torch.zeros(2, dtype=torch.float32, device=self.params.device)
+        self.ows_bytes = int(self.lib.mac_optimizer_workspace_bytes())
+        self.ows = torch.zeros(self.ows_bytes, dtype=torch.uint8, device=self.params.device)
+        self.hp = dict(lr=lr, clip=clip, ema=ema_decay, b1=beta1, b2=beta2, eps=eps)
+        self.dropouts = dropouts or (cfg.memoryDropout, cfg.readDropout, cfg.writeDropout)
+        self.step_id = 0
+        self.base_seed = seed
+        self._cells = {}
+
+    def cell_for(self, key, batch):
+        from .mac_cell import MACCell
+        if key not in self._cells:
+            dm, dr, dw = self.dropouts
+            self._cells[key] = MACCell(batch["vecQuestions"], batch["questionWords"], batch["questionCntxWords"],
+                                       batch["questionLengths"], batch["knowledgeBase"], dm, dr, dw,
+                                       batch["knowledgeBase"].shape[0], True, config=self.cfg, params=self.params,
+                                       save_for_backward=True)
+        return self._cells[key]
+
+    def grads(self, key, batch, t_control, t_memory, global_batch):
+        """Forward + backward of the local shard into the flat bucket (not yet reduced)."""
+        from .autograd import mac_backward
+        from .mac_cell import mac_network
+        cell = self.cell_for(key, batch)
+        cell._rw.clear()
+        # per-(step, rank) dropout stream: masks differ across ranks and steps, reproducibly
+        cell.seed = (self.base_seed * 1000003 + self.step_id * 7919 + self.rank * 104729 + 1) & 0x7FFFFFFFFFFFFFFF
+        control, memory = mac_network(cell, self.L)
+        scale = 1.0 / float(global_batch)
+        g = mac_backward(cell, None if t_control is None else t_control * scale,
+                         None if t_memory is None else t_memory * scale, bucket=self.bucket)
+        return control, memory, g
+
+    def apply(self):
+        """all-reduce the bucket, then clip + Adam + EMA (model.py:645-667) in one fused pass; refresh derived weights."""
+        allreduce_sum_(self.bucket)
+        self.step_id += 1
+        h = self.hp
+        check(self.lib.mac_clip_adam_ema_step(ptr(self.params.flat), ptr(self.bucket), ptr(self.adam_m), ptr(self.adam_v),
+                                              ptr(self.ema), self.params.numel, 1.0, h["clip"], h["lr"], h["b1"], h["b2"],
+                                              h["eps"], self.step_id, h["ema"], ptr(self.norm), ptr(self.ows),
+                                              self.ows_bytes, stream_ptr()), "mac_clip_adam_ema_step")
+        self.params.touch()
+
+    def train_step(self, key, batch, t_control, t_memory, global_batch):
+        control, memory, _ = self.grads(key, batch, t_control, t_memory, global_batch)
+        self.apply()
+        return control, memory
+
+
+def adam_reference(p, g, m, v, ema, step, lr=1e-4, clip=8.0, b1=0.9, b2=0.999, eps=1e-8, ema_decay=0.999):
+    """numpy restatement of the fused step (tests): tf.clip_by_global_norm + tf.train.AdamOptimizer + EMA.apply."""
+    p, g, m, v, ema = (np.asarray(a, np.float64) for a in (p, g, m, v, ema))
+    norm = np.sqrt(np.sum(g * g))
+    g = g * (clip / max(norm, clip))
+    m = b1 * m + (1 - b1) * g
+    v = b2 * v + (1 - b2) * g * g
+    lr_t = lr * np.sqrt(1 - b2 ** step) / (1 - b1 ** step)
+    p = p - lr_t * m / (np.sqrt(v) + eps)
+    ema = ema_decay * ema + (1 - ema_decay) * p
+    return p, m, v, ema, norm

@@ -42,6 +42,26 @@ def set_defaults(config=None, params=None):
         _defaults["params"] = params
 
 
+def flat_layout(specs):
+    """name -> element offset of each variable in the flat parameter / gradient bucket (+ "__total__")."""
+    off, out = 0, {}
+    for name, (shape, _) in specs.items():
+        out[name] = off
+        n = int(np.prod(shape)) if shape else 1
+        off += (n + 63) // 64 * 64
+    out["__total__"] = off
+    return out
+
+
+def views_of(flat, specs, offsets):
+    """Per-variable views into a flat buffer laid out by `flat_layout`."""
+    out = collections.OrderedDict()
+    for name, (shape, _) in specs.items():
+        n = int(np.prod(shape)) if shape else 1
+        out[name] = flat[offsets[name]:offsets[name] + n].view(shape if shape else (1,))
+    return out
+
+
 class MACParams(object):
     """Cell parameters on the device, keyed by the reference's TF variable names."""
 
@@ -55,11 +75,18 @@ class MACParams(object):
         if missing:
             raise KeyError("missing parameters: %s" % sorted(missing)[:4])
         self.device = torch.device(device)
+        # ONE flat fp32 buffer (the layout of the data-parallel gradient bucket and of the fused optimizer step);
+        # every variable is a view into it, offsets padded to 64 elements so rows stay 256-byte aligned
+        self.offsets = flat_layout(self.specs)
+        self.numel = self.offsets["__total__"]
+        self.flat = torch.zeros(self.numel, dtype=torch.float32, device=self.device)
         self.t = collections.OrderedDict()
         for name, (shape, _) in self.specs.items():
             v = np.asarray(values[name], dtype=np.float32)
             assert tuple(v.shape) == tuple(shape), (name, v.shape, shape)
-            self.t[name] = torch.from_numpy(np.ascontiguousarray(v)).to(self.device)
+            view = self.flat[self.offsets[name]:self.offsets[name] + max(1, v.size)].view(shape if shape else (1,))
+            view.copy_(torch.from_numpy(np.ascontiguousarray(v).reshape(view.shape)))
+            self.t[name] = view
         self.version = 0
         self._derived = {}
 
