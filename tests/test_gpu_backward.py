@@ -91,4 +91,4 @@ def test_dp_half_batches_sum_to_full_batch_and_optimizer_step():
     assert abs(float(tr.norm[0]) - norm) < 1e-4 * norm
     assert np.max(np.abs(tr.params.flat.cpu().numpy() - p1)) < 1e-6
     assert np.max(np.abs(tr.ema.cpu().numpy() - e1)) < 1e-6
-    assert max_rel(tr.adam_v.cpu().numpy(), v1) < 1e-5
+    assert max_rel(tr.adam_v.cpu().numpy(), v1) < 2e-4      # (1 - beta2) is rounded in fp32, as in TF
