@@ -319,59 +319,85 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for w in range(args.warmup):
-        slots[w % NSLOTS].run()
+    # `--streams S`: S independent passes (different resident batches) in flight at once, each on its own stream.
+    # A pass is one serial dependency chain whose small kernels leave most SMs idle; a second chain fills them.
+    nstreams = max(1, args.streams)
+    side = [torch.cuda.Stream() for _ in range(nstreams - 1)]
+    main_stream = torch.cuda.current_stream()
+
+    def run_passes(n):
+        if nstreams == 1:
+            for k in range(n):
+                slots[k % NSLOTS].run()
+            return
+        fork = torch.cuda.Event()
+        fork.record(main_stream)
+        for st in side:
+            st.wait_event(fork)
+        for k in range(n):
+            j = k % nstreams
+            if j == 0:
+                slots[k % NSLOTS].run()
+            else:
+                with torch.cuda.stream(side[j - 1]):
+                    slots[k % NSLOTS].run()
+        for st in side:
+            ev = torch.cuda.Event()
+            ev.record(st)
+            main_stream.wait_event(ev)
+
+    run_passes(max(args.warmup, nstreams))
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for k in range(args.steps):
-        slots[k % NSLOTS].run()
+    run_passes(args.steps)
     e1.record()
     barrier()
     t_dev = e0.elapsed_time(e1) * 1e-3
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- end-to-end arm: host (pinned) buffers, H2D + compute + D2H per pass, double-buffered
+    # ---- end-to-end arm: host (pinned) buffers; every pass does H2D of its batch, the netLength unroll, and D2H of the
+    #      final state + attention maps.  ND device slots, each on its own stream, so the copies of one pass overlap the
+    #      compute of the others (the public-API pattern for streaming batches).
+    ND = max(2, nstreams)
     host = []
     for s in range(4):
         inp = make_inputs(B, S, N, d, seed=777 + 1000 * rank + s)
         host.append({k: torch.from_numpy(v).pin_memory() for k, v in inp.items()})
     dev = [Slot(cfg, params, shape, 0, args.prec, use_graph, host_inputs={k: v.numpy() for k, v in host[0].items()})
-           for _ in range(2)]
+           for _ in range(ND)]
     outs_host = [[torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in dv.outputs()] for dv in dev]
     h2d_bytes = sum(v.numel() * v.element_size() for k, v in host[0].items() if k != "questionWords")
     d2h_bytes = sum(t.numel() * t.element_size() for t in outs_host[0])
-    copy_stream = torch.cuda.Stream()
-    main = torch.cuda.current_stream()
-    ev_in = [torch.cuda.Event() for _ in range(2)]
-    ev_done = [torch.cuda.Event() for _ in range(2)]
+    estreams = [torch.cuda.Stream() for _ in range(ND)]
 
-    def e2e_pass(k):
-        sl = k % 2
-        hb = host[k % len(host)]
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(ev_done[sl])            # slot's previous compute + D2H finished
-            for key, t in dev[sl].x.items():
-                if key != "questionWords":                 # unused when controlContextual (mac_cell.py:570)
-                    t.copy_(hb[key], non_blocking=True)
-            ev_in[sl].record(copy_stream)
-        main.wait_event(ev_in[sl])
-        dev[sl].run()
-        for src, dst in zip(dev[sl].outputs(), outs_host[sl]):
-            dst.copy_(src, non_blocking=True)
-        ev_done[sl].record(main)
+    def e2e_passes(n):
+        fork = torch.cuda.Event()
+        fork.record(main_stream)
+        for st in estreams:
+            st.wait_event(fork)
+        for k in range(n):
+            sl = k % ND
+            hb = host[k % len(host)]
+            with torch.cuda.stream(estreams[sl]):
+                for key, t in dev[sl].x.items():
+                    if key != "questionWords":             # unused when controlContextual (mac_cell.py:570)
+                        t.copy_(hb[key], non_blocking=True)
+                dev[sl].run()
+                for src, dst in zip(dev[sl].outputs(), outs_host[sl]):
+                    dst.copy_(src, non_blocking=True)
+        for st in estreams:
+            ev = torch.cuda.Event()
+            ev.record(st)
+            main_stream.wait_event(ev)
 
-    for sl in range(2):
-        ev_done[sl].record(main)
-    for k in range(max(args.warmup, 2)):
-        e2e_pass(k)
+    e2e_passes(max(args.warmup, ND))
     barrier()
     e0.record()
-    for k in range(args.steps):
-        e2e_pass(k)
+    e2e_passes(args.steps)
     e1.record()
     barrier()
     t_e2e = e0.elapsed_time(e1) * 1e-3
@@ -398,7 +424,7 @@ def run_ours(args):
                        "step": "one netLength-step unroll over one batch (%d reasoning steps)" % L,
                        "l2": "timed passes rotate over %d resident batches (%.0f MB > 126 MB L2)"
                              % (NSLOTS, NSLOTS * (B * N * d + B * S * d) * 4 / 1e6),
-                       "cuda_graph": use_graph, "projections": args.prec, "parallelism": "dp%d (replicas, no "
+                       "cuda_graph": use_graph, "projections": args.prec, "concurrent_passes": nstreams, "parallelism": "dp%d (replicas, no "
                        "data-path collective in inference)" % world},
             "sample_steps_per_sec": value * B,
             "e2e": {"value": args.steps * L * world / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
@@ -468,10 +494,16 @@ def run_train(args):
     t_dev = e0.elapsed_time(e1) * 1e-3
     launches = lib.mac_b200_launch_count() - n0
     clocks = sampler.stop() if rank == 0 else None
+    in_sync = True
     if dist is not None:
         tt = torch.tensor([t_dev], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         t_dev = float(tt[0])
+        # replicas must stay bit-identical: every rank applied the same all-reduced gradient
+        chk = torch.stack([tr.params.flat.double().sum(), tr.params.flat.double().abs().sum()])
+        allc = [torch.zeros_like(chk) for _ in range(world)]
+        dist.all_gather(allc, chk)
+        in_sync = all(bool(torch.equal(allc[0], c)) for c in allc)
     if rank == 0:
         value = args.steps * L * world / t_dev
         nparam = tr.params.numel
@@ -485,7 +517,8 @@ def run_train(args):
                                    "%d reasoning steps" % (nparam, nparam * 4 / 1e6, L),
                            "l2": "timed steps rotate over %d resident batches per rank; activations saved for backward "
                                  "(%.0f MB per step) exceed L2" % (nslots, L * 3 * B * N * d * 4 / 1e6),
-                           "cuda_graph": False, "projections": "fp32", "parallelism": "dp%d, NCCL all-reduce per step" % world},
+                           "cuda_graph": False, "projections": "fp32", "parallelism": "dp%d, NCCL all-reduce per step" % world,
+                           "replicas_in_sync_after_run": in_sync},
                 "sample_steps_per_sec": value * B, "gpu_launches": int(launches), "clocks": clocks,
                 "e2e": None, "roofline": None, "cpu_baseline": None}
         print(json.dumps(line))
@@ -539,6 +572,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--mode", default="infer", choices=["infer", "train"])
+    ap.add_argument("--streams", type=int, default=4, help="independent passes in flight (each on its own stream)")
     ap.add_argument("--rooflines-only", action="store_true", help="only the per-kernel measurements (for ncu)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
