@@ -111,24 +111,32 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;                 // 64 bf16 = 128 B = one swizzle atom row
 constexpr int TC_MAX_VEC = 4;              // a 128-row tile spans at most this many samples on the smem-parameter path
 constexpr int TC_EPI_WARPS = 8;            // two per TMEM lane quarter: each handles half of the tile's columns
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 
-template <int BN>
+// Tile shapes.  The measured per-SM TMA fill rate is ~64 B/clk (profiles/r1/NOTES.md): a k-block of a BM x BN tile
+// brings (BM + BN) * 128 B and feeds BM * BN / 64 MMA cycles, so
+//   128 x 128 -> 128 B/clk needed (2x fill-bound), 128 x 256 -> 96 B/clk (1.5x), 256 x 256 -> 64 B/clk (balanced).
+// BM = 256 is two M=128 UMMAs per k-step that share the B tile in shared memory and own one accumulator each
+// (2 x 256 TMEM columns, not double-buffered); BM = 128 keeps two accumulator buffers so the epilogue of tile i
+// overlaps the MMAs of tile i+1.
+template <int BM, int BN>
 struct TcCfg {
-  static constexpr int STAGES = BN == 256 ? 4 : 6;
-  static constexpr int A_BYTES = TC_BM * TC_BK * 2;        // 16 KB
-  static constexpr int B_BYTES = BN * TC_BK * 2;           // 32 KB (BN = 256)
+  static constexpr int NMS = BM / 128;                      // M sub-tiles (UMMA M = 128 each)
+  static constexpr int STAGES = BM == 256 ? 3 : (BN == 256 ? 4 : 6);
+  static constexpr int A_BYTES = BM * TC_BK * 2;            // 16 / 32 KB
+  static constexpr int B_BYTES = BN * TC_BK * 2;            // 16 / 32 KB
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STG_WORDS = 32 * 16;                // per epilogue warp: 32 rows x 16 words, XOR-swizzled
-  static constexpr int PAR_ROWS = 2 + TC_MAX_VEC;          // bias, wr, and up to TC_MAX_VEC per-sample rows (y / control)
-  static constexpr int PAR_WORDS = 2 * PAR_ROWS * BN;      // double-buffered with the accumulators
+  static constexpr int NBUF = BM == 256 ? 1 : 2;            // accumulator buffers
+  static constexpr int BUF_COLS = NMS * BN;
+  static constexpr int TMEM_COLS = 512 / (BM == 128 && BN == 128 ? 2 : 1);   // NBUF * BUF_COLS, a power of two
+  static constexpr int STG_WORDS = 32 * 16;                 // per epilogue warp: 32 rows x 16 words, XOR-swizzled
+  static constexpr int PAR_ROWS = 2 + TC_MAX_VEC;           // bias, wr, and up to TC_MAX_VEC per-sample rows (y / control)
+  static constexpr int PAR_WORDS = NBUF * PAR_ROWS * BN;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ +
                                     TC_EPI_WARPS * STG_WORDS * 4 + PAR_WORDS * 4;
-  static constexpr int TMEM_COLS = 2 * BN;                 // two accumulator buffers; power of two >= 32
 };
 
 // fast ELU for the tensor-core path: x > 0 ? x : exp(x) - 1 with the SFU exponential (abs error ~1e-7 near 0,
@@ -147,11 +155,12 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
-template <int BN, int EPI, int ACT>
+template <int BM, int BN, int EPI, int ACT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                const __grid_constant__ CUtensorMap map_b, const TcGemmParams p) {
-  using C = TcCfg<BN>;
+  using C = TcCfg<BM, BN>;
+  constexpr int TC_BM = BM;
   extern __shared__ unsigned char smem_dyn[];
   // 1024-byte aligned operand ring
   const uint32_t base_u32 = smem_u32(smem_dyn);
@@ -221,16 +230,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer
-    constexpr uint32_t idesc = make_idesc_bf16(TC_BM, BN);
+    constexpr uint32_t idesc = make_idesc_bf16(128, BN);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
-      mbar_wait(&tempty[acc], acc_phase ^ 1);        // epilogue has drained this accumulator
+      const int acc = it % C::NBUF;
+      const uint32_t acc_phase = (it / C::NBUF) & 1;
+      mbar_wait(&tempty[acc], acc_phase ^ 1);        // epilogue has drained this accumulator buffer
       tc_fence_after();
-      const uint32_t tmem_d = tmem_base + acc * BN;
+      const uint32_t tmem_d = tmem_base + acc * C::BUF_COLS;
       for (int kb = 0; kb < kblocks; ++kb) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
@@ -240,8 +249,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           const uint64_t bdesc = make_sw128_kmajor_desc(sa + C::A_BYTES);
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k) {
-            // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle atom: +2 in the 16-B address field
-            if (!(p.debug & 2)) umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+            // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle atom: +2 in the 16-B address field;
+            // the second M sub-tile's rows start 16 KB (= 1024 in 16-B units) further
+#pragma unroll
+            for (int ms = 0; ms < C::NMS; ++ms)
+              if (!(p.debug & 2))
+                umma_bf16(tmem_d + ms * BN, adesc + 2 * k + ms * 1024, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
           }
           umma_commit(&empty[stage]);                // frees the smem slot when these MMAs retire
           if (kb == kblocks - 1) umma_commit(&tfull[acc]);
@@ -255,7 +268,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     // thread == one output row of the tile; 32 fp32 columns per tcgen05.ld
     const int q = warp & 3;
     uint32_t* stg = stg_all + (warp - 2) * C::STG_WORDS;
-    const int chalf = (warp - 2) >> 2;              // which half of the tile's columns this warp drains
+    const int grp = (warp - 2) >> 2;                // BM=128: which half of the tile's columns; BM=256: which M sub-tile
+    const int ms = C::NMS == 2 ? grp : 0;
+    const int c_begin = C::NMS == 2 ? 0 : grp * (BN / 2), c_end = C::NMS == 2 ? BN : (grp + 1) * (BN / 2);
     // Row-per-thread registers -> coalesced 128-bit global stores.  The warp's 32-row chunk goes through a private
     // shared-memory patch whose 16-byte groups are XOR-swizzled with the row (conflict-free both ways): thread == row
     // writes 16-B groups, then lane l reads group (l % G) of row (i*32/G + l / G) and stores 16 B to global, so one
@@ -297,8 +312,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     int it = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       const int mt = t / n_tiles, nt = t % n_tiles;
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
+      const int acc = it % C::NBUF;
+      const uint32_t acc_phase = (it / C::NBUF) & 1;
       // ---- stage this tile's parameters in shared memory while the MMAs of the tile are still running:
       //      row 0 bias[BN], row 1 wr[BN], rows 2.. the y / control vectors of the samples this tile touches
       float* par = par_all + acc * (C::PAR_ROWS * BN);
@@ -319,15 +334,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       }
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      const int row0 = mt * TC_BM + q * 32;
+      const int row0 = mt * TC_BM + ms * 128 + q * 32;
       const int row = row0 + lane;
       const bool row_ok = row < p.M;
       const int bidx = row_ok ? row / p.rows_per_batch : b_lo;
       const float* vrow = vec_smem ? par + (2 + bidx - b_lo) * BN : nullptr;   // this row's y / control vector (tile-local)
-      const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
+      const uint32_t taddr = tmem_base + acc * C::BUF_COLS + ms * BN + ((uint32_t)(q * 32) << 16);
       float part = 0.f;
 #pragma unroll 1
-      for (int c0 = chalf * (BN / 2); c0 < (chalf + 1) * (BN / 2); c0 += 32) {
+      for (int c0 = c_begin; c0 < c_end; c0 += 32) {
         if (p.debug & 1) break;
         uint32_t r[32];
         if (p.debug & 8) {
@@ -406,8 +421,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         }
       }
       if constexpr (EPI == TC_EPI_LOGITS) {
-        // two partial sums per (row, n-tile): one per column half
-        if (row_ok) p.parts[((size_t)row * n_tiles + nt) * 2 + chalf] = part;
+        // BM=128: two partial sums per (row, n-tile), one per column half; BM=256: one
+        if (row_ok) {
+          if (C::NMS == 2) p.parts[(size_t)row * n_tiles + nt] = part;
+          else p.parts[((size_t)row * n_tiles + nt) * 2 + grp] = part;
+        }
       }
       // release the accumulator buffer to the MMA warp
       tc_fence_before();
@@ -436,74 +454,86 @@ inline int tc_num_sms() {
   return sms;
 }
 
-template <int BN, int EPI, int ACT>
+template <int BM, int BN, int EPI, int ACT>
 inline int tc_gemm_launch_t(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtensorMap& mb,
                             const TcGemmParams& p, cudaStream_t stream) {
-  auto kern = tc_gemm_kernel<BN, EPI, ACT>;
-  MAC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM_BYTES));
-  const int tiles = ((p.M + TC_BM - 1) / TC_BM) * (p.N / BN);
+  auto kern = tc_gemm_kernel<BM, BN, EPI, ACT>;
+  MAC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BM, BN>::SMEM_BYTES));
+  const int tiles = ((p.M + BM - 1) / BM) * (p.N / BN);
   const int grid = tiles < tc_num_sms() ? tiles : tc_num_sms();
-  kern<<<grid, TC_THREADS, TcCfg<BN>::SMEM_BYTES, stream>>>(ma0, ma1, mb, p);
+  kern<<<grid, TC_THREADS, TcCfg<BM, BN>::SMEM_BYTES, stream>>>(ma0, ma1, mb, p);
   MAC_LAUNCH_CHECK();
   return MAC_OK;
 }
 
-template <int BN>
+template <int BM, int BN>
 inline int tc_gemm_dispatch(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtensorMap& mb,
                             const TcGemmParams& p, cudaStream_t stream) {
   switch (p.epi) {
-    case TC_EPI_P: return tc_gemm_launch_t<BN, TC_EPI_P, MAC_ACT_NON>(ma0, ma1, mb, p, stream);
-    case TC_EPI_LOGITS: return tc_gemm_launch_t<BN, TC_EPI_LOGITS, MAC_ACT_NON>(ma0, ma1, mb, p, stream);
+    case TC_EPI_P: return tc_gemm_launch_t<BM, BN, TC_EPI_P, MAC_ACT_NON>(ma0, ma1, mb, p, stream);
+    case TC_EPI_LOGITS: return tc_gemm_launch_t<BM, BN, TC_EPI_LOGITS, MAC_ACT_NON>(ma0, ma1, mb, p, stream);
     case TC_EPI_ACT:
-      if (p.act == MAC_ACT_ELU) return tc_gemm_launch_t<BN, TC_EPI_ACT, MAC_ACT_ELU>(ma0, ma1, mb, p, stream);
-      if (p.act == MAC_ACT_NON) return tc_gemm_launch_t<BN, TC_EPI_ACT, MAC_ACT_NON>(ma0, ma1, mb, p, stream);
+      if (p.act == MAC_ACT_ELU) return tc_gemm_launch_t<BM, BN, TC_EPI_ACT, MAC_ACT_ELU>(ma0, ma1, mb, p, stream);
+      if (p.act == MAC_ACT_NON) return tc_gemm_launch_t<BM, BN, TC_EPI_ACT, MAC_ACT_NON>(ma0, ma1, mb, p, stream);
       return MAC_ERR_UNSUPPORTED;
     case TC_EPI_F32:
       switch (p.act) {
-        case MAC_ACT_NON: return tc_gemm_launch_t<BN, TC_EPI_F32, MAC_ACT_NON>(ma0, ma1, mb, p, stream);
-        case MAC_ACT_TANH: return tc_gemm_launch_t<BN, TC_EPI_F32, MAC_ACT_TANH>(ma0, ma1, mb, p, stream);
-        case MAC_ACT_SIGMOID: return tc_gemm_launch_t<BN, TC_EPI_F32, MAC_ACT_SIGMOID>(ma0, ma1, mb, p, stream);
-        case MAC_ACT_ELU: return tc_gemm_launch_t<BN, TC_EPI_F32, MAC_ACT_ELU>(ma0, ma1, mb, p, stream);
-        case MAC_ACT_RELU: return tc_gemm_launch_t<BN, TC_EPI_F32, MAC_ACT_RELU>(ma0, ma1, mb, p, stream);
+        case MAC_ACT_NON: return tc_gemm_launch_t<BM, BN, TC_EPI_F32, MAC_ACT_NON>(ma0, ma1, mb, p, stream);
+        case MAC_ACT_TANH: return tc_gemm_launch_t<BM, BN, TC_EPI_F32, MAC_ACT_TANH>(ma0, ma1, mb, p, stream);
+        case MAC_ACT_SIGMOID: return tc_gemm_launch_t<BM, BN, TC_EPI_F32, MAC_ACT_SIGMOID>(ma0, ma1, mb, p, stream);
+        case MAC_ACT_ELU: return tc_gemm_launch_t<BM, BN, TC_EPI_F32, MAC_ACT_ELU>(ma0, ma1, mb, p, stream);
+        case MAC_ACT_RELU: return tc_gemm_launch_t<BM, BN, TC_EPI_F32, MAC_ACT_RELU>(ma0, ma1, mb, p, stream);
       }
       return MAC_ERR_UNSUPPORTED;
   }
   return MAC_ERR_UNSUPPORTED;
 }
 
-// tile width: the one that minimises (rounds over the SMs) x (tile width) -- 392 tiles of 128 x 128 finish in 3
-// rounds of half-size tiles where 196 tiles of 128 x 256 need 2 full rounds
-inline int tc_pick_bn(int M, int N) {
-  if (N % 256) return 128;
+// Tile shape: minimise rounds-over-the-SMs x per-tile time, per-tile time = max(MMA cycles, bytes / 64 B/clk) per k-block
+// (256x256: 1024, 128x256: 768, 128x128: 512).  Returns BM*1000 + BN.
+inline int tc_pick_tile(int M, int N) {
   const int sms = tc_num_sms();
-  const int mt = (M + TC_BM - 1) / TC_BM;
-  const int r256 = (mt * (N / 256) + sms - 1) / sms, r128 = (mt * (N / 128) + sms - 1) / sms;
-  return (r128 * 128 < r256 * 256) ? 128 : 256;
+  auto cost = [&](int bm, int bn, int per_tile) {
+    if (N % bn) return 1 << 30;
+    const int tiles = ((M + bm - 1) / bm) * (N / bn);
+    return ((tiles + sms - 1) / sms) * per_tile;
+  };
+  int best = 128128, bc = cost(128, 128, 512);
+  const int c2 = cost(128, 256, 768), c3 = cost(256, 256, 1024);
+  if (c2 < bc) { best = 128256; bc = c2; }
+  if (c3 < bc || (c3 == bc && M >= 2048)) { best = 256256; bc = c3; }
+  return best;
 }
 
 // A = [a0 (K0 cols) | a1 (K1 cols)] bf16 row-major (ld = own K), Wt bf16 [N, K0+K1]
 inline int tc_gemm_launch(const void* a0, int K0, const void* a1, int K1, const void* wt, TcGemmParams p,
-                          cudaStream_t stream, int* bn_used = nullptr) {
+                          cudaStream_t stream, int* nparts_per_row = nullptr) {
   if (p.M <= 0 || p.N <= 0 || (p.N % 128) || (K0 % TC_BK) || (K1 % TC_BK) || K0 <= 0) return MAC_ERR_UNSUPPORTED;
   if (!mac_aligned16(a0) || !mac_aligned16(wt)) return MAC_ERR_ALIGN;
-  int BN = tc_pick_bn(p.M, p.N);
-  if (const char* e = getenv("MAC_TC_BN")) { const int v = atoi(e); if ((v == 128 || v == 256) && p.N % v == 0) BN = v; }
+  int tile = tc_pick_tile(p.M, p.N);
+  if (const char* e = getenv("MAC_TC_TILE")) {
+    const int v = atoi(e);
+    if ((v == 128128 || v == 128256 || v == 256256) && p.N % (v % 1000) == 0) tile = v;
+  }
   if (const char* e = getenv("MAC_TC_DEBUG")) p.debug = atoi(e);
-  if (bn_used) *bn_used = BN;
+  const int BM = tile / 1000, BN = tile % 1000;
+  if (nparts_per_row) *nparts_per_row = (p.N / BN) * (BM == 256 ? 1 : 2);
   p.K = K0 + K1;
   p.kblocks0 = K0 / TC_BK;
   CUtensorMap ma0, ma1, mb;
-  int st = make_tmap_2d(&ma0, a0, 1, (uint64_t)p.M, (uint64_t)K0, (uint64_t)K0 * 2, TC_BM, TC_BK, 1);
+  int st = make_tmap_2d(&ma0, a0, 1, (uint64_t)p.M, (uint64_t)K0, (uint64_t)K0 * 2, (uint32_t)BM, TC_BK, 1);
   if (st != MAC_OK) return st;
   if (K1 > 0) {
-    st = make_tmap_2d(&ma1, a1, 1, (uint64_t)p.M, (uint64_t)K1, (uint64_t)K1 * 2, TC_BM, TC_BK, 1);
+    st = make_tmap_2d(&ma1, a1, 1, (uint64_t)p.M, (uint64_t)K1, (uint64_t)K1 * 2, (uint32_t)BM, TC_BK, 1);
     if (st != MAC_OK) return st;
   } else {
     ma1 = ma0;
   }
   st = make_tmap_2d(&mb, wt, 1, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)p.K * 2, (uint32_t)BN, TC_BK, 1);
   if (st != MAC_OK) return st;
-  return BN == 256 ? tc_gemm_dispatch<256>(ma0, ma1, mb, p, stream) : tc_gemm_dispatch<128>(ma0, ma1, mb, p, stream);
+  if (tile == 256256) return tc_gemm_dispatch<256, 256>(ma0, ma1, mb, p, stream);
+  if (tile == 128256) return tc_gemm_dispatch<128, 256>(ma0, ma1, mb, p, stream);
+  return tc_gemm_dispatch<128, 128>(ma0, ma1, mb, p, stream);
 }
 
 // fp32 [K, N] (in, out) weight -> bf16 [N, K] (out, in): the K-major B operand of the forward GEMMs
@@ -555,10 +585,8 @@ inline int tc_read_chain(const void* kb_bf16, const float* y, const float* contr
   // logits parts = sum_n ELU((H @ Wm2 + bm2) * control) * wr
   p.epi = TC_EPI_LOGITS; p.bias = w->bm2; p.out0 = I1; p.ctrl = control; p.wr = w->wr; p.parts = parts;
   p.e_thresh = thr; p.e_scale = scale; p.e_site = MAC_SITE_READ_INTER;
-  int bn = 256;
-  st = tc_gemm_launch(H, d, nullptr, 0, w->Wm2_bf16, p, stream, &bn);
+  st = tc_gemm_launch(H, d, nullptr, 0, w->Wm2_bf16, p, stream, nparts);
   if (st != MAC_OK) return st;
-  *nparts = 2 * (d / bn);
   return MAC_OK;
 }
 

@@ -11,9 +11,9 @@ Wt = torch.empty(N, K, dtype=torch.bfloat16, device="cuda")
 L.check(lib.mac_pack_weight_bf16(L.ptr(W), L.ptr(Wt), K, N, L.stream_ptr()))
 bias = torch.zeros(N, device="cuda")
 y = torch.empty(M, N, device="cuda")
-for bn in ("128", "256"):
-    for dbg in ("0", "1", "6", "7", "14", "22", "38", "62"):
-        os.environ["MAC_TC_BN"] = bn
+for bn in ("128128", "128256", "256256"):
+    for dbg in ("1", "3", "5"):
+        os.environ["MAC_TC_TILE"] = bn
         os.environ["MAC_TC_DEBUG"] = dbg
         for x in xs:
             L.check(lib.mac_linear_tc_fwd(L.ptr(x), L.ptr(Wt), L.ptr(bias), 3, L.ptr(y), M, K, N, L.stream_ptr()))
@@ -25,4 +25,4 @@ for bn in ("128", "256"):
         b.record()
         torch.cuda.synchronize()
         t = a.elapsed_time(b) / 30 * 1e3
-        print("BN=%s debug=%s (1=no epi 2=no MMA 4=no TMA 8=no LDTM 16=no bias 32=no store): %.1f us  %.0f TFLOP/s-equivalent" % (bn, dbg, t, 2.0 * M * K * N / t / 1e6))
+        print("tile=%s debug=%s (1=no epi 2=no MMA 4=no TMA 8=no LDTM 16=no bias 32=no store): %.1f us  %.0f TFLOP/s-equivalent" % (bn, dbg, t, 2.0 * M * K * N / t / 1e6))
