@@ -443,6 +443,346 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   }
 }
 
+// =====================================================================================================
+// cta_group::2 variant: a CTA PAIR (2-CTA cluster, one TPC) computes a 256 x 256 tile with ONE tcgen05.mma issued by
+// the leader CTA.  Each CTA stages its own 128 rows of A and only HALF of the B tile (128 of the 256 W rows) and keeps
+// its 128 x 256 half of the accumulator in its own TMEM, so per MMA each SM's shared memory supplies 8 KB instead of
+// 12 KB -- the measured SS-mode operand-read limit (~64 B/clk/SM) stops throttling the tensor core.
+//   * TMA loads are issued by both CTAs into their own smem but complete on the LEADER's `full` barrier
+//     (cp.async.bulk.tensor ... .cta_group::2, barrier address with the peer bit cleared).
+//   * the leader's tcgen05.commit multicasts to both CTAs' `empty` / `tfull` barriers.
+//   * each CTA's epilogue drains its own TMEM half; every epilogue warp of BOTH CTAs arrives on the leader's `tempty`.
+// =====================================================================================================
+__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(cta_mask)
+               : "memory");
+}
+// TMA load into this CTA's smem, transaction bytes counted on the LEADER CTA's barrier (peer bit 24 cleared)
+__device__ __forceinline__ void tma2_load_2d(void* smem_dst, const void* tmap, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar) & 0xFEFFFFFFu)
+      : "memory");
+}
+// arrive on the barrier at the same offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(smem_u32(bar)), "r"(cta)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_barrier() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+struct Tc2Cfg {
+  static constexpr int BN = 256;
+  static constexpr int STAGES = 5;
+  static constexpr int A_BYTES = 128 * TC_BK * 2;            // this CTA's 128 rows of A
+  static constexpr int B_BYTES = (BN / 2) * TC_BK * 2;       // this CTA's half of the B tile
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;      // 32 KB per CTA per k-block
+  static constexpr int TMEM_COLS = 512;                      // two 256-column accumulator buffers
+  static constexpr int STG_WORDS = 32 * 16;
+  static constexpr int PAR_ROWS = 2 + TC_MAX_VEC;
+  static constexpr int PAR_WORDS = 2 * PAR_ROWS * BN;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + TC_EPI_WARPS * STG_WORDS * 4 + PAR_WORDS * 4;
+};
+
+template <int EPI, int ACT>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc2_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
+                const __grid_constant__ CUtensorMap map_b, const TcGemmParams p) {
+  using C = Tc2Cfg;
+  constexpr int BN = C::BN;
+  extern __shared__ unsigned char smem_dyn[];
+  const uint32_t base_u32 = smem_u32(smem_dyn);
+  const uint32_t pad = (1024u - (base_u32 & 1023u)) & 1023u;
+  unsigned char* tiles = smem_dyn + pad;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + C::STAGES * C::STAGE_BYTES);
+  uint64_t* full = bars;                       // [STAGES]  (leader's are the live ones)
+  uint64_t* empty = bars + C::STAGES;          // [STAGES]  per CTA
+  uint64_t* tfull = bars + 2 * C::STAGES;      // [2]       per CTA
+  uint64_t* tempty = tfull + 2;                // [2]       leader's are the live ones
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint32_t* stg_all = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(bars) + 256);
+  float* par_all = reinterpret_cast<float*>(stg_all + TC_EPI_WARPS * C::STG_WORDS);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_rank();                     // 0 = leader
+  const int m_pairs = (p.M + 255) / 256;
+  const int n_tiles = p.N / BN;
+  const int num_tiles = m_pairs * n_tiles;
+  const int kblocks = p.K / TC_BK;
+  const int pair0 = blockIdx.x >> 1, pair_stride = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a0);
+    tma_prefetch_desc(&map_a1);
+    tma_prefetch_desc(&map_b);
+#pragma unroll
+    for (int i = 0; i < C::STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(&tfull[0], 1);
+    mbar_init(&tfull[1], 1);
+    mbar_init(&tempty[0], 2 * TC_EPI_WARPS);
+    mbar_init(&tempty[1], 2 * TC_EPI_WARPS);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc2(tmem_ptr, C::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  cluster_barrier();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer (both CTAs)
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = pair0; t < num_tiles; t += pair_stride) {
+        const int mp = t / n_tiles, nt = t % n_tiles;
+        const int row_a = mp * 256 + (int)rank * 128;
+        const int row_b = nt * BN + (int)rank * (BN / 2);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          unsigned char* sa = tiles + stage * C::STAGE_BYTES;
+          unsigned char* sb = sa + C::A_BYTES;
+          if (rank == 0) mbar_expect_tx(&full[stage], 2 * C::STAGE_BYTES);   // both CTAs' bytes land on the leader's barrier
+          if (kb < p.kblocks0)
+            tma2_load_2d(sa, &map_a0, kb * TC_BK, row_a, &full[stage]);
+          else
+            tma2_load_2d(sa, &map_a1, (kb - p.kblocks0) * TC_BK, row_a, &full[stage]);
+          tma2_load_2d(sb, &map_b, kb * TC_BK, row_b, &full[stage]);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer (leader CTA only)
+    if (rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(256, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int t = pair0; t < num_tiles; t += pair_stride, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tempty[acc], acc_phase ^ 1);      // both CTAs' epilogues have drained this buffer
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t sa = smem_u32(tiles + stage * C::STAGE_BYTES);
+            const uint64_t adesc = make_sw128_kmajor_desc(sa);
+            const uint64_t bdesc = make_sw128_kmajor_desc(sa + C::A_BYTES);
+#pragma unroll
+            for (int k = 0; k < TC_BK / 16; ++k) umma2_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+            umma2_commit_mc(&empty[stage], 0x3);     // both CTAs may refill this slot
+            if (kb == kblocks - 1) umma2_commit_mc(&tfull[acc], 0x3);
+          }
+          __syncwarp();
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ===================================================== epilogue (both CTAs; own 128 rows)
+    const int q = warp & 3;
+    uint32_t* stg = stg_all + (warp - 2) * C::STG_WORDS;
+    const int grp = (warp - 2) >> 2;
+    const int c_begin = grp * (BN / 2), c_end = (grp + 1) * (BN / 2);
+    auto store_bf16_chunk = [&](const uint32_t (&w)[16], __nv_bfloat16* out, int row0, int col0) {
+      __syncwarp();
+      uint4* s4 = reinterpret_cast<uint4*>(stg);
+#pragma unroll
+      for (int g = 0; g < 4; ++g) s4[lane * 4 + (g ^ (lane & 3))] = make_uint4(w[4 * g], w[4 * g + 1], w[4 * g + 2], w[4 * g + 3]);
+      __syncwarp();
+      const int g = lane & 3;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int rr = i * 8 + (lane >> 2);
+        const uint4 v = s4[rr * 4 + (g ^ (rr & 3))];
+        if (row0 + rr < p.M) *reinterpret_cast<uint4*>(out + (size_t)(row0 + rr) * p.ldo + col0 + 8 * g) = v;
+      }
+    };
+    auto store_f32_chunk = [&](const float (&w)[32], float* out, int row0, int col0) {
+      float4* s4 = reinterpret_cast<float4*>(stg);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        __syncwarp();
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          s4[lane * 4 + (g ^ (lane & 3))] = make_float4(w[16 * h + 4 * g], w[16 * h + 4 * g + 1], w[16 * h + 4 * g + 2], w[16 * h + 4 * g + 3]);
+        __syncwarp();
+        const int g = lane & 3;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int rr = i * 8 + (lane >> 2);
+          const float4 v = s4[rr * 4 + (g ^ (rr & 3))];
+          if (row0 + rr < p.M) *reinterpret_cast<float4*>(out + (size_t)(row0 + rr) * p.ldo + col0 + 16 * h + 4 * g) = v;
+        }
+      }
+    };
+    const int etid = threadIdx.x - 64;
+    const float* vec_src = (EPI == TC_EPI_P) ? p.y : (EPI == TC_EPI_LOGITS ? p.ctrl : nullptr);
+    int it = 0;
+    for (int t = pair0; t < num_tiles; t += pair_stride, ++it) {
+      const int mp = t / n_tiles, nt = t % n_tiles;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int tile_row0 = mp * 256 + (int)rank * 128;
+      float* par = par_all + acc * (C::PAR_ROWS * BN);
+      const int b_lo = min(tile_row0, p.M - 1) / p.rows_per_batch;
+      const int last_row = max(min(p.M, tile_row0 + 128) - 1, min(tile_row0, p.M - 1));
+      const int nvec = vec_src ? (last_row / p.rows_per_batch - b_lo + 1) : 0;
+      const bool vec_smem = nvec <= TC_MAX_VEC;
+      {
+        const int nb = nt * BN;
+        for (int i = etid; i < BN; i += 32 * TC_EPI_WARPS) {
+          par[i] = p.bias ? __ldg(p.bias + nb + i) : 0.f;
+          if constexpr (EPI == TC_EPI_LOGITS) par[BN + i] = __ldg(p.wr + nb + i);
+        }
+        if (vec_src && vec_smem)
+          for (int i = etid; i < nvec * BN; i += 32 * TC_EPI_WARPS)
+            par[2 * BN + i] = __ldg(vec_src + (size_t)(b_lo + i / BN) * p.N + nb + (i % BN));
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
+      }
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const int row0 = tile_row0 + q * 32;
+      const int row = row0 + lane;
+      const bool row_ok = row < p.M;
+      const int bidx = row_ok ? row / p.rows_per_batch : b_lo;
+      const float* vrow = vec_smem ? par + (2 + bidx - b_lo) * BN : nullptr;
+      const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
+      float part = 0.f;
+#pragma unroll 1
+      for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(taddr + c0, r);
+        tmem_ld_wait();
+        const int n0 = nt * BN + c0;
+        const float4* bias4 = reinterpret_cast<const float4*>(par + c0);
+        if constexpr (EPI == TC_EPI_P) {
+          const float4* y4 = vec_smem ? reinterpret_cast<const float4*>(vrow + c0)
+                                      : reinterpret_cast<const float4*>(p.y + (size_t)bidx * p.N + n0);
+          uint32_t w0[16], w1[16];
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b0 = bias4[j / 4], y0 = y4[j / 4];
+            const float x0 = __uint_as_float(r[j]) + b0.x, x1 = __uint_as_float(r[j + 1]) + b0.y;
+            const float x2 = __uint_as_float(r[j + 2]) + b0.z, x3 = __uint_as_float(r[j + 3]) + b0.w;
+            w0[j / 2] = pack_bf16(x0, x1);
+            w0[j / 2 + 1] = pack_bf16(x2, x3);
+            w1[j / 2] = pack_bf16(x0 * y0.x, x1 * y0.y);
+            w1[j / 2 + 1] = pack_bf16(x2 * y0.z, x3 * y0.w);
+          }
+          store_bf16_chunk(w0, p.out0, row0, n0);
+          store_bf16_chunk(w1, p.out1, row0, n0);
+        } else if constexpr (EPI == TC_EPI_ACT) {
+          uint32_t w0[16];
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b0 = bias4[j / 4];
+            w0[j / 2] = pack_bf16(act_ct<ACT>(__uint_as_float(r[j]) + b0.x), act_ct<ACT>(__uint_as_float(r[j + 1]) + b0.y));
+            w0[j / 2 + 1] = pack_bf16(act_ct<ACT>(__uint_as_float(r[j + 2]) + b0.z), act_ct<ACT>(__uint_as_float(r[j + 3]) + b0.w));
+          }
+          store_bf16_chunk(w0, p.out0, row0, n0);
+        } else if constexpr (EPI == TC_EPI_F32) {
+          float w0[32];
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b0 = bias4[j / 4];
+            w0[j] = act_ct<ACT>(__uint_as_float(r[j]) + b0.x);
+            w0[j + 1] = act_ct<ACT>(__uint_as_float(r[j + 1]) + b0.y);
+            w0[j + 2] = act_ct<ACT>(__uint_as_float(r[j + 2]) + b0.z);
+            w0[j + 3] = act_ct<ACT>(__uint_as_float(r[j + 3]) + b0.w);
+          }
+          store_f32_chunk(w0, p.outf, row0, n0);
+        } else {
+          const float4* c4 = vec_smem ? reinterpret_cast<const float4*>(vrow + c0)
+                                      : reinterpret_cast<const float4*>(p.ctrl + (size_t)bidx * p.N + n0);
+          const float4* w4 = reinterpret_cast<const float4*>(par + BN + c0);
+          uint32_t w0[16];
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b0 = bias4[j / 4], cc = c4[j / 4], ww = w4[j / 4];
+            const float i0 = __uint_as_float(r[j]) + b0.x, i1 = __uint_as_float(r[j + 1]) + b0.y;
+            const float i2 = __uint_as_float(r[j + 2]) + b0.z, i3 = __uint_as_float(r[j + 3]) + b0.w;
+            w0[j / 2] = pack_bf16(i0, i1);
+            w0[j / 2 + 1] = pack_bf16(i2, i3);
+            float t0 = elu_fast(i0 * cc.x), t1 = elu_fast(i1 * cc.y), t2 = elu_fast(i2 * cc.z), t3 = elu_fast(i3 * cc.w);
+            if (p.e_thresh) {
+              const uint64_t e = (uint64_t)row * (uint64_t)p.N + (uint64_t)(n0 + j);
+              const Philox4 rr = philox4x32_10(p.seed, e >> 2, (uint32_t)p.e_site, (uint32_t)p.step);
+              t0 = ((rr.x >> 8) >= p.e_thresh) ? t0 * p.e_scale : 0.f;
+              t1 = ((rr.y >> 8) >= p.e_thresh) ? t1 * p.e_scale : 0.f;
+              t2 = ((rr.z >> 8) >= p.e_thresh) ? t2 * p.e_scale : 0.f;
+              t3 = ((rr.w >> 8) >= p.e_thresh) ? t3 * p.e_scale : 0.f;
+            }
+            part = fmaf(t0, ww.x, part);
+            part = fmaf(t1, ww.y, part);
+            part = fmaf(t2, ww.z, part);
+            part = fmaf(t3, ww.w, part);
+          }
+          if (p.out0) store_bf16_chunk(w0, p.out0, row0, n0);
+        }
+      }
+      if constexpr (EPI == TC_EPI_LOGITS) {
+        if (row_ok) p.parts[((size_t)row * n_tiles + nt) * 2 + grp] = part;
+      }
+      // release the accumulator buffer: every epilogue warp of both CTAs arrives on the LEADER's barrier
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (rank == 0) mbar_arrive(&tempty[acc]);
+        else mbar_arrive_remote(&tempty[acc], 0);
+      }
+    }
+  }
+
+  // ---- teardown: nobody leaves while the partner may still signal it or read its shared memory
+  tc_fence_before();
+  __syncthreads();
+  cluster_barrier();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, C::TMEM_COLS);
+  }
+}
+
 // ------------------------------------------------------------------ host side
 inline int tc_num_sms() {
   static int sms = 0;
@@ -489,6 +829,49 @@ inline int tc_gemm_dispatch(const CUtensorMap& ma0, const CUtensorMap& ma1, cons
   return MAC_ERR_UNSUPPORTED;
 }
 
+template <int EPI, int ACT>
+inline int tc2_gemm_launch_t(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtensorMap& mb,
+                             const TcGemmParams& p, cudaStream_t stream) {
+  auto kern = tc2_gemm_kernel<EPI, ACT>;
+  MAC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Tc2Cfg::SMEM_BYTES));
+  const int tiles = ((p.M + 255) / 256) * (p.N / Tc2Cfg::BN);
+  const int max_pairs = tc_num_sms() / 2;
+  const int pairs = tiles < max_pairs ? tiles : max_pairs;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * pairs, 1, 1);
+  cfg.blockDim = dim3(TC_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = Tc2Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  MAC_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ma0, ma1, mb, p));
+  MAC_LAUNCH_CHECK();
+  return MAC_OK;
+}
+
+inline int tc2_gemm_dispatch(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtensorMap& mb,
+                             const TcGemmParams& p, cudaStream_t stream) {
+  switch (p.epi) {
+    case TC_EPI_P: return tc2_gemm_launch_t<TC_EPI_P, MAC_ACT_NON>(ma0, ma1, mb, p, stream);
+    case TC_EPI_LOGITS: return tc2_gemm_launch_t<TC_EPI_LOGITS, MAC_ACT_NON>(ma0, ma1, mb, p, stream);
+    case TC_EPI_ACT:
+      if (p.act == MAC_ACT_ELU) return tc2_gemm_launch_t<TC_EPI_ACT, MAC_ACT_ELU>(ma0, ma1, mb, p, stream);
+      if (p.act == MAC_ACT_NON) return tc2_gemm_launch_t<TC_EPI_ACT, MAC_ACT_NON>(ma0, ma1, mb, p, stream);
+      return MAC_ERR_UNSUPPORTED;
+    case TC_EPI_F32:
+      if (p.act == MAC_ACT_NON) return tc2_gemm_launch_t<TC_EPI_F32, MAC_ACT_NON>(ma0, ma1, mb, p, stream);
+      if (p.act == MAC_ACT_ELU) return tc2_gemm_launch_t<TC_EPI_F32, MAC_ACT_ELU>(ma0, ma1, mb, p, stream);
+      if (p.act == MAC_ACT_TANH) return tc2_gemm_launch_t<TC_EPI_F32, MAC_ACT_TANH>(ma0, ma1, mb, p, stream);
+      return MAC_ERR_UNSUPPORTED;
+  }
+  return MAC_ERR_UNSUPPORTED;
+}
+
 // Tile shape: minimise rounds-over-the-SMs x per-tile time, per-tile time = max(MMA cycles, bytes / 64 B/clk) per k-block
 // (256x256: 1024, 128x256: 768, 128x128: 512).  Returns BM*1000 + BN.
 inline int tc_pick_tile(int M, int N) {
@@ -516,6 +899,26 @@ inline int tc_gemm_launch(const void* a0, int K0, const void* a1, int K1, const 
     if ((v == 128128 || v == 128256 || v == 256256) && p.N % (v % 1000) == 0) tile = v;
   }
   if (const char* e = getenv("MAC_TC_DEBUG")) p.debug = atoi(e);
+  // cta_group::2 pair kernel (opt-in while it is being qualified): MAC_TC_PAIR=1
+  bool pair = false;
+  if (const char* e = getenv("MAC_TC_PAIR")) pair = atoi(e) != 0 && (p.N % 256 == 0) && p.M > 128;
+  if (pair) {
+    if (nparts_per_row) *nparts_per_row = (p.N / 256) * 2;
+    p.K = K0 + K1;
+    p.kblocks0 = K0 / TC_BK;
+    CUtensorMap ma0, ma1, mb;
+    int st = make_tmap_2d(&ma0, a0, 1, (uint64_t)p.M, (uint64_t)K0, (uint64_t)K0 * 2, 128, TC_BK, 1);
+    if (st != MAC_OK) return st;
+    if (K1 > 0) {
+      st = make_tmap_2d(&ma1, a1, 1, (uint64_t)p.M, (uint64_t)K1, (uint64_t)K1 * 2, 128, TC_BK, 1);
+      if (st != MAC_OK) return st;
+    } else {
+      ma1 = ma0;
+    }
+    st = make_tmap_2d(&mb, wt, 1, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)p.K * 2, 128, TC_BK, 1);
+    if (st != MAC_OK) return st;
+    return tc2_gemm_dispatch(ma0, ma1, mb, p, stream);
+  }
   const int BM = tile / 1000, BN = tile % 1000;
   if (nparts_per_row) *nparts_per_row = (p.N / BN) * (BM == 256 ? 1 : 2);
   p.K = K0 + K1;

@@ -11,9 +11,10 @@ Wt = torch.empty(N, K, dtype=torch.bfloat16, device="cuda")
 L.check(lib.mac_pack_weight_bf16(L.ptr(W), L.ptr(Wt), K, N, L.stream_ptr()))
 bias = torch.zeros(N, device="cuda")
 y = torch.empty(M, N, device="cuda")
-for bn in ("128128", "128256", "256256"):
-    for dbg in ("1", "3", "5"):
-        os.environ["MAC_TC_TILE"] = bn
+for bn in ("256256", "pair"):
+    os.environ["MAC_TC_PAIR"] = "1" if bn == "pair" else "0"
+    for dbg in ("0", "1"):
+        os.environ["MAC_TC_TILE"] = "256256"
         os.environ["MAC_TC_DEBUG"] = dbg
         for x in xs:
             L.check(lib.mac_linear_tc_fwd(L.ptr(x), L.ptr(Wt), L.ptr(bias), 3, L.ptr(y), M, K, N, L.stream_ptr()))
