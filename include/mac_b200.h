@@ -149,6 +149,16 @@ size_t mac_write_workspace_bytes(int B, int d);
 int mac_bcast_mul(const float* x, const float* v, float mul_bias, float* out, int B, int N, int d, mac_stream_t stream);
 /* out = act(x) elementwise */
 int mac_activation(const float* x, int act, float* out, long long n, mac_stream_t stream);
+/* ---- general (unfused) path: primitives for the flag combinations outside mac_read_fwd / mac_write_fwd ---- */
+/* out[r] = sum_s x_s[r,:] . w[k-range of s] + b      (ops.linear with outDim == 1 on concatenated inputs, ops.py:316-317) */
+int mac_rowdot_fwd(const float* const* x_segs, const int* k_segs, const int* ldx, int nseg, const float* w, float b,
+                   float* out, long long R, mac_stream_t stream);
+/* att = softmax(logits - 1e30*[m >= len]) (lengths may be NULL); out[b,:] = sum_m att[b,m] * feats[b,m,:]   (ops.py:143-150, 243-247) */
+int mac_attend_fwd(const float* logits, const int32_t* lengths, const float* feats, long long feat_bstride,
+                   long long feat_rstride, float* att, float* out, int B, int M, int d, mac_stream_t stream);
+/* ops.mul interaction on a broadcast operand (ops.py:694-713): mode 0 MUL (x+mb)*(v+mb); 1 BL x*v + bias[k]; 2 ADD tanh(x+v) */
+int mac_bcast_op(const float* x, const float* v, int mode, float mul_bias, const float* bias, float* out,
+                 int B, int N, int d, mac_stream_t stream);
 /* variational / plain dropout: out = x / keep * [u >= 1-keep]  with u from mac_dropout_uniform(seed, site, step) */
 int mac_dropout_fwd(const float* x, float keep, uint64_t seed, int site, int step, float* out, long long n,
                     mac_stream_t stream);

@@ -68,6 +68,10 @@ PROTOTYPES = {
     "mac_clip_adam_ema_step": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_ll, c_f, c_f, c_f, c_f, c_f, c_f, c_int, c_f, c_fp, c_fp,
                                        c_sz, c_fp]),
     "mac_optimizer_workspace_bytes": (c_sz, []),
+    "mac_rowdot_fwd": (c_int, [ctypes.POINTER(c_fp), ctypes.POINTER(c_int), ctypes.POINTER(c_int), c_int, c_fp, c_f, c_fp,
+                               c_ll, c_fp]),
+    "mac_attend_fwd": (c_int, [c_fp, c_fp, c_fp, c_ll, c_ll, c_fp, c_fp, c_int, c_int, c_int, c_fp]),
+    "mac_bcast_op": (c_int, [c_fp, c_fp, c_int, c_f, c_fp, c_fp, c_int, c_int, c_int, c_fp]),
     "mac_pack_weight_bf16": (c_int, [c_fp, c_fp, c_int, c_int, c_fp]),
     "mac_linear_tc_fwd": (c_int, [c_fp, c_fp, c_fp, c_int, c_fp, c_int, c_int, c_int, c_fp]),
 }

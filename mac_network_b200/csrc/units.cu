@@ -342,3 +342,116 @@ extern "C" int mac_linear_tc_fwd(const void* x_bf16, const void* wt_bf16, const 
   p.M = M; p.N = n_out; p.epi = TC_EPI_F32; p.act = act; p.bias = b; p.outf = y; p.ldo = n_out; p.rows_per_batch = 1;
   return tc_gemm_launch(x_bf16, K, nullptr, 0, wt_bf16, p, stream);
 }
+
+// ------------------------------------------------------------------------------------------------ general (unfused) path
+// Primitives that let the host compose the cell for flag combinations outside the fused read/write kernels
+// (SURVEY.md section 8(a) "P2": controlConcatWords/Proj, read*AttType in {BL, ADD}, readCtrlConcatKB, readSmryKBProj,
+// writeInputs in {MEM, INFO, SUM}, ...).  Not performance-tuned; same arithmetic order as the reference ops.
+namespace mac {
+// out[r] = sum over segments of x_s[r,:] . w[koff_s:...] + b      (ops.linear with outDim == 1, ops.py:316-317)
+__global__ void __launch_bounds__(256) rowdot_kernel(const float* x0, const float* x1, const float* x2, int k0, int k1,
+                                                    int k2, int ld0, int ld1, int ld2, const float* __restrict__ w,
+                                                    float b, float* __restrict__ out, long long R) {
+  const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= R) return;
+  float acc = 0.f;
+  for (int k = lane; k < k0; k += 32) acc = fmaf(x0[r * ld0 + k], __ldg(w + k), acc);
+  if (x1) for (int k = lane; k < k1; k += 32) acc = fmaf(x1[r * ld1 + k], __ldg(w + k0 + k), acc);
+  if (x2) for (int k = lane; k < k2; k += 32) acc = fmaf(x2[r * ld2 + k], __ldg(w + k0 + k1 + k), acc);
+  acc = warp_sum(acc);
+  if (lane == 0) out[r] = acc + b;
+}
+
+// att[b,:] = softmax(logits[b,:] - 1e30*[m >= len[b]]);  out[b,:] = sum_m att[b,m] * feats[b,m,:]
+// grid (ceil(d/128), B), 128 threads; feats row (b,m) at feats + b*bstride + m*rstride
+__global__ void __launch_bounds__(128) attend_kernel(const float* __restrict__ logits, const int32_t* __restrict__ lengths,
+                                                    const float* __restrict__ feats, long long bstride, long long rstride,
+                                                    float* __restrict__ att, float* __restrict__ out, int M, int d) {
+  extern __shared__ float s_a[];
+  __shared__ float s_red[4];
+  const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int len = lengths ? min(max(lengths[b], 0), M) : M;
+  float mx = -INFINITY;
+  for (int m = tid; m < M; m += 128) {
+    const float l = logits[(size_t)b * M + m] + (m < len ? 0.f : -1e30f);
+    s_a[m] = l;
+    mx = fmaxf(mx, l);
+  }
+  mx = warp_max(mx);
+  if (lane == 0) s_red[warp] = mx;
+  __syncthreads();
+  mx = fmaxf(fmaxf(s_red[0], s_red[1]), fmaxf(s_red[2], s_red[3]));
+  __syncthreads();
+  float sum = 0.f;
+  for (int m = tid; m < M; m += 128) {
+    const float e = expf(s_a[m] - mx);
+    s_a[m] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  if (lane == 0) s_red[warp] = sum;
+  __syncthreads();
+  const float inv = 1.f / (s_red[0] + s_red[1] + s_red[2] + s_red[3]);
+  for (int m = tid; m < M; m += 128) {
+    const float a = s_a[m] * inv;
+    s_a[m] = a;
+    if (blockIdx.x == 0) att[(size_t)b * M + m] = a;
+  }
+  __syncthreads();
+  const int k = blockIdx.x * 128 + tid;
+  if (k < d) {
+    const float* f = feats + (size_t)b * bstride + k;
+    float acc = 0.f;
+    for (int m = 0; m < M; ++m) acc = fmaf(s_a[m], f[(size_t)m * rstride], acc);
+    out[(size_t)b * d + k] = acc;
+  }
+}
+
+// ops.mul interaction modes on a broadcast operand (ops.py:694-713): mode 0 MUL (x+mb)*(v+mb); 1 BL x*v + bias[k];
+// 2 ADD tanh(x+v)
+__global__ void bcast_op_kernel(const float* __restrict__ x, const float* __restrict__ v, int mode, float mb,
+                                const float* __restrict__ bias, float* __restrict__ out, long long total, int N, int d) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long long row = i / d;
+  const int k = (int)(i - row * d);
+  const float a = x[i], y = v[(row / N) * d + k];
+  out[i] = mode == 0 ? (a + mb) * (y + mb) : mode == 1 ? a * y + (bias ? bias[k] : 0.f) : tanhf(a + y);
+}
+}  // namespace mac
+
+extern "C" int mac_rowdot_fwd(const float* const* x_segs, const int* k_segs, const int* ldx, int nseg, const float* w,
+                              float b, float* out, long long R, mac_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!x_segs || !k_segs || !ldx || nseg < 1 || nseg > 3 || !w || !out || R <= 0) return MAC_ERR_INVALID;
+  const float* x[3] = {nullptr, nullptr, nullptr};
+  int k[3] = {0, 0, 0}, ld[3] = {0, 0, 0};
+  for (int i = 0; i < nseg; ++i) { x[i] = x_segs[i]; k[i] = k_segs[i]; ld[i] = ldx[i]; }
+  rowdot_kernel<<<(unsigned)((R + 7) / 8), 256, 0, stream>>>(x[0], x[1], x[2], k[0], k[1], k[2], ld[0], ld[1], ld[2], w, b,
+                                                            out, R);
+  MAC_LAUNCH_CHECK();
+  return MAC_OK;
+}
+
+extern "C" int mac_attend_fwd(const float* logits, const int32_t* lengths, const float* feats, long long feat_bstride,
+                              long long feat_rstride, float* att, float* out, int B, int M, int d, mac_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!logits || !feats || !att || !out || B <= 0 || M <= 0 || d <= 0) return MAC_ERR_INVALID;
+  if ((size_t)M * 4 > 160 * 1024) return MAC_ERR_UNSUPPORTED;
+  MAC_CUDA_TRY(cudaFuncSetAttribute(attend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, M * 4 + 16));
+  attend_kernel<<<dim3((d + 127) / 128, B), 128, (size_t)M * 4 + 16, stream>>>(logits, lengths, feats, feat_bstride,
+                                                                             feat_rstride, att, out, M, d);
+  MAC_LAUNCH_CHECK();
+  return MAC_OK;
+}
+
+extern "C" int mac_bcast_op(const float* x, const float* v, int mode, float mul_bias, const float* bias, float* out,
+                            int B, int N, int d, mac_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!x || !v || !out || B <= 0 || N <= 0 || d <= 0 || mode < 0 || mode > 2) return MAC_ERR_INVALID;
+  const long long total = (long long)B * N * d;
+  bcast_op_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(x, v, mode, mul_bias, bias, out, total, N, d);
+  MAC_LAUNCH_CHECK();
+  return MAC_OK;
+}

@@ -144,16 +144,12 @@ class MACCell(object):
         if not isinstance(self.cfg, MACConfig):
             raise TypeError("config must be a MACConfig")
         self.cfg.validate()
-        if not self.cfg.is_fast_path:
-            raise NotImplementedError(
-                "this flag set is outside the fused sm_100a path (shipped args*.txt family); see DESIGN.md section 6")
         c = self.cfg
-        unsupported = [k for k in ("controlConcatWords", "controlProj", "controlInWordsProj", "controlOutWordsProj",
-                                   "unsharedCells", "writeInfoProj", "writeMergeCtrl", "writeConcatMul")
-                       if getattr(c, k)]
-        if unsupported or c.writeInputs != "BOTH" or c.writeInfoAct != "NON" or c.writeMemAct != "NON" \
-                or not c.writeMemProj:
-            raise NotImplementedError("flags outside the fused path: %s" % unsupported)
+        # which units run on the fused sm_100a kernels; everything else goes through the general (composed) path
+        self._fused_read = c.is_fast_path
+        self._fused_write = (c.writeInputs == "BOTH" and c.writeMemProj and not c.writeConcatMul and not c.writeInfoProj
+                             and c.writeInfoAct == "NON" and not c.writeMergeCtrl and c.writeMemAct == "NON")
+        self._fused_control = not (c.controlConcatWords or c.controlProj)
         for t in (vecQuestions, questionCntxWords, knowledgeBase):
             if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
                 raise ValueError("inputs must be contiguous CUDA float32 tensors")
@@ -176,12 +172,15 @@ class MACCell(object):
         self.iteration = 0
         self.L = self.params.L
         self.ws = _Workspaces(self.lib, B, N, d, self.prec, self.device)
-        self._hoist = not (c.controlFeedPrev or c.controlWholeQ or c.controlContinuous)
+        self._hoist = (not (c.controlFeedPrev or c.controlWholeQ or c.controlContinuous or c.unsharedCells)
+                       and self._fused_control)
         self._rw = {}
         self.kb_bf16 = None
         self.save_for_backward = bool(save_for_backward)
-        if self.save_for_backward and self.prec != PREC["fp32"]:
-            raise NotImplementedError("backward is implemented on the fp32 path (DESIGN.md section 9)")
+        if self.save_for_backward and (self.prec != PREC["fp32"] or not (self._fused_read and self._fused_write and self._hoist)):
+            raise NotImplementedError("backward is implemented on the fused fp32 path (DESIGN.md section 9)")
+        if self.prec != PREC["fp32"] and not self._fused_read:
+            raise NotImplementedError("the tensor-core projections cover the fused read unit only")
 
     # ------------------------------------------------------------------ reference properties
     @property
@@ -243,6 +242,12 @@ class MACCell(object):
         self.contControl = c0                                                          # mac_cell.py:553
         words = self.questionCntxWords if c.controlContextual else self.questionWords  # mac_cell.py:570
         self.inWords = self.outWords = words
+        if c.controlInWordsProj or c.controlOutWordsProj:                                # mac_cell.py:578-581
+            Wp, bp = self.params.lin("", "wordsProj")
+            S_ = words.shape[1]
+            pWords = self._linear([words.view(B * S_, d)], Wp, bp, self._new(B * S_, d)).view(B, S_, d)
+            self.inWords = pWords if c.controlInWordsProj else words
+            self.outWords = pWords if c.controlOutWordsProj else words
         self._att_q = self._new(L, B, words.shape[1])
         self._att_kb = self._new(L, B, self.N)
         self._gate = self._new(L, B, d) if c.writeGate else None
@@ -317,6 +322,17 @@ class MACCell(object):
         att = _att_out if _att_out is not None else self._new(B, S)
         out = _out if _out is not None else self._new(B, d)
         lsc = sc + "inter2logits/linearLayerlogits/"
+        if not self._fused_control:
+            # general path (mac_cell.py:155-181 with controlConcatWords / controlProj)
+            inter = self._bcast(inWords.reshape(B * S, d), newContControl, 0, S, mul_bias=0.0)   # plain product, mac_cell.py:155
+            segs = [inter] + ([inWords.reshape(B * S, d)] if c.controlConcatWords else [])
+            if c.controlProj:
+                segs = [self._ops_linear(segs, sc, "", act=c.controlProjAct)]
+            logits = self._rowdot(segs, lsc)
+            check(self.lib.mac_attend_fwd(ptr(logits), ptr(questionLengths), ptr(outWords), S * d, d, ptr(att), ptr(out),
+                                          B, S, d, stream_ptr()), "mac_attend_fwd")
+            self.attentions["question"].append(att)
+            return (newContControl if c.controlContinuous else out), newContControl
         self._attend(newContControl, 0, d, inWords, S * d, d, outWords, S * d, d, questionLengths,
                      self.params[lsc + "weights/weight"], self.params.scalar(lsc + "biases/bias"), att, out, 1, S)
         self.attentions["question"].append(att)
@@ -360,6 +376,8 @@ class MACCell(object):
                 memory = self._dropout(memory, keep_m, _lib.SITE_MEM_PLAIN, i, self._mem_in)
         att = _att_out if _att_out is not None else self._new(B, N)
         info = _out if _out is not None else self._new(B, d)
+        if not self._fused_read:
+            return self._read_general(knowledgeBase, memory, control, name, att, info)
         if self.save_for_backward and _save is None:
             _save = self._save[i]
             self._mem_in_hist[i].copy_(memory)
@@ -377,6 +395,8 @@ class MACCell(object):
         c, B, d = self.cfg, self.B, self.d
         sc = "MACCell/write" + name + "/"
         i = self.iteration
+        if not self._fused_write:
+            return self._write_general(memory, info, control, contControl, name, _out, _gate_out)
         selfSmry = None
         if c.writeSelfAtt:
             selfControl = contControl if c.writeSelfAttMod == "CONT" else control
@@ -408,6 +428,153 @@ class MACCell(object):
             self.attentions["gate"].append(gate)
         return out
 
+    # ------------------------------------------------------------------ general (composed) path
+    def _act_code(self, act):
+        return ACT["ELU"] if (act == "RELU" and self.cfg.relu == "ELU") else ACT["RELU_STD"] if act == "RELU" else ACT[act]
+
+    def _ops_linear(self, xs, scope, name, act="NON", bias_const=0.0):
+        """ops.linear incl. the nested "<name>_2" layer when act != NON (ops.py:298-333); xs: list of 2-D segments."""
+        W, b = self.params.lin(scope, name)
+        y = self._linear(xs, W, b, self._new(xs[0].shape[0], W.shape[1]), act=act, bias_const=bias_const)
+        if act != "NON":
+            W2, b2 = self.params.lin(scope + "linearLayer" + name + "/", name + "_2")
+            y = self._linear([y], W2, b2, self._new(y.shape[0], W2.shape[1]))
+        return y
+
+    def _rowdot(self, xs, lscope):
+        """outDim == 1 linear (vector weight, scalar bias) over concatenated segments -> [R]."""
+        n, R = len(xs), xs[0].shape[0]
+        out = self._new(R)
+        arr_p = (ctypes.c_void_p * n)(*[x.data_ptr() for x in xs])
+        arr_k = (ctypes.c_int * n)(*[x.shape[1] for x in xs])
+        arr_ld = (ctypes.c_int * n)(*[x.stride(0) for x in xs])
+        check(self.lib.mac_rowdot_fwd(arr_p, arr_k, arr_ld, n, ptr(self.params[lscope + "weights/weight"]),
+                                      self.params.scalar(lscope + "biases/bias"), ptr(out), R, stream_ptr()), "mac_rowdot_fwd")
+        return out
+
+    def _bcast(self, x2d, v, mode, N, bias=None, mul_bias=None):
+        """ops.mul interaction of x [B*N, d] with the per-sample vector v [B, d] (MUL / BL tail / ADD)."""
+        out = self._new(*x2d.shape)
+        mb = self.cfg.mulBias if mul_bias is None else mul_bias
+        check(self.lib.mac_bcast_op(ptr(x2d), ptr(v), mode, float(mb), ptr(bias), ptr(out), self.B, N,
+                                    x2d.shape[1], stream_ptr()), "mac_bcast_op")
+        return out
+
+    def _act(self, x, act):
+        if act == "NON":
+            return x
+        out = self._new(*x.shape)
+        check(self.lib.mac_activation(ptr(x), self._act_code(act), ptr(out), x.numel(), stream_ptr()), "mac_activation")
+        return out
+
+    def _mul_general(self, x2d, y, dim, N, scope, name, proj, inter_mod, concat_x, concat_proj):
+        """ops.mul (ops.py:668-725) -> (list of segments [B*N, .], projected x or None)."""
+        sc = scope + "mul" + name + "/"
+        orig_x, proj_x = x2d, None
+        if proj is not None:
+            xn, yn = ("proj", "proj") if proj["shared"] else ("projX", "projY")
+            x2d = self._ops_linear([x2d], sc, xn)
+            y = self._ops_linear([y], sc, yn)
+            proj_x = x2d
+        if inter_mod == "MUL":
+            inter = self._bcast(x2d, y, 0, N)
+        elif inter_mod == "BL":
+            W, b = self.params[sc + "weights/weight"], self.params[sc + "biases/bias"]
+            xw = self._linear([x2d], W, None, self._new(x2d.shape[0], W.shape[1]))
+            inter = self._bcast(xw, y, 1, N, bias=b)
+        else:  # ADD
+            inter = self._bcast(x2d, y, 2, N)
+        segs = [inter]
+        if concat_x:
+            segs.append(proj_x if concat_proj else orig_x)
+        return segs, proj_x
+
+    def _read_general(self, knowledgeBase, memory, control, name, att, info):
+        """mac_cell.py:209-277 composed from primitives (flag sets outside the fused read kernel)."""
+        c, B, N, d = self.cfg, self.B, self.N, self.d
+        if self.dropouts["read"] < 1.0:
+            raise NotImplementedError("train-mode read dropout on the general path (use the fused flag family)")
+        sc = "MACCell/read" + name + "/"
+        kb2 = knowledgeBase.view(B * N, d)
+        proj = {"shared": c.readProjShared} if c.readProjInputs else None
+        segs, projectedKB = self._mul_general(kb2, memory, c.memDim, N, sc, "memInter", proj, c.readMemAttType,
+                                              c.readMemConcatKB, c.readMemConcatProj)
+        if c.readMemProj:
+            segs = [self._ops_linear(segs, sc, "memKbProj", act=c.readMemAct)]
+        if c.readCtrl:
+            segs, _ = self._mul_general(segs[0], control, 0, N, sc, "ctrlInter", None, c.readCtrlAttType, False, False)
+            if c.readCtrlConcatKB:
+                segs.append(projectedKB if c.readCtrlConcatProj else kb2)
+            segs = [self._act(x, c.readCtrlAct) for x in segs]          # act(concat) == concat(act)
+        logits = self._rowdot(segs, sc + "inter2att/inter2logits/linearLayerlogits/")
+        feats = projectedKB if c.readSmryKBProj else kb2
+        dd = feats.shape[1]
+        check(self.lib.mac_attend_fwd(ptr(logits), None, ptr(feats), N * dd, dd, ptr(att), ptr(info), B, N, dd,
+                                      stream_ptr()), "mac_attend_fwd")
+        self.attentions["kb"].append(att)
+        return info
+
+    def _write_general(self, memory, info, control, contControl, name, _out, _gate_out):
+        """mac_cell.py:305-375 composed from primitives."""
+        c, B, d = self.cfg, self.B, self.d
+        sc = "MACCell/write" + name + "/"
+        i = self.iteration
+        if c.writeInfoProj:
+            info = self._ops_linear([info], sc, "info")
+        info = self._act(info, c.writeInfoAct)
+        selfSmry = None
+        if c.writeSelfAtt:
+            selfControl = contControl if c.writeSelfAttMod == "CONT" else control
+            selfControl = self._ops_linear([selfControl], sc, "ctrlProj")
+            lsc = sc + "inter2attselfAttention/inter2logits/linearLayerlogits/"
+            satt, selfSmry = self._new(B, i + 1), self._new(B, d)
+            self._attend(selfControl, 0, selfControl.stride(0), self._hc, d, B * d, self._hm, d, B * d, None,
+                         self.params[lsc + "weights/weight"], self.params.scalar(lsc + "biases/bias"), satt, selfSmry,
+                         1, i + 1)
+            self.attentions["self"].append(satt)
+        if c.writeInputs == "INFO":
+            segs = [info]
+        elif c.writeInputs == "SUM":
+            ssum = memory.clone()
+            check(self.lib.mac_axpy(ptr(ssum), ptr(info), 1.0, ssum.numel(), stream_ptr()), "mac_axpy")
+            segs = [ssum]
+        elif c.writeInputs == "BOTH":
+            segs = [memory, info]
+            if c.writeConcatMul:                                                          # ops.py:65-78
+                prod = self._new(B, d)
+                check(self.lib.mac_bcast_op(ptr(memory), ptr(info), 0, 0.0, None, ptr(prod), B, 1, d, stream_ptr()), "mul")
+                segs.append(prod)
+        else:  # MEM
+            segs = [memory]
+        if selfSmry is not None:
+            segs.append(selfSmry)
+        if c.writeMergeCtrl:
+            segs.append(control)
+        dim = sum(x.shape[1] for x in segs)
+        out = _out if _out is not None else self._new(B, d)
+        if c.writeMemProj or dim != c.memDim:
+            if len(segs) > 4:
+                raise NotImplementedError("more than four concatenated write inputs")
+            W, b = self.params.lin(sc, "newMemory")
+            newMemory = self._linear(segs, W, b, self._new(B, d))
+        else:
+            newMemory = segs[0]
+        newMemory = self._act(newMemory, c.writeMemAct)
+        if c.writeGate:
+            Wg, bg = self.params.lin(sc, "gate")
+            z = self._linear([control], Wg, bg, _gate_out if _gate_out is not None else self._new(B, d), act="SIGMOID",
+                             bias_const=c.writeGateBias)
+            self.attentions["gate"].append(z)
+            # m' * z + m * (1 - z) = m + z * (m' - m)
+            diff = newMemory.clone()
+            check(self.lib.mac_axpy(ptr(diff), ptr(memory), -1.0, diff.numel(), stream_ptr()), "mac_axpy")
+            zd = self._new(B, d)
+            check(self.lib.mac_bcast_op(ptr(diff), ptr(z), 0, 0.0, None, ptr(zd), B, 1, d, stream_ptr()), "mul")
+            newMemory = memory.clone()
+            check(self.lib.mac_axpy(ptr(newMemory), ptr(zd), 1.0, zd.numel(), stream_ptr()), "mac_axpy")
+        out.copy_(newMemory)
+        return out
+
     # ------------------------------------------------------------------ one reasoning step (mac_cell.py:420-480)
     def __call__(self, inputs, state, scope=None):
         c, B, d = self.cfg, self.B, self.d
@@ -415,6 +582,7 @@ class MACCell(object):
         if i >= self.L:
             raise IndexError("iteration %d >= netLength %d the parameters were built for" % (i, self.L))
         control, memory = state.control, state.memory
+        cellName = str(i) if c.unsharedCells else ""                                    # mac_cell.py:434-438
         if self._hoist:
             newControl = self._hc[i + 1]
             self.contControl = self._ci[:, i * d:(i + 1) * d] if c.controlInputUnshared else self._ci
@@ -426,18 +594,19 @@ class MACCell(object):
             W, b = self.params.lin("MACCell/", nameU)
             ci = self._linear([u], W, b, self._new(B, d))
             newControl, self.contControl = self.control(ci, self.inWords, self.outWords, self.questionLengths,
-                                                        control, self.contControl, _att_out=self._att_q[i],
-                                                        _out=self._hc[i + 1])
+                                                        control, self.contControl, name=cellName,
+                                                        _att_out=self._att_q[i], _out=self._hc[i + 1])
             if c.controlContinuous:
                 self._hc[i + 1].copy_(newControl)
                 newControl = self._hc[i + 1]
         if c.controlWholeQ:                                                            # mac_cell.py:455-456
             self._hc[i + 1].copy_(self.vecQuestions)
             newControl = self._hc[i + 1]
-        info = self.read(self.knowledgeBase, memory, newControl, _att_out=self._att_kb[i], _out=self._hi[i + 1])
+        info = self.read(self.knowledgeBase, memory, newControl, name=cellName, _att_out=self._att_kb[i],
+                         _out=self._hi[i + 1])
         if c.writeDropout < 1.0 and self.dropouts["write"] < 1.0:                      # mac_cell.py:461-463
             info = self._dropout(info, self.dropouts["write"], _lib.SITE_WRITE_INFO, i, self._hi[i + 1])
-        newMemory = self.write(memory, info, newControl, self.contControl, _out=self._hm[i + 1],
+        newMemory = self.write(memory, info, newControl, self.contControl, name=cellName, _out=self._hm[i + 1],
                                _gate_out=None if self._gate is None else self._gate[i])
         self._set_histories(i + 1)                                                     # mac_cell.py:472-474
         return self.none, MACCellTuple(newControl, newMemory)

@@ -15,8 +15,7 @@ from tests._util import golden_cases, load_golden, rebuild, max_rel
 pytestmark = pytest.mark.gpu
 
 TOL = 1e-4
-FAST_FIXTURES = [c for c in golden_cases() if not c.startswith("p2_") and not c.startswith("novardp")] + \
-                ["novardp_train_small"]
+FAST_FIXTURES = golden_cases()       # every fixture: the shipped flag files AND the P2 flag combinations
 
 
 def _to_dev(inputs):
