@@ -408,6 +408,13 @@ def run_ours(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         t_dev, t_e2e = float(tt[0]), float(tt[1])
 
+    # ---- data-parallel training arm (all ranks take part: it contains the path's one collective)
+    train = None
+    if not args.skip_train:
+        del dev, slots
+        torch.cuda.empty_cache()
+        train = train_arm(min(args.steps, 4), 2, rank, world, dist)
+
     if rank == 0:
         roofs = kernel_rooflines(shape, args.prec, pk)
         cpu, _ = cpu_reference(cfg, shape, pv) if not args.skip_cpu else ({"value": None, "unit": UNIT, "cores": 0,
@@ -436,10 +443,55 @@ def run_ours(args):
             "rooflines_all": roofs,
             "peaks": pk,
             "cpu_baseline": cpu,
+            "train": train,
         }
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
+
+
+def train_arm(steps, warmup, rank, world, dist):
+    """Short DP-training measurement used inside the default (inference) bench line: returns a dict or None."""
+    from mac_network_b200.dp import DPTrainer
+    shape = SHAPES[WORKLOAD]
+    B, S, N, d, L = shape
+    cfg = MACConfig.args("args", netLength=L)
+    pv = perturb_biases(init_params(cfg, L, seed=100), seed=101)
+    tr = DPTrainer(cfg, L, param_values=pv, seed=7, rank=rank, world=world)
+    inp = make_inputs(B, S, N, d, seed=4321 + 1000 * rank)
+    batch = {k: torch.from_numpy(v).cuda() for k, v in inp.items()}
+    g = torch.Generator(device="cuda").manual_seed(5 + rank)
+    tc, tm = torch.randn(B, d, device="cuda", generator=g), torch.randn(B, d, device="cuda", generator=g)
+    for _ in range(warmup):
+        tr.train_step(0, batch, tc, tm, B * world)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        tr.train_step(0, batch, tc, tm, B * world)
+    e1.record()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = e0.elapsed_time(e1) * 1e-3
+    sync = True
+    if dist is not None:
+        tt = torch.tensor([t], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t = float(tt[0])
+        chk = torch.stack([tr.params.flat.double().sum(), tr.params.flat.double().abs().sum()])
+        allc = [torch.zeros_like(chk) for _ in range(world)]
+        dist.all_gather(allc, chk)
+        sync = all(bool(torch.equal(allc[0], c)) for c in allc)
+    out = {"value": steps * L * world / t, "unit": UNIT, "ms_per_step": t / steps * 1e3, "steps": steps,
+           "what": "DP training step of the cell: train-mode forward + hand-written backward + all-reduce of the flat "
+                   "gradient bucket (%.1f MB, NCCL) + fused clip/Adam/EMA; B=%d per GPU, fp32 path" % (tr.params.numel * 4 / 1e6, B),
+           "replicas_in_sync": sync}
+    del tr
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_train(args):
@@ -571,6 +623,7 @@ def main():
     ap.add_argument("--prec", default="bf16", choices=["fp32", "bf16"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-train", action="store_true", help="skip the short DP-training arm of the default run")
     ap.add_argument("--mode", default="infer", choices=["infer", "train"])
     ap.add_argument("--streams", type=int, default=4, help="independent passes in flight (each on its own stream)")
     ap.add_argument("--rooflines-only", action="store_true", help="only the per-kernel measurements (for ncu)")
