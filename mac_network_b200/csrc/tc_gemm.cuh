@@ -954,19 +954,30 @@ __global__ void pack_weight_bf16_kernel(const float* __restrict__ W, __nv_bfloat
   }
 }
 
+// training mode: bf16 copy of dropout(KB) for this step (ops.py:678), same Philox stream as the fp32 path
+__global__ void dropout_cast_bf16_kernel(const float4* __restrict__ x, uint2* __restrict__ out, uint32_t thresh,
+                                         float scale, uint64_t seed, int site, int step, long long n4) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 v = x[i];
+  const Philox4 r = philox4x32_10(seed, (uint64_t)i, (uint32_t)site, (uint32_t)step);
+  const float a = ((r.x >> 8) >= thresh) ? v.x * scale : 0.f, b = ((r.y >> 8) >= thresh) ? v.y * scale : 0.f;
+  const float c = ((r.z >> 8) >= thresh) ? v.z * scale : 0.f, d = ((r.w >> 8) >= thresh) ? v.w * scale : 0.f;
+  out[i] = make_uint2(pack_bf16(a, b), pack_bf16(c, d));
+}
+
 // extra workspace of the bf16 read chain: P, P*y, H (+ I1 when saving for backward), each [B*N, d] bf16
 inline size_t tc_read_extra_workspace_bytes(int B, int N, int d) {
-  return (size_t)4 * (((size_t)B * N * d * 2 + 1023) & ~(size_t)1023) + 1024;
+  return (size_t)5 * (((size_t)B * N * d * 2 + 1023) & ~(size_t)1023) + 1024;     // P, P*y, H, I1, dropout(KB)
 }
 
 // The read unit's three projections on tensor cores (see mac_read_fwd in mac_b200.h).
-inline int tc_read_chain(const void* kb_bf16, const float* y, const float* control, const mac_read_weights* w,
+inline int tc_read_chain(const float* kb_f32, const void* kb_bf16, const float* y, const float* control, const mac_read_weights* w,
                          uint32_t thr, float scale, uint64_t seed, int step, float* /*P_f32*/, float* /*H_f32*/,
                          float* /*I1_f32*/, float* parts, int* nparts, void* ws, size_t ws_bytes, int B, int N, int d,
                          bool save, cudaStream_t stream) {
   if (!kb_bf16 || !w->Wx_bf16 || !w->Wm_bf16 || !w->Wm2_bf16) return MAC_ERR_INVALID;
   if (d % 128) return MAC_ERR_UNSUPPORTED;
-  if (thr != 0) return MAC_ERR_UNSUPPORTED;      // training-mode dropout on the tensor-core path: not yet
   if (ws_bytes < tc_read_extra_workspace_bytes(B, N, d)) return MAC_ERR_WORKSPACE;
   const int M = B * N;
   const size_t slab = (((size_t)M * d * 2 + 1023) & ~(size_t)1023);
@@ -975,6 +986,15 @@ inline int tc_read_chain(const void* kb_bf16, const float* y, const float* contr
   __nv_bfloat16* PY = reinterpret_cast<__nv_bfloat16*>(base + slab);
   __nv_bfloat16* H = reinterpret_cast<__nv_bfloat16*>(base + 2 * slab);
   __nv_bfloat16* I1 = save ? reinterpret_cast<__nv_bfloat16*>(base + 3 * slab) : nullptr;
+  if (thr != 0) {
+    // A operand of the first projection = dropout(KB) (ops.py:678): TMA cannot mask in flight, so make this step's copy
+    __nv_bfloat16* kbd = reinterpret_cast<__nv_bfloat16*>(base + 4 * slab);
+    const long long n4 = (long long)M * d / 4;
+    dropout_cast_bf16_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(
+        reinterpret_cast<const float4*>(kb_f32), reinterpret_cast<uint2*>(kbd), thr, scale, seed, MAC_SITE_READ_KB, step, n4);
+    MAC_LAUNCH_CHECK();
+    kb_bf16 = kbd;
+  }
   TcGemmParams p{};
   p.M = M; p.N = d; p.rows_per_batch = N; p.ldo = d; p.seed = seed; p.step = step;
   // P = KB @ Wx + bx ; also P*y

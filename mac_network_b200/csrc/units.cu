@@ -182,7 +182,7 @@ extern "C" int mac_read_fwd(const float* kb, const void* kb_bf16, const float* m
   }
   int nparts = 0;
   if (prec == MAC_PREC_BF16) {
-    int st = tc_read_chain(kb_bf16, y, control, w, thr, scale, seed, step, P, H, I1, parts, &nparts,
+    int st = tc_read_chain(kb, kb_bf16, y, control, w, thr, scale, seed, step, P, H, I1, parts, &nparts,
                            ws + fp32_total, workspace_bytes - fp32_total, B, N, d, save != nullptr, stream);
     if (st != MAC_OK) return st;
   } else {

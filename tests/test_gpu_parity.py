@@ -177,3 +177,18 @@ def test_bf16_tensor_core_path(variant, shape):
     print("bf16 path max-rel errors:", errs)
     assert errs["control"] < 1e-4            # the control chain stays fp32
     assert errs["memory"] < 3e-2 and errs["info"] < 3e-2
+
+
+def test_bf16_train_mode_forward():
+    """Tensor-core path with training dropouts: same Philox masks as the fp32 path, so the oracle fed the kernels'
+    uniforms bounds the error the same way as in eval."""
+    B, S, N, d, L = 8, 10, 196, 512, 3
+    cfg = MACConfig.args("args", netLength=L, memDim=d, ctrlDim=d, attDim=d)
+    inputs = make_inputs(B, S, N, d, seed=81, dtype=np.float64)
+    params = perturb_biases(init_params(cfg, L, seed=82, dtype=np.float64), seed=83)
+    dp = (0.85, 0.85, 1.0)
+    got, cell = run_gpu(cfg, params, inputs, L, dropouts=dp, train=True, prec="bf16", seed=777)
+    ref = run_oracle(cfg, params, inputs, L, dropouts=dp, uniforms=cell.dropout_uniforms())
+    errs = {k: max_rel(got[k], ref[k]) for k in ("control", "memory", "info")}
+    print("bf16 train-mode max-rel errors:", errs)
+    assert errs["control"] < 1e-4 and errs["memory"] < 3e-2 and errs["info"] < 3e-2
