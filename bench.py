@@ -192,6 +192,14 @@ class Slot(object):
         return [c._hc[self.L], c._hm[self.L], c._att_kb, c._att_q]
 
 
+def ncu_traffic(key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[key]["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 def time_kernel(fns, iters=24, flush=None):
     """Average device time (s) per launch.  `fns` is a list of closures launching the SAME kernel on DIFFERENT
     buffers whose total footprint exceeds the 126 MB L2 (so every launch reads HBM); the launches are issued back
@@ -246,7 +254,8 @@ def kernel_rooflines(shape, prec, pk):
         t_cold = time_kernel(fns, iters=12, flush=flush)
         nbytes = B * N * d * (2 if bf16 else 4) + B * N * 4 * 4 + B * N * 4 + B * d * 4
         out["kb_attend_" + name] = {"bound": "hbm", "achieved": nbytes / t / 1e9, "peak": pk["hbm"], "unit": "GB/s",
-                                    "frac": nbytes / t / 1e9 / pk["hbm"], "traffic": None, "us": t * 1e6,
+                                    "frac": nbytes / t / 1e9 / pk["hbm"], "traffic": ncu_traffic("kb_attend_" + name),
+                                    "us": t * 1e6,
                                     "algorithmic_bytes": nbytes,
                                     "l2": "launches rotate over %d knowledge bases (%.0f MB > 126 MB L2), back to back"
                                           % (NB, NB * B * N * d * (2 if bf16 else 4) / 1e6),
@@ -278,15 +287,18 @@ def kernel_rooflines(shape, prec, pk):
     Wt = torch.empty(d, K, dtype=torch.bfloat16, device="cuda")
     L.check(lib.mac_pack_weight_bf16(L.ptr(W), L.ptr(Wt), K, d, L.stream_ptr()))
 
+    yb = torch.empty(M, d, device="cuda", dtype=torch.bfloat16)
+
     def mkt(x):
-        def gemm():
-            L.check(lib.mac_linear_tc_fwd(L.ptr(x), L.ptr(Wt), L.ptr(bias), 3, L.ptr(y), M, K, d, L.stream_ptr()))
+        def gemm():   # the form the read unit uses: ELU epilogue, bf16 output
+            L.check(lib.mac_linear_tc_fwd(L.ptr(x), L.ptr(Wt), L.ptr(bias), 3, L.ptr(yb), 1, M, K, d, L.stream_ptr()))
         return gemm
     t = time_kernel([mkt(x) for x in xb], iters=30)
     out["memKbProj_gemm_tc"] = {"bound": "tensor", "achieved": flops / t / 1e12, "peak": pk["tensor_burst"],
-                                "unit": "TFLOP/s", "frac": flops / t / 1e12 / pk["tensor_burst"], "traffic": None,
-                                "us": t * 1e6, "algorithmic_flops": flops,
-                                "note": "tcgen05 128x256x16 UMMA, [12544,1024]x[1024,512] bf16 -> fp32 out, burst peak"}
+                                "unit": "TFLOP/s", "frac": flops / t / 1e12 / pk["tensor_burst"],
+                                "traffic": ncu_traffic("tc_gemm_memKbProj"), "us": t * 1e6, "algorithmic_flops": flops,
+                                "note": "tcgen05 UMMA 256x256 tile, H = ELU([12544,1024] @ [1024,512] + b) bf16 in / bf16 out, "
+                                        "fp32 accumulate in TMEM; A rotates over 6 buffers (154 MB > L2); burst peak"}
     return out
 
 

@@ -172,10 +172,11 @@ int mac_cast_bf16(const float* x, void* out_bf16, long long n, mac_stream_t stre
  * mac_pack_weight_bf16: fp32 W[K, n_out] (the reference's [in, out] layout, ops.py:304) -> bf16 Wt[n_out, K], the
  *   K-major B operand tcgen05.mma consumes; call once per weight update.
  * mac_linear_tc_fwd: y[M,n_out] = act(x[M,K] @ W + b) with x bf16 row-major and W given as the packed Wt;
- *   fp32 accumulation in TMEM, fp32 output.  Requires K % 64 == 0 and n_out % 256 == 0.
+ *   fp32 accumulation in TMEM; output fp32, or bf16 when y_is_bf16 (the form the read-unit chain uses; act in
+ *   {NON, ELU}, b required).  Requires K % 64 == 0 and n_out % 128 == 0.
  * --------------------------------------------------------------------------------------------- */
 int mac_pack_weight_bf16(const float* W, void* Wt_bf16, int K, int n_out, mac_stream_t stream);
-int mac_linear_tc_fwd(const void* x_bf16, const void* wt_bf16, const float* b, int act, float* y,
+int mac_linear_tc_fwd(const void* x_bf16, const void* wt_bf16, const float* b, int act, void* y, int y_is_bf16,
                       int M, int K, int n_out, mac_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------

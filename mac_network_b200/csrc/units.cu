@@ -333,13 +333,19 @@ extern "C" int mac_pack_weight_bf16(const float* W, void* Wt_bf16, int K, int N,
   return MAC_OK;
 }
 
-extern "C" int mac_linear_tc_fwd(const void* x_bf16, const void* wt_bf16, const float* b, int act, float* y, int M,
-                                 int K, int n_out, mac_stream_t stream_) {
+extern "C" int mac_linear_tc_fwd(const void* x_bf16, const void* wt_bf16, const float* b, int act, void* y, int y_is_bf16,
+                                 int M, int K, int n_out, mac_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (!x_bf16 || !wt_bf16 || !y || M <= 0) return MAC_ERR_INVALID;
   if (!mac_b200_device_ok()) return MAC_ERR_ARCH;
   TcGemmParams p{};
-  p.M = M; p.N = n_out; p.epi = TC_EPI_F32; p.act = act; p.bias = b; p.outf = y; p.ldo = n_out; p.rows_per_batch = 1;
+  p.M = M; p.N = n_out; p.act = act; p.bias = b; p.ldo = n_out; p.rows_per_batch = 1;
+  if (y_is_bf16) {
+    if (!b) return MAC_ERR_INVALID;
+    p.epi = TC_EPI_ACT; p.out0 = reinterpret_cast<__nv_bfloat16*>(y);
+  } else {
+    p.epi = TC_EPI_F32; p.outf = reinterpret_cast<float*>(y);
+  }
   return tc_gemm_launch(x_bf16, K, nullptr, 0, wt_bf16, p, stream);
 }
 

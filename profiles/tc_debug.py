@@ -17,12 +17,12 @@ for bn in ("256256", "pair"):
         os.environ["MAC_TC_TILE"] = "256256"
         os.environ["MAC_TC_DEBUG"] = dbg
         for x in xs:
-            L.check(lib.mac_linear_tc_fwd(L.ptr(x), L.ptr(Wt), L.ptr(bias), 3, L.ptr(y), M, K, N, L.stream_ptr()))
+            L.check(lib.mac_linear_tc_fwd(L.ptr(x), L.ptr(Wt), L.ptr(bias), 3, L.ptr(y), 0, M, K, N, L.stream_ptr()))
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         for i in range(30):
-            L.check(lib.mac_linear_tc_fwd(L.ptr(xs[i % 6]), L.ptr(Wt), L.ptr(bias), 3, L.ptr(y), M, K, N, L.stream_ptr()))
+            L.check(lib.mac_linear_tc_fwd(L.ptr(xs[i % 6]), L.ptr(Wt), L.ptr(bias), 3, L.ptr(y), 0, M, K, N, L.stream_ptr()))
         b.record()
         torch.cuda.synchronize()
         t = a.elapsed_time(b) / 30 * 1e3

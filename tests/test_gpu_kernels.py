@@ -141,8 +141,13 @@ def test_linear_tensor_core(M, K, N, act):
     torch.cuda.synchronize()
     assert torch.equal(Wt, W.t().contiguous().to(torch.bfloat16))
     y = torch.zeros(M, N, device="cuda")
-    L.check(lib.mac_linear_tc_fwd(L.ptr(x), L.ptr(Wt), L.ptr(b), L.ACT[act], L.ptr(y), M, K, N, L.stream_ptr()))
+    L.check(lib.mac_linear_tc_fwd(L.ptr(x), L.ptr(Wt), L.ptr(b), L.ACT[act], L.ptr(y), 0, M, K, N, L.stream_ptr()))
     torch.cuda.synchronize()
     z = x.float().cpu().numpy().astype(np.float64) @ Wt.float().cpu().numpy().astype(np.float64).T + b.cpu().numpy()
     ref = {"NON": z, "ELU": O.elu(z), "TANH": np.tanh(z)}[act]
     assert max_rel(y.cpu().numpy(), ref) < 1e-4
+    if act in ("NON", "ELU"):        # bf16 output form used inside the read-unit chain
+        yb = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
+        L.check(lib.mac_linear_tc_fwd(L.ptr(x), L.ptr(Wt), L.ptr(b), L.ACT[act], L.ptr(yb), 1, M, K, N, L.stream_ptr()))
+        torch.cuda.synchronize()
+        assert max_rel(yb.float().cpu().numpy(), ref) < 6e-3
