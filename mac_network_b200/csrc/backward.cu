@@ -3,6 +3,7 @@
 // Appendix E.  Reductions are per-sample partial sums (one CTA owns a (sample, column-slice)), reduced over the batch
 // at the end of the backward pass, so gradients are deterministic (no atomics anywhere).
 #include "common.cuh"
+#define SGEMM_MIN_BLOCKS 1      // the transposed-A / split-K weight-gradient GEMMs are faster with the full register budget
 #include "sgemm.cuh"
 #include "skinny.cuh"
 

@@ -125,8 +125,11 @@ __device__ __forceinline__ float4 sg_load_at(const SgemmParams& p, int m, int k)
   return v;
 }
 
+#ifndef SGEMM_MIN_BLOCKS
+#define SGEMM_MIN_BLOCKS 2      // forward: 128 registers, two CTAs per SM (+14 % on the [12544,1024]x[1024,512] projection)
+#endif
 template <int BM, int BN>
-__global__ void __launch_bounds__(256) sgemm_kernel(const SgemmParams p) {
+__global__ void __launch_bounds__(256, SGEMM_MIN_BLOCKS) sgemm_kernel(const SgemmParams p) {
   constexpr int BK = 16;
   constexpr int TM = BM / 16, TN = BN / 16;         // 8x8 (128x128) or 4x4 (64x64)
   constexpr int A_LD = BM + 4;
