@@ -16,59 +16,55 @@ namespace cg = cooperative_groups;
 constexpr int SK_CLUSTER = 8;
 constexpr int SK_BM = 64, SK_BN = 32, SK_THREADS = 128;
 
+// pointer to four consecutive k of row m of the segmented A view (A_SEGS), or nullptr outside M
+__device__ __forceinline__ const float* sk_ptr_a(const SgemmParams& p, int m, int k) {
+  if (m >= p.M) return nullptr;
+  int off = 0;
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    if (s < p.nseg) {
+      if (k < off + p.ak[s]) return p.a[s] + (size_t)m * p.lda[s] + (k - off);
+      off += p.ak[s];
+    }
+  }
+  return nullptr;
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+
 static __global__ void __launch_bounds__(SK_THREADS) skinny_gemm_kernel(const SgemmParams p, int ks, int dbg) {
   extern __shared__ __align__(16) float sk_smem[];
-  constexpr int XLD = SK_BM + 4;                // 16-byte aligned rows of the transposed A slice
+  const int XP = ks + 4;                        // row pitch of the A slice (16-byte aligned rows)
   float* ws = sk_smem;                          // [ks][SK_BN]       W slice
   float* part = ws + (size_t)ks * SK_BN;        // [SK_BM][SK_BN]    this CTA's partial tile
-  float* xs = part + SK_BM * SK_BN;             // [ks][XLD]         A slice, transposed
+  float* xs = part + SK_BM * SK_BN;             // [SK_BM][XP]       A slice, natural layout
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();   // K-slice index (cluster spans gridDim.x)
   const int tid = threadIdx.x;
   const int n0 = blockIdx.y * SK_BN;
   const int k0 = rank * ks;
 
-  // ---- operand load in batches of 8 float4 per thread: all requests of a batch are in flight before the first
-  //      shared-memory store of the batch (ks = 64 -> one round trip for A and one for W)
-  {
-    constexpr int BATCH = 8;
-    const int nx = SK_BM * (ks / 4), nw = ks * (SK_BN / 4);
-    for (int base = 0; base < nx && !(dbg & 1); base += BATCH * SK_THREADS) {
-      float4 rx[BATCH];
-#pragma unroll
-      for (int i = 0; i < BATCH; ++i) {
-        const int f = base + tid + i * SK_THREADS;
-        if (f < nx) rx[i] = sg_load_a(p, f % SK_BM, k0 + (f / SK_BM) * 4);   // lane <-> row: conflict-free transposed stores
-      }
-#pragma unroll
-      for (int i = 0; i < BATCH; ++i) {
-        const int f = base + tid + i * SK_THREADS;
-        if (f < nx) {
-          const int row = f % SK_BM, kq = f / SK_BM;
-          xs[(kq * 4 + 0) * XLD + row] = rx[i].x;
-          xs[(kq * 4 + 1) * XLD + row] = rx[i].y;
-          xs[(kq * 4 + 2) * XLD + row] = rx[i].z;
-          xs[(kq * 4 + 3) * XLD + row] = rx[i].w;
-        }
-      }
+  // ---- operand load: 16-byte cp.async (LDGSTS) straight into shared memory -- every request of the CTA is in flight
+  //      at once, no register staging, one L2 round trip
+  if (!(dbg & 1)) {
+    const int xc = ks / 4;
+    for (int f = tid; f < SK_BM * xc; f += SK_THREADS) {
+      const int row = f / xc, c = f % xc;
+      const float* src = sk_ptr_a(p, row, k0 + c * 4);
+      float* dst = xs + (size_t)row * XP + c * 4;
+      if (src) cp_async16(dst, src);
+      else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    for (int base = 0; base < nw && !(dbg & 1); base += BATCH * SK_THREADS) {
-      float4 rw[BATCH];
-#pragma unroll
-      for (int i = 0; i < BATCH; ++i) {
-        const int f = base + tid + i * SK_THREADS;
-        if (f < nw) {
-          const int kr = f / (SK_BN / 4), n = n0 + (f % (SK_BN / 4)) * 4;
-          rw[i] = (n < p.N) ? __ldg(reinterpret_cast<const float4*>(p.W + (size_t)(k0 + kr) * p.ldw + n))
-                            : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < BATCH; ++i) {
-        const int f = base + tid + i * SK_THREADS;
-        if (f < nw) *reinterpret_cast<float4*>(ws + (size_t)(f / (SK_BN / 4)) * SK_BN + (f % (SK_BN / 4)) * 4) = rw[i];
-      }
+    for (int f = tid; f < ks * (SK_BN / 4); f += SK_THREADS) {
+      const int kr = f / (SK_BN / 4), c = f % (SK_BN / 4);
+      const int n = n0 + c * 4;
+      float* dst = ws + (size_t)kr * SK_BN + c * 4;
+      if (n < p.N) cp_async16(dst, p.W + (size_t)(k0 + kr) * p.ldw + n);
+      else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
   __syncthreads();
 
@@ -80,18 +76,25 @@ static __global__ void __launch_bounds__(SK_THREADS) skinny_gemm_kernel(const Sg
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   if (!(dbg & 2)) {
-#pragma unroll 4
-    for (int k = 0; k < ks; ++k) {
-      const float4 a = *reinterpret_cast<const float4*>(xs + k * XLD + rg * 4);
-      const float4 w = *reinterpret_cast<const float4*>(ws + k * SK_BN + cgp * 4);
-      acc[0][0] = fmaf(a.x, w.x, acc[0][0]); acc[0][1] = fmaf(a.x, w.y, acc[0][1]);
-      acc[0][2] = fmaf(a.x, w.z, acc[0][2]); acc[0][3] = fmaf(a.x, w.w, acc[0][3]);
-      acc[1][0] = fmaf(a.y, w.x, acc[1][0]); acc[1][1] = fmaf(a.y, w.y, acc[1][1]);
-      acc[1][2] = fmaf(a.y, w.z, acc[1][2]); acc[1][3] = fmaf(a.y, w.w, acc[1][3]);
-      acc[2][0] = fmaf(a.z, w.x, acc[2][0]); acc[2][1] = fmaf(a.z, w.y, acc[2][1]);
-      acc[2][2] = fmaf(a.z, w.z, acc[2][2]); acc[2][3] = fmaf(a.z, w.w, acc[2][3]);
-      acc[3][0] = fmaf(a.w, w.x, acc[3][0]); acc[3][1] = fmaf(a.w, w.y, acc[3][1]);
-      acc[3][2] = fmaf(a.w, w.z, acc[3][2]); acc[3][3] = fmaf(a.w, w.w, acc[3][3]);
+    const float* xr = xs + (size_t)(rg * 4) * XP;
+#pragma unroll 2
+    for (int k = 0; k < ks; k += 4) {
+      float4 a[4], w[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4*>(xr + (size_t)i * XP + k);
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) w[kk] = *reinterpret_cast<const float4*>(ws + (k + kk) * SK_BN + cgp * 4);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float av[4] = {a[i].x, a[i].y, a[i].z, a[i].w};
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          acc[i][0] = fmaf(av[kk], w[kk].x, acc[i][0]);
+          acc[i][1] = fmaf(av[kk], w[kk].y, acc[i][1]);
+          acc[i][2] = fmaf(av[kk], w[kk].z, acc[i][2]);
+          acc[i][3] = fmaf(av[kk], w[kk].w, acc[i][3]);
+        }
+      }
     }
   }
 #pragma unroll
@@ -138,7 +141,7 @@ inline bool skinny_ok(const SgemmParams& p) {
 
 inline int skinny_launch(const SgemmParams& p, cudaStream_t stream) {
   const int ks = p.K / SK_CLUSTER;
-  const size_t smem = ((size_t)ks * (SK_BM + 4) + (size_t)ks * SK_BN + SK_BM * SK_BN) * sizeof(float);
+  const size_t smem = ((size_t)SK_BM * (ks + 4) + (size_t)ks * SK_BN + SK_BM * SK_BN) * sizeof(float);
   MAC_CUDA_TRY(cudaFuncSetAttribute(skinny_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(SK_CLUSTER, (p.N + SK_BN - 1) / SK_BN, 1);

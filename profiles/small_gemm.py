@@ -18,7 +18,7 @@ for (M, K, N) in [(64, 512, 512), (64, 1024, 512), (64, 1536, 512), (64, 512, 61
     y = torch.empty(M, N, device="cuda")
     wsb = int(lib.mac_linear_workspace_bytes(M, K, N)); ws = torch.zeros(wsb, dtype=torch.uint8, device="cuda")
     arr_p = (ctypes.c_void_p * 1)(x.data_ptr()); arr_k = (ctypes.c_int * 1)(K)
-    for mode in ("0", "1", "2", "3"):
+    for mode in ("0", "3"):
         os.environ["MAC_SK_DEBUG"] = mode
         def f():
             L.check(lib.mac_linear_fwd(arr_p, arr_k, arr_k, 1, L.ptr(W), L.ptr(b), 0.0, 0, L.ptr(y), N, M, N, L.ptr(ws), wsb, L.stream_ptr()))
