@@ -800,7 +800,10 @@ inline int tc_gemm_launch_t(const CUtensorMap& ma0, const CUtensorMap& ma1, cons
   auto kern = tc_gemm_kernel<BM, BN, EPI, ACT>;
   MAC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BM, BN>::SMEM_BYTES));
   const int tiles = ((p.M + BM - 1) / BM) * (p.N / BN);
-  const int grid = tiles < tc_num_sms() ? tiles : tc_num_sms();
+  // persistent grid balanced over the rounds: same makespan as one CTA per SM, but e.g. 196 tiles run as 98 CTAs x 2
+  // tiles (epilogue of the first overlaps the MMAs of the second) and leave 50 SMs to concurrent streams
+  const int rounds = (tiles + tc_num_sms() - 1) / tc_num_sms();
+  const int grid = (tiles + rounds - 1) / rounds;
   kern<<<grid, TC_THREADS, TcCfg<BM, BN>::SMEM_BYTES, stream>>>(ma0, ma1, mb, p);
   MAC_LAUNCH_CHECK();
   return MAC_OK;
@@ -872,8 +875,11 @@ inline int tc2_gemm_dispatch(const CUtensorMap& ma0, const CUtensorMap& ma1, con
   return MAC_ERR_UNSUPPORTED;
 }
 
-// Tile shape: minimise rounds-over-the-SMs x per-tile time, per-tile time = max(MMA cycles, bytes / 64 B/clk) per k-block
-// (256x256: 1024, 128x256: 768, 128x128: 512).  Returns BM*1000 + BN.
+// Tile shape: minimise rounds-over-the-SMs x measured cycles per k-block of one tile.  SS-mode UMMAs are fed ~55-64 B/clk
+// from shared memory (profiles/r1/NOTES.md): a 128x256x16 UMMA takes ~224 cycles, a 128x128x16 one ~149, so per
+// k-block: 256x256 -> 1792, 128x256 -> 896 (fill needs 768), 128x128 -> ~620.  Ties go to 128x256: with the balanced
+// persistent grid it runs as 2 tiles per CTA and hides the first tile's epilogue under the second tile's MMAs
+// (measured 21.2k vs 20.9k (256x256) vs 19.4k (128x128) reasoning-steps/s at the headline shape).  Returns BM*1000 + BN.
 inline int tc_pick_tile(int M, int N) {
   const int sms = tc_num_sms();
   auto cost = [&](int bm, int bn, int per_tile) {
@@ -881,10 +887,10 @@ inline int tc_pick_tile(int M, int N) {
     const int tiles = ((M + bm - 1) / bm) * (N / bn);
     return ((tiles + sms - 1) / sms) * per_tile;
   };
-  int best = 128128, bc = cost(128, 128, 512);
-  const int c2 = cost(128, 256, 768), c3 = cost(256, 256, 1024);
-  if (c2 < bc) { best = 128256; bc = c2; }
-  if (c3 < bc || (c3 == bc && M >= 2048)) { best = 256256; bc = c3; }
+  int best = 128256, bc = cost(128, 256, 896);
+  const int c3 = cost(256, 256, 1792), c1 = cost(128, 128, 620);
+  if (c3 < bc) { best = 256256; bc = c3; }
+  if (c1 < bc) { best = 128128; bc = c1; }
   return best;
 }
 
