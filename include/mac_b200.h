@@ -229,6 +229,13 @@ int mac_clip_adam_ema_step(float* params, const float* grads, float* adam_m, flo
                            float ema_decay, float* norm_out, void* workspace, size_t workspace_bytes, mac_stream_t stream);
 size_t mac_optimizer_workspace_bytes(void);
 
+/* ------------------------------------------------------------------------------------------------
+ * Answer loss of the output unit ("next" row, model.py:593-596): mean sparse softmax cross entropy.
+ *   losses[b] = logsumexp(logits[b,:]) - logits[b, labels[b]];  dlogits = (softmax - onehot) * scale
+ * --------------------------------------------------------------------------------------------- */
+int mac_softmax_xent(const float* logits, const int32_t* labels, float* losses, float* dlogits, float scale,
+                     int B, int A, mac_stream_t stream);
+
 /* dropout sites (the `site` word of the Philox counter) */
 enum { MAC_SITE_MEM_VAR = 0, MAC_SITE_READ_KB = 1, MAC_SITE_READ_MEM = 2, MAC_SITE_READ_INTER = 3,
        MAC_SITE_WRITE_INFO = 4, MAC_SITE_MEM_PLAIN = 5 };

@@ -461,3 +461,35 @@ extern "C" int mac_bcast_op(const float* x, const float* v, int mode, float mul_
   MAC_LAUNCH_CHECK();
   return MAC_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ answer loss
+// losses[b] = logsumexp(logits[b,:]) - logits[b, label[b]]   (tf.nn.sparse_softmax_cross_entropy_with_logits, model.py:595)
+// dlogits[b,:] = (softmax(logits[b,:]) - onehot(label[b])) * scale       one warp per row
+namespace mac {
+__global__ void __launch_bounds__(256) softmax_xent_kernel(const float* __restrict__ logits, const int32_t* __restrict__ labels,
+                                                          float* __restrict__ losses, float* __restrict__ dlogits,
+                                                          float scale, int B, int A) {
+  const int b = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const float* row = logits + (size_t)b * A;
+  float mx = -INFINITY;
+  for (int a = lane; a < A; a += 32) mx = fmaxf(mx, row[a]);
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int a = lane; a < A; a += 32) sum += expf(row[a] - mx);
+  sum = warp_sum(sum);
+  const int lab = labels[b];
+  if (lane == 0) losses[b] = mx + logf(sum) - row[lab];
+  const float inv = 1.f / sum;
+  for (int a = lane; a < A; a += 32) dlogits[(size_t)b * A + a] = (expf(row[a] - mx) * inv - (a == lab ? 1.f : 0.f)) * scale;
+}
+}  // namespace mac
+
+extern "C" int mac_softmax_xent(const float* logits, const int32_t* labels, float* losses, float* dlogits, float scale,
+                                int B, int A, mac_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!logits || !labels || !losses || !dlogits || B <= 0 || A <= 0) return MAC_ERR_INVALID;
+  softmax_xent_kernel<<<(B + 7) / 8, 256, 0, stream>>>(logits, labels, losses, dlogits, scale, B, A);
+  MAC_LAUNCH_CHECK();
+  return MAC_OK;
+}

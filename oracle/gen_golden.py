@@ -172,6 +172,37 @@ def run_case(name, src, extra, shape, train, seed=7):
     return out
 
 
+def run_output_case(name, train, seed=17, B=6, d=16, A=12, hidden=(8,)):
+    """Output unit + classifier + loss through the reference's own MACnet methods (model.py:512-528, 547-576, 593-596)."""
+    import types
+    ref_model = importlib.import_module("model")
+    set_reference_config("@args.txt", ["--outClassifierDims"] + [str(h) for h in hidden], dict(L=1, d=d), train)
+    rc = _ref_config.config
+    rc.answerWordsNum = A
+    from mac_network_b200.output_unit import output_specs, init_output_params
+    specs = output_specs(d, d, list(hidden), A)
+    params = init_output_params(specs, seed=seed, dtype=np.float64)
+    rng = np.random.RandomState(seed + 1)
+    memory, vecq = rng.standard_normal((B, d)), 0.5 * np.tanh(rng.standard_normal((B, d)))
+    answers = rng.randint(0, A, size=(B,)).astype(np.int32)
+    keep = rc.outputDropout if train else 1.0
+    store = tf.reset_shim(values=params, seed=seed + 2, dtype=np.float64)
+    me = types.SimpleNamespace(dropouts={"output": keep}, batchNorm=None, answerLossList=[])
+    feats, dim = ref_model.MACnet.outputOp(me, tf.constant(memory), tf.constant(vecq), None, None)
+    logits = ref_model.MACnet.classifier(me, feats, dim)
+    loss, losses = ref_model.MACnet.addAnswerLossOp(me, logits, answers)
+    created = {k: list(v.shape) for k, v in store.vars.items()}
+    assert created == {k: list(v[0]) for k, v in specs.items()}, (created, specs)
+    out = {"logits": np.asarray(logits), "losses": np.asarray(losses), "loss": np.asarray(loss),
+           "memory": memory, "vecQuestions": vecq, "answers": answers}
+    for i, u in enumerate(store.uniform_draws):
+        out["uniform_%03d" % i] = u.astype(np.float64)
+    meta = {"case": name, "train": train, "keep": keep, "B": B, "d": d, "A": A, "hidden": list(hidden), "param_seed": seed,
+            "relu": rc.relu, "variables": created, "n_uniform": len(store.uniform_draws)}
+    out["meta_json"] = np.frombuffer(json.dumps(meta, sort_keys=True).encode(), dtype=np.uint8)
+    return out
+
+
 def main():
     outdir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(outdir, exist_ok=True)
@@ -185,6 +216,13 @@ def main():
         print("%-22s %8.1f KB  vars=%d draws=%d" % (name, os.path.getsize(path) / 1024.0,
                                                      len(json.loads(bytes(out["meta_json"]).decode())["variables"]),
                                                      sum(k.startswith("uniform_") for k in out)))
+    for name, train in (("output_eval", False), ("output_train", True)):
+        if only and name not in only:
+            continue
+        out = run_output_case(name, train)
+        path = os.path.join(outdir, name + ".npz")
+        np.savez_compressed(path, **out)
+        print("%-22s %8.1f KB" % (name, os.path.getsize(path) / 1024.0))
 
 
 if __name__ == "__main__":

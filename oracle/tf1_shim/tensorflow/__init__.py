@@ -281,6 +281,14 @@ class _nn(object):
         return sigmoid(x)
 
     @staticmethod
+    def sparse_softmax_cross_entropy_with_logits(labels=None, logits=None, **kw):
+        # TF: -log_softmax(logits)[label], computed as logsumexp(logits) - logits[label]
+        m = np.max(logits, axis=-1, keepdims=True)
+        lse = m[..., 0] + np.log(np.sum(np.exp(logits - m), axis=-1))
+        idx = np.asarray(labels).astype(np.int64)
+        return _t(lse - np.take_along_axis(np.asarray(logits), idx[..., None], axis=-1)[..., 0])
+
+    @staticmethod
     def dropout(x, keep_prob, **kw):
         # TF1: x / keep_prob * floor(keep_prob + U[0,1)).  keep_prob == 1.0 is an exact identity
         # (TF short-circuits a python-number keep_prob of 1 and the formula gives x anyway).
