@@ -469,20 +469,19 @@ def train_arm(steps, warmup, rank, world, dist):
     B, S, N, d, L = shape
     cfg = MACConfig.args("args", netLength=L)
     pv = perturb_biases(init_params(cfg, L, seed=100), seed=101)
-    tr = DPTrainer(cfg, L, param_values=pv, seed=7, rank=rank, world=world)
+    tr = DPTrainer(cfg, L, param_values=pv, seed=7, rank=rank, world=world, classifier=(28, [512]))   # CLEVR: 28 answers
     inp = make_inputs(B, S, N, d, seed=4321 + 1000 * rank)
     batch = {k: torch.from_numpy(v).cuda() for k, v in inp.items()}
-    g = torch.Generator(device="cuda").manual_seed(5 + rank)
-    tc, tm = torch.randn(B, d, device="cuda", generator=g), torch.randn(B, d, device="cuda", generator=g)
+    answers = torch.from_numpy(np.random.RandomState(5 + rank).randint(0, 28, size=(B,)).astype(np.int32)).cuda()
     for _ in range(warmup):
-        tr.train_step(0, batch, tc, tm, B * world)
+        tr.train_step_answers(0, batch, answers, B * world)
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
-        tr.train_step(0, batch, tc, tm, B * world)
+        tr.train_step_answers(0, batch, answers, B * world)
     e1.record()
     if dist is not None:
         dist.barrier()
@@ -498,8 +497,9 @@ def train_arm(steps, warmup, rank, world, dist):
         dist.all_gather(allc, chk)
         sync = all(bool(torch.equal(allc[0], c)) for c in allc)
     out = {"value": steps * L * world / t, "unit": UNIT, "ms_per_step": t / steps * 1e3, "steps": steps,
-           "what": "DP training step of the cell: train-mode forward + hand-written backward + all-reduce of the flat "
-                   "gradient bucket (%.1f MB, NCCL) + fused clip/Adam/EMA; B=%d per GPU, fp32 path" % (tr.params.numel * 4 / 1e6, B),
+           "what": "DP training step: train-mode cell forward + output unit + mean softmax-CE over the global batch + hand-written "
+                   "backward + all-reduce of the flat gradient bucket (%.1f MB, NCCL) + fused clip/Adam/EMA; B=%d per GPU, "
+                   "fp32 path" % (tr.params.numel * 4 / 1e6, B),
            "replicas_in_sync": sync}
     del tr
     torch.cuda.empty_cache()

@@ -27,7 +27,7 @@ def _t(params, W, key):
 
 
 class _Bwd(object):
-    def __init__(self, cell, bucket=None):
+    def __init__(self, cell, bucket=None, zero_bucket=True):
         self.cell, self.lib = cell, cell.lib
         self.p = cell.params
         c = cell.cfg
@@ -40,7 +40,7 @@ class _Bwd(object):
         # parameter gradients are views into ONE flat bucket laid out like MACParams.flat (what NCCL all-reduces)
         from .mac_cell import views_of
         self.bucket = bucket if bucket is not None else torch.zeros_like(self.p.flat)
-        if bucket is not None:
+        if bucket is not None and zero_bucket:
             self.bucket.zero_()
         self.g = views_of(self.bucket, self.p.specs, self.p.offsets)
         cache = getattr(cell, "_bwd_ws", None)            # scratch is allocated once per cell and reused every step
@@ -83,7 +83,7 @@ class _Bwd(object):
         Bp, d = part.shape
         check(self.lib.mac_colsum(ptr(part), ptr(out_flat), 1, Bp, d, 1, stream_ptr()), "mac_colsum")
 
-    def run(self, d_control, d_memory):
+    def run(self, d_control, d_memory, d_vecq=None):
         cell, c, lib = self.cell, self.cell.cfg, self.lib
         B, N, d, L = self.B, self.N, self.d, self.L
         z, e = self.z, self.e
@@ -96,6 +96,8 @@ class _Bwd(object):
         dkb = z(B, N, d)
         dwords = z(B, S, d)
         dq = z(B, d)
+        if d_vecq is not None:          # e.g. from the output unit (model.py:519), which also consumes vecQuestions
+            dq.copy_(d_vecq)
         unshared = c.controlInputUnshared
         dci = z(B, L * d) if unshared else z(B, d)       # gradient w.r.t. ci_i (cell._ci layout)
         part = {k: z(B, d) for k in ("wr", "bx", "bm", "bm2", "wc", "ws")}
@@ -219,8 +221,8 @@ class _Bwd(object):
         return out
 
 
-def mac_backward(cell, d_control, d_memory, bucket=None):
+def mac_backward(cell, d_control, d_memory, bucket=None, zero_bucket=True, d_vecq=None):
     """Gradients of sum(d_control * control_L) + sum(d_memory * memory_L) w.r.t. every cell parameter and input."""
     if not getattr(cell, "save_for_backward", False):
         raise RuntimeError("construct the MACCell with save_for_backward=True and run the forward first")
-    return _Bwd(cell, bucket).run(d_control, d_memory)
+    return _Bwd(cell, bucket, zero_bucket).run(d_control, d_memory, d_vecq)

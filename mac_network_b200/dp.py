@@ -35,11 +35,27 @@ def allreduce_sum_(bucket, group=None):
 
 class DPTrainer(object):
     def __init__(self, cfg, netLength, param_values=None, seed=0, rank=0, world=1, lr=1e-4, clip=8.0, ema_decay=0.999,
-                 beta1=0.9, beta2=0.999, eps=1e-8, dropouts=None, device="cuda"):
-        from .mac_cell import MACParams
+                 beta1=0.9, beta2=0.999, eps=1e-8, dropouts=None, device="cuda", classifier=None, output_dropout=0.85):
+        """`classifier=(answerWordsNum, outClassifierDims)` adds the reference's output unit + answer loss
+        (model.py:512-528, 547-576, 593-596); its variables join the same flat buckets."""
+        from .mac_cell import MACParams, views_of
+        from .params import init_params
         self.cfg, self.L, self.rank, self.world = cfg, netLength, rank, world
         self.lib = _lib.load()
-        self.params = MACParams(cfg, netLength, values=param_values, seed=seed, device=device)   # replicated
+        extra_specs = extra_values = None
+        if classifier is not None:
+            from .output_unit import output_specs, init_output_params
+            extra_specs = output_specs(cfg.ctrlDim, cfg.memDim, list(classifier[1]), classifier[0])
+            extra_values = init_output_params(extra_specs, seed=seed + 17, bias_scale=0.0)
+            if param_values is None:
+                param_values = init_params(cfg, netLength, seed=seed)
+        self.params = MACParams(cfg, netLength, values=param_values, seed=seed, device=device, extra_specs=extra_specs,
+                                extra_values=extra_values)   # replicated
+        self.out = None
+        if classifier is not None:
+            from .output_unit import OutputUnit
+            self.out = OutputUnit({k: self.params.t[k] for k in extra_specs}, relu=cfg.relu, keep=output_dropout, seed=seed)
+            self._views_of = views_of
         n = self.params.numel
         z = lambda: torch.zeros(n, dtype=torch.float32, device=self.params.device)
         self.bucket, self.adam_m, self.adam_v = z(), z(), z()
@@ -87,6 +103,27 @@ class DPTrainer(object):
                                               h["eps"], self.step_id, h["ema"], ptr(self.norm), ptr(self.ows),
                                               self.ows_bytes, stream_ptr()), "mac_clip_adam_ema_step")
         self.params.touch()
+
+    def train_step_answers(self, key, batch, answers, global_batch):
+        """One DP step on the reference's loss: cell forward -> output unit -> mean softmax-CE over the GLOBAL batch ->
+        output-unit backward -> cell backward -> all-reduce -> clip/Adam/EMA.  Returns (logits, per-sample losses)."""
+        from .autograd import mac_backward
+        from .mac_cell import mac_network
+        cell = self.cell_for(key, batch)
+        cell._rw.clear()
+        cell.seed = (self.base_seed * 1000003 + self.step_id * 7919 + self.rank * 104729 + 1) & 0x7FFFFFFFFFFFFFFF
+        self.out.seed = cell.seed
+        control, memory = mac_network(cell, self.L)
+        self.bucket.zero_()
+        gviews = self._views_of(self.bucket, self.params.specs, self.params.offsets)
+        logits, losses, _ = self.out.forward(memory, batch["vecQuestions"], answers, step=self.step_id,
+                                             loss_scale=1.0 / float(global_batch))
+        d_mem, d_q = torch.zeros_like(memory), torch.zeros_like(memory)
+        self.out.backward(gviews, d_mem, d_q)
+        mac_backward(cell, None, d_mem, bucket=self.bucket, zero_bucket=False, d_vecq=d_q)
+        self.apply()
+        self.out.invalidate()
+        return logits, losses
 
     def train_step(self, key, batch, t_control, t_memory, global_batch):
         control, memory, _ = self.grads(key, batch, t_control, t_memory, global_batch)

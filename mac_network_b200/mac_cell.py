@@ -65,12 +65,16 @@ def views_of(flat, specs, offsets):
 class MACParams(object):
     """Cell parameters on the device, keyed by the reference's TF variable names."""
 
-    def __init__(self, cfg, netLength=None, values=None, seed=0, device="cuda"):
+    def __init__(self, cfg, netLength=None, values=None, seed=0, device="cuda", extra_specs=None, extra_values=None):
         self.cfg = cfg
         self.L = cfg.netLength if netLength is None else netLength
         self.specs = param_specs(cfg, self.L)
         if values is None:
             values = init_params(cfg, self.L, seed=seed)
+        if extra_specs:            # e.g. the output unit's variables: same flat bucket, same optimizer step
+            self.specs = collections.OrderedDict(list(self.specs.items()) + list(extra_specs.items()))
+            values = dict(values)
+            values.update(extra_values)
         missing = set(self.specs) - set(values)
         if missing:
             raise KeyError("missing parameters: %s" % sorted(missing)[:4])

@@ -113,12 +113,14 @@ class OutputUnit(object):
                                         stream_ptr()), "mac_softmax_xent")
         return self.logits, self.losses, self.dlogits
 
+    def invalidate(self):
+        """Call after the parameters were updated in place (optimizer step): drops the cached transposes."""
+        self._wt.clear()
+
     def _wt_of(self, name):
-        W = self.p[name]
-        key = (name, W.data_ptr(), W._version)
-        if self._wt.get(name, (None,))[0] != key:
-            self._wt[name] = (key, W.t().contiguous())
-        return self._wt[name][1]
+        if name not in self._wt:
+            self._wt[name] = self.p[name].t().contiguous()
+        return self._wt[name]
 
     def backward(self, grads, d_memory, d_vecq):
         """Accumulates parameter gradients into `grads` (dict name -> tensor) and ADDS dL/dmemory, dL/dvecQuestions."""

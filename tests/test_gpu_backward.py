@@ -92,3 +92,21 @@ def test_dp_half_batches_sum_to_full_batch_and_optimizer_step():
     assert np.max(np.abs(tr.params.flat.cpu().numpy() - p1)) < 1e-6
     assert np.max(np.abs(tr.ema.cpu().numpy() - e1)) < 1e-6
     assert max_rel(tr.adam_v.cpu().numpy(), v1) < 2e-4      # (1 - beta2) is rounded in fp32, as in TF
+
+
+def test_training_on_the_reference_loss_decreases():
+    """DPTrainer with the output unit: a few steps of clip/Adam on the mean softmax-CE must reduce the loss on a fixed
+    batch, and the step must leave split-K counters / buckets in a reusable state."""
+    from mac_network_b200.dp import DPTrainer
+    B, S, N, d, L = 16, 8, 49, 128, 3
+    cfg = MACConfig.args("gqa", netLength=L, memDim=d, ctrlDim=d, attDim=d)
+    inputs = make_inputs(B, S, N, d, seed=91)
+    batch = {k: torch.from_numpy(v).cuda() for k, v in inputs.items()}
+    answers = torch.from_numpy(np.random.RandomState(92).randint(0, 12, size=(B,)).astype(np.int32)).cuda()
+    tr = DPTrainer(cfg, L, seed=5, lr=3e-3, classifier=(12, [64]), dropouts=(1.0, 1.0, 1.0), output_dropout=1.0)
+    losses = []
+    for _ in range(12):
+        _, ls = tr.train_step_answers(0, batch, answers, B)
+        losses.append(float(ls.mean()))
+    assert np.isfinite(losses).all()
+    assert losses[-1] < 0.7 * losses[0], losses
