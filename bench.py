@@ -429,8 +429,11 @@ def run_ours(args):
 
     if rank == 0:
         roofs = kernel_rooflines(shape, args.prec, pk)
-        cpu, _ = cpu_reference(cfg, shape, pv) if not args.skip_cpu else ({"value": None, "unit": UNIT, "cores": 0,
-                                                                           "kind": "port", "sample": "skipped"}, 0)
+        if args.skip_cpu or world > 1:      # the CPU baseline is timed at N=1 only (rank 0)
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port",
+                   "sample": "skipped (--skip-cpu)" if args.skip_cpu else "timed at N=1 only"}
+        else:
+            cpu, _ = cpu_reference(cfg, shape, pv)
         value = args.steps * L * world / t_dev
         dom = "memKbProj_gemm_fp32" if args.prec == "fp32" else "memKbProj_gemm_tc"
         line = {
