@@ -839,7 +839,8 @@ inline int tc2_gemm_launch_t(const CUtensorMap& ma0, const CUtensorMap& ma1, con
   MAC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Tc2Cfg::SMEM_BYTES));
   const int tiles = ((p.M + 255) / 256) * (p.N / Tc2Cfg::BN);
   const int max_pairs = tc_num_sms() / 2;
-  const int pairs = tiles < max_pairs ? tiles : max_pairs;
+  const int rounds = (tiles + max_pairs - 1) / max_pairs;
+  const int pairs = (tiles + rounds - 1) / rounds;        // balanced: 98 pair-tiles -> 49 pairs x 2 tiles (98 SMs)
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * pairs, 1, 1);
   cfg.blockDim = dim3(TC_THREADS, 1, 1);
