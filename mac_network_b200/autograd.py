@@ -31,8 +31,11 @@ class _Bwd(object):
         self.cell, self.lib = cell, cell.lib
         self.p = cell.params
         c = cell.cfg
-        if c.controlFeedPrev or c.controlWholeQ or c.controlContinuous:
-            raise NotImplementedError("backward covers the controlFeedPrev-off family (args, args2, args3, args4, GQA)")
+        if c.controlWholeQ or c.controlContinuous:
+            raise NotImplementedError("backward covers the shipped flag files (args, args1, args2, args3, args4, GQA)")
+        self.recurrent = bool(c.controlFeedPrev)
+        if self.recurrent and c.writeSelfAtt and c.writeSelfAttMod == "CONT":
+            raise NotImplementedError("backward of controlFeedPrev together with writeSelfAttMod=CONT")
         self.B, self.N, self.d, self.L = cell.B, cell.N, cell.d, cell.L
         dev = cell.device
         self.z = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)
@@ -100,6 +103,7 @@ class _Bwd(object):
             dq.copy_(d_vecq)
         unshared = c.controlInputUnshared
         dci = z(B, L * d) if unshared else z(B, d)       # gradient w.r.t. ci_i (cell._ci layout)
+        du_rec = z(B, d)                                  # recurrent control: gradient w.r.t. u accumulated over the steps
         part = {k: z(B, d) for k in ("wr", "bx", "bm", "bm2", "wc", "ws")}
         spart = {k: z(B) for k in ("br", "bc", "bs")}
         tmp_dm, tmp_dpre, dinfo, dss, dsc, dmem_in, tmp2 = (e(B, d) for _ in range(7))
@@ -163,8 +167,13 @@ class _Bwd(object):
             else:
                 self.axpy(gM[i], dmem_in)
 
-        # ---------------- control unit, all L steps in one launch (mac_cell.py:155-181)
+            if self.recurrent:
+                self._control_step_bwd(i, gC, dwords, du_rec, part, spart, S)
+
         lsc = "MACCell/control/inter2logits/linearLayerlogits/"
+        if self.recurrent:
+            return self._finish(gC, gM, dkb, dwords, dq, du_rec, part, spart, rsc, wsc, lsc, nbx, nbm, nbm2)
+        # ---------------- control unit, all L steps in one launch (mac_cell.py:155-181)
         cc_t, cc_b = (d, L * d) if unshared else (0, d)
         check(lib.mac_control_attend_bwd(ptr(cell._ci), cc_t, cc_b, ptr(cell.inWords), S * d, d, ptr(cell.outWords), S * d, d,
                                          ptr(self.p[lsc + "weights/weight"]), ptr(cell._att_q), ptr(gC[1:]), B * d, d,
@@ -190,7 +199,50 @@ class _Bwd(object):
         else:
             nW, nb = self.lin_names("MACCell/", "qInputU")
             self.linear_bwd([u], nW, nb, dci, [du], [0])
-        dpre = e(B, d)
+        return self._finish(gC, gM, dkb, dwords, dq, du, part, spart, rsc, wsc, lsc, nbx, nbm, nbm2)
+
+    def _control_step_bwd(self, i, gC, dwords, du_rec, part, spart, S):
+        """Recurrent control unit of step i (mac_cell.py:141-181 with controlFeedPrev):
+        cc_i = linear_2(act(linear_1([prev, ci_i]))), c_i = attention(cc_i); ci_i = linear_qInputU/qInput{i}(u)."""
+        cell, c, lib = self.cell, self.cell.cfg, self.lib
+        B, d = self.B, self.d
+        prev, ci, hidden, cc = cell._ctrl_saved[i]
+        sc = "MACCell/control/"
+        lsc = sc + "inter2logits/linearLayerlogits/"
+        dcc = self.e(B, d)
+        check(lib.mac_control_attend_bwd(ptr(cc), 0, d, ptr(cell.inWords), S * d, d, ptr(cell.outWords), S * d, d,
+                                         ptr(self.p[lsc + "weights/weight"]), ptr(cell._att_q[i]), ptr(gC[i + 1]), 0, d,
+                                         ptr(dwords), ptr(dwords), ptr(dcc), 0, d, 0, ptr(part["wc"]), ptr(spart["bc"]),
+                                         1, B, S, d, stream_ptr()), "control bwd")
+        dy = dcc
+        if c.controlContAct != "NON":
+            nW2, nb2 = self.lin_names(sc + "linearLayercontControl/", "contControl_2")
+            dh = self.e(B, d)
+            self.linear_bwd([hidden], nW2, nb2, dcc, [dh], [0])
+            dpre = self.e(B, d)
+            act = c.controlContAct
+            code = ACT["ELU"] if (act == "RELU" and c.relu == "ELU") else ACT["RELU_STD"] if act == "RELU" else ACT[act]
+            check(lib.mac_activation_bwd(ptr(hidden), ptr(dh), code, ptr(dpre), B * d, stream_ptr()), "act bwd")
+            dy = dpre
+        nW, nb = self.lin_names(sc, "contControl")
+        dci = self.e(B, d)
+        # prev = c_{i-1} (controlFeedPrevAtt) lives in history slot i; the continuous variant feeds cc_{i-1}
+        if not c.controlFeedPrevAtt:
+            raise NotImplementedError("backward of controlFeedPrev without controlFeedPrevAtt")
+        if c.controlFeedInputs:
+            self.linear_bwd([prev, ci], nW, nb, dy, [gC[i], dci], [1, 0])
+        else:
+            self.linear_bwd([prev], nW, nb, dy, [gC[i]], [1])
+            dci.zero_()
+        nameU = ("qInput%d" % i) if c.controlInputUnshared else "qInputU"
+        nWu, nbu = self.lin_names("MACCell/", nameU)
+        self.linear_bwd([cell._u_saved], nWu, nbu, dci, [du_rec], [1])
+
+    def _finish(self, gC, gM, dkb, dwords, dq, du, part, spart, rsc, wsc, lsc, nbx, nbm, nbm2):
+        cell, c, lib = self.cell, self.cell.cfg, self.lib
+        B, d = self.B, self.d
+        u = cell._u_saved
+        dpre = self.e(B, d)
         act = c.controlInputAct
         code = ACT["ELU"] if (act == "RELU" and c.relu == "ELU") else ACT["RELU_STD"] if act == "RELU" else ACT[act]
         check(lib.mac_activation_bwd(ptr(u), ptr(du), code, ptr(dpre), B * d, stream_ptr()), "act bwd")

@@ -181,7 +181,10 @@ class MACCell(object):
         self._rw = {}
         self.kb_bf16 = None
         self.save_for_backward = bool(save_for_backward)
-        if self.save_for_backward and (self.prec != PREC["fp32"] or not (self._fused_read and self._fused_write and self._hoist)):
+        recurrent_ctrl_ok = (c.controlFeedPrev and self._fused_control and not (c.controlWholeQ or c.controlContinuous
+                                                                                or c.unsharedCells))
+        if self.save_for_backward and (self.prec != PREC["fp32"] or not (self._fused_read and self._fused_write)
+                                       or not (self._hoist or recurrent_ctrl_ok)):
             raise NotImplementedError("backward is implemented on the fused fp32 path (DESIGN.md section 9)")
         if self.prec != PREC["fp32"] and not self._fused_read:
             raise NotImplementedError("the tensor-core projections cover the fused read unit only")
@@ -261,6 +264,7 @@ class MACCell(object):
                                          stream_ptr()), "mac_cast_bf16")
         self._mem_in = self._new(B, d)
         if self.save_for_backward:
+            self._ctrl_saved = {}
             M = B * self.N
             self._save = [self._new(3 * M * d + B * d) for _ in range(L)]      # [P | H | I1 | y] per step
             self._mem_in_hist = self._new(L, B, d)
@@ -319,9 +323,12 @@ class MACCell(object):
             xs = [prev, controlInput] if c.controlFeedInputs else [prev]
             W, b = self.params.lin(sc, "contControl")
             newContControl = self._linear(xs, W, b, self._new(B, d), act=c.controlContAct)
+            hidden = newContControl
             if c.controlContAct != "NON":                                            # nested "_2" layer, ops.py:325-328
                 W2, b2 = self.params.lin(sc + "linearLayercontControl/", "contControl_2")
                 newContControl = self._linear([newContControl], W2, b2, self._new(B, d))
+            if self.save_for_backward:      # what the recurrent control chain's backward needs, per step
+                self._ctrl_saved[self.iteration] = (prev, controlInput, hidden, newContControl)
         S = inWords.shape[1]
         att = _att_out if _att_out is not None else self._new(B, S)
         out = _out if _out is not None else self._new(B, d)

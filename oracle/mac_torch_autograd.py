@@ -38,6 +38,7 @@ def run(cfg, params_np, inputs_np, L, dropouts=(1.0, 1.0, 1.0), uniforms=None, d
     memory = vecQ if c.initMem == "Q" else (p[PREFIX + "initMem"].unsqueeze(0).repeat(B, 1) if c.initMem == "PRM"
                                             else torch.zeros(B, d, dtype=torch.float64))
     controls, memories = control.unsqueeze(1), memory.unsqueeze(1)
+    cont_prev = control
     var_mask = None
     if c.memoryVariationalDropout and km < 1.0:
         var_mask = torch.floor(km + t64(next(us)))
@@ -46,7 +47,17 @@ def run(cfg, params_np, inputs_np, L, dropouts=(1.0, 1.0, 1.0), uniforms=None, d
     for i in range(L):
         ci = act_in(lin(vecQ, "MACCell/", "qInput"))
         ci = lin(ci, "MACCell/", ("qInput%d" % i) if c.controlInputUnshared else "qInputU")
-        logits = lin(ci.unsqueeze(1) * words, "MACCell/control/inter2logits/", "logits")
+        cc = ci
+        if c.controlFeedPrev:                                                    # mac_cell.py:141-151
+            prev = control if c.controlFeedPrevAtt else cont_prev
+            xin = torch.cat([prev, ci], dim=-1) if c.controlFeedInputs else prev
+            cc = lin(xin, "MACCell/control/", "contControl")
+            if c.controlContAct != "NON":
+                cc = torch.tanh(cc) if c.controlContAct == "TANH" else torch.nn.functional.elu(cc)
+                cc = lin(cc, "MACCell/control/linearLayercontControl/", "contControl_2")
+        cont_prev = cc
+        ci_for_selfatt = cc
+        logits = lin(cc.unsqueeze(1) * words, "MACCell/control/inter2logits/", "logits")
         qatt = torch.softmax(logits + mask, dim=-1)
         control = (qatt.unsqueeze(-1) * words).sum(-2)
         # read
@@ -68,7 +79,7 @@ def run(cfg, params_np, inputs_np, L, dropouts=(1.0, 1.0, 1.0), uniforms=None, d
             info = dropout(info, kw)
         parts = [memory, info]
         if c.writeSelfAtt:
-            sc = lin(ci if c.writeSelfAttMod == "CONT" else control, "MACCell/write/", "ctrlProj")
+            sc = lin(ci_for_selfatt if c.writeSelfAttMod == "CONT" else control, "MACCell/write/", "ctrlProj")
             satt = torch.softmax(lin(controls * sc.unsqueeze(1), "MACCell/write/inter2attselfAttention/inter2logits/",
                                      "logits"), -1)
             parts.append((satt.unsqueeze(-1) * memories).sum(-2))

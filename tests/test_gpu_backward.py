@@ -17,6 +17,7 @@ pytestmark = pytest.mark.gpu
     ("gqa", (5, 7, 49, 128, 4), (0.9, 0.8, 0.9)),
     ("args4", (4, 6, 20, 64, 3), (1.0, 0.85, 1.0)),
     ("args3", (4, 6, 20, 64, 3), (0.85, 1.0, 1.0)),
+    ("args1", (5, 7, 20, 64, 4), (0.85, 0.85, 1.0)),      # recurrent control chain (controlFeedPrev)
 ])
 def test_backward_matches_autograd(variant, shape, dp):
     from mac_network_b200.autograd import mac_backward

@@ -78,7 +78,7 @@ def test_torch_cpu_port_matches_oracle(variant):
     assert np.max(np.abs(m.numpy() - ref.memory)) / np.max(np.abs(ref.memory)) < 1e-5
 
 
-@pytest.mark.parametrize("case", ["args_train_small", "gqa_train_small", "args4_small"])
+@pytest.mark.parametrize("case", ["args_train_small", "gqa_train_small", "args4_small", "args1_train_small"])
 def test_torch_autograd_restatement_matches_reference_fixture(case):
     """The differentiable fp64 torch restatement (gradient oracle) reproduces the reference fixtures' forward."""
     from oracle import mac_torch_autograd as TA
