@@ -1,0 +1,77 @@
+"""Checkpoint interchange and attention-map export.
+
+* Weights are exchanged under the reference's TensorFlow variable names (`macModel/MACnetwork/MACCell/...`,
+  `main.py:163-201`, Appendix B), including the EMA shadows `<name>/ExponentialMovingAverage` (`model.py:659-667`).
+  TensorFlow's binary checkpoint format needs TensorFlow; the interchange container here is a flat `.npz` with those
+  names as keys, which `tf.train.load_checkpoint(...)`-side tooling can produce with a ten-line script
+  (`{n: reader.get_tensor(n) for n in reader.get_variable_to_shape_map()}`).
+* `attention_maps` lays the per-step maps out the way `MACnet.buildPredsList` does (`model.py:693-710`):
+  `attMap[key][step][sample]`, keys `kb` (length H*W, reshaped to the image grid by `visualization.py:121`),
+  `question`, `self`, `gate`, so the reference's visualisation script can consume them unchanged.
+"""
+import collections
+import json
+
+import numpy as np
+
+MODEL_SCOPE = "macModel/"          # model.py:774
+EMA_SUFFIX = "/ExponentialMovingAverage"
+
+
+def save_checkpoint(path, params, ema_flat=None):
+    """Write parameters (and optionally the EMA shadow buffer laid out like `params.flat`) under TF variable names."""
+    out = collections.OrderedDict()
+    for name, t in params.t.items():
+        shape = params.specs[name][0]
+        out[MODEL_SCOPE + name] = t.detach().cpu().numpy().reshape(shape)
+    if ema_flat is not None:
+        ema = ema_flat.detach().cpu().numpy()
+        for name, (shape, _) in params.specs.items():
+            n = int(np.prod(shape)) if shape else 1
+            o = params.offsets[name]
+            out[MODEL_SCOPE + name + EMA_SUFFIX] = ema[o:o + n].reshape(shape)
+    np.savez(path, **out)
+    return list(out)
+
+
+def load_checkpoint(path, use_ema=False):
+    """Returns {variable name without the model scope: array}, ready for `MACParams(values=...)`.
+    `use_ema=True` substitutes the EMA shadows, like the reference's evaluation swap (`main.py:717-719`)."""
+    z = np.load(path)
+    vals = {}
+    for k in z.files:
+        if not k.startswith(MODEL_SCOPE) or k.endswith(EMA_SUFFIX):
+            continue
+        name = k[len(MODEL_SCOPE):]
+        src = k + EMA_SUFFIX if (use_ema and k + EMA_SUFFIX in z.files) else k
+        vals[name] = np.asarray(z[src], dtype=np.float32)
+    return vals
+
+
+def attention_maps(cell, image_dims=None):
+    """`attMap[key][step][sample]` as nested python lists (what model.py:703-705 indexes)."""
+    out = {}
+    for key in ("kb", "question", "self", "gate"):
+        steps = []
+        for a in cell.attentions[key]:
+            arr = a.detach().cpu().numpy()
+            if key == "kb" and image_dims is not None:
+                arr = arr.reshape(arr.shape[0], image_dims[0], image_dims[1])
+            steps.append(arr.tolist())
+        out[key] = steps
+    return out
+
+
+def write_preds(path, cell, predictions=None, image_dims=(14, 14)):
+    """One JSON record per sample with its per-step attention maps (`model.py:693-710`, `preprocess.py:263-272`)."""
+    att = attention_maps(cell, image_dims)
+    B = cell.B
+    recs = []
+    for i in range(B):
+        rec = {"index": i, "attentions": {k: [step[i] for step in v] for k, v in att.items() if v}}
+        if predictions is not None:
+            rec["prediction"] = int(predictions[i])
+        recs.append(rec)
+    with open(path, "w") as fh:
+        json.dump(recs, fh)
+    return recs

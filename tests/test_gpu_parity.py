@@ -192,3 +192,57 @@ def test_bf16_train_mode_forward():
     errs = {k: max_rel(got[k], ref[k]) for k in ("control", "memory", "info")}
     print("bf16 train-mode max-rel errors:", errs)
     assert errs["control"] < 1e-4 and errs["memory"] < 3e-2 and errs["info"] < 3e-2
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_full_size_properties(prec):
+    """BASELINE.json's full headline shape (B=64, S=40, N=196, d=512, netLength=12) through size-independent properties:
+    run-to-run determinism (bit-identical), attention rows are distributions with exact zeros behind the question
+    length, batch independence (a sample's trajectory does not depend on its batch mates), and state boundedness."""
+    from mac_network_b200.synthetic import SHAPES
+    B, S, N, d, L = SHAPES["headline"]
+    cfg = MACConfig.args("args", netLength=L)
+    inputs = make_inputs(B, S, N, d, seed=1234)
+    params = perturb_biases(init_params(cfg, L, seed=100), seed=101)
+    a, _ = run_gpu(cfg, params, inputs, L, prec=prec)
+    b, _ = run_gpu(cfg, params, inputs, L, prec=prec)
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k                                  # deterministic: no atomics anywhere
+    assert np.allclose(a["att_question"].sum(-1), 1.0, atol=1e-5)
+    assert np.allclose(a["att_kb"].sum(-1), 1.0, atol=1e-5)
+    for bi, n in enumerate(inputs["questionLengths"]):
+        assert np.all(a["att_question"][:, bi, n:] == 0.0)
+    assert np.isfinite(a["memory"]).all() and np.isfinite(a["control"]).all()
+    # batch independence: samples 0..7 alone give the same trajectories as inside the batch of 64
+    sub = {k: np.ascontiguousarray(v[:8]) for k, v in inputs.items()}
+    c, _ = run_gpu(cfg, params, sub, L, prec=prec)
+    tol = 1e-5 if prec == "fp32" else 2e-3       # different tile -> row mapping changes only the bf16 rounding pattern
+    assert max_rel(c["memory"], a["memory"][:, :8]) < tol
+    assert max_rel(c["att_kb"], a["att_kb"][:, :8]) < max(tol, 1e-5)
+
+
+def test_checkpoint_roundtrip_and_attention_export(tmp_path):
+    """Weights travel under the reference's TF variable names; attention maps come out as attMap[key][step][sample]."""
+    from mac_network_b200.checkpoint import save_checkpoint, load_checkpoint, write_preds, MODEL_SCOPE, EMA_SUFFIX
+    from mac_network_b200.mac_cell import MACParams
+    B, S, N, d, L = 4, 6, 196, 64, 2
+    cfg = MACConfig.args("gqa", netLength=L, memDim=d, ctrlDim=d, attDim=d)
+    pv = perturb_biases(init_params(cfg, L, seed=7), seed=8)
+    params = MACParams(cfg, L, values=pv)
+    ema = params.flat * 0.5
+    names = save_checkpoint(str(tmp_path / "w.npz"), params, ema_flat=ema)
+    assert (MODEL_SCOPE + "MACnetwork/MACCell/read/linearLayermemKbProj/linearLayermemKbProj_2/weights/weight") in names
+    assert any(n.endswith(EMA_SUFFIX) for n in names)
+    back = load_checkpoint(str(tmp_path / "w.npz"))
+    for k, v in pv.items():
+        assert np.array_equal(back[k].reshape(v.shape), v), k
+    half = load_checkpoint(str(tmp_path / "w.npz"), use_ema=True)
+    k0 = "MACnetwork/MACCell/linearLayerqInput/weights/weight"
+    assert np.allclose(half[k0], 0.5 * pv[k0])
+    inputs = make_inputs(B, S, N, d, seed=9)
+    got, cell = run_gpu(cfg, back, inputs, L)
+    recs = write_preds(str(tmp_path / "preds.json"), cell)
+    assert len(recs) == B and len(recs[0]["attentions"]["kb"]) == L
+    assert np.asarray(recs[0]["attentions"]["kb"][0]).shape == (14, 14)       # visualization.py:121 reshapes to the grid
+    assert abs(np.asarray(recs[1]["attentions"]["kb"][1]).sum() - 1.0) < 1e-5
+    assert len(recs[0]["attentions"]["self"]) == L and len(recs[0]["attentions"]["gate"]) == L
