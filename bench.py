@@ -260,6 +260,16 @@ def kernel_rooflines(shape, prec, pk):
                                     "l2": "launches rotate over %d knowledge bases (%.0f MB > 126 MB L2), back to back"
                                           % (NB, NB * B * N * d * (2 if bf16 else 4) / 1e6),
                                     "us_single_launch_after_256MB_write_flush": t_cold * 1e6}
+        if not bf16:
+            # context for the fraction: what plain streaming kernels of the SAME size reach when timed the same way
+            # (MEASURED_PEAKS' denominator is a 2 GiB copy; a 26 MB launch pays launch + first-byte latency on ~4 us)
+            srcs = [k.view(-1) for k in kbs]
+            dst = torch.empty(srcs[0].numel() // 2, device="cuda")
+            t_copy = time_kernel([(lambda s_=s_: dst.copy_(s_[:dst.numel()])) for s_ in srcs], iters=48)
+            t_sum = time_kernel([(lambda s_=s_: torch.sum(s_)) for s_ in srcs], iters=48)
+            out["kb_attend_" + name]["same_size_context"] = {
+                "torch_copy_13MB_read_13MB_write_us": t_copy * 1e6, "torch_copy_frac_of_peak": nbytes / t_copy / 1e9 / pk["hbm"],
+                "torch_sum_26MB_read_us": t_sum * 1e6, "torch_sum_frac_of_peak": nbytes / t_sum / 1e9 / pk["hbm"]}
         del kbs
     # ---- dominant projection GEMM: memKbProj, [B*N, 2d] x [2d, d] (49.6 % of the step's FLOPs)
     M, K = B * N, 2 * d
