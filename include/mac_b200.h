@@ -236,6 +236,14 @@ size_t mac_optimizer_workspace_bytes(void);
 int mac_softmax_xent(const float* logits, const int32_t* labels, float* losses, float* dlogits, float scale,
                      int B, int A, mac_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Image stem ("next" row, model.py:165-204, ops.py:380-438): convolution as GEMM.
+ * mac_im2col3x3: cols[(b,h,w), (kh*3+kw)*C + c] = dropout(x)[b, h+kh-1, w+kw-1, c] for NHWC x, zero outside (SAME padding);
+ * the [9*C, Cout] reshape of the HWIO kernel is the GEMM weight.  cols is fp32, or bf16 when cols_bf16 != 0.
+ * --------------------------------------------------------------------------------------------- */
+int mac_im2col3x3(const float* x, void* cols, int cols_bf16, float keep, uint64_t seed, int site, int step,
+                  int B, int H, int W, int C, mac_stream_t stream);
+
 /* dropout sites (the `site` word of the Philox counter) */
 enum { MAC_SITE_MEM_VAR = 0, MAC_SITE_READ_KB = 1, MAC_SITE_READ_MEM = 2, MAC_SITE_READ_INTER = 3,
        MAC_SITE_WRITE_INFO = 4, MAC_SITE_MEM_PLAIN = 5 };

@@ -493,3 +493,66 @@ extern "C" int mac_softmax_xent(const float* logits, const int32_t* labels, floa
   MAC_LAUNCH_CHECK();
   return MAC_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ stem: im2col
+// cols[(b,h,w), (kh*3+kw)*C + c] = dropout(x)[b, h+kh-1, w+kw-1, c]  (zero outside the image: SAME padding, ops.py:395)
+// The keep-mask is a function of the SOURCE element's flat index, so every copy of a pixel carries the same mask
+// (tf.nn.dropout is applied to the layer input before the convolution, ops.py:393).
+namespace mac {
+template <typename OT>
+__global__ void im2col3x3_kernel(const float* __restrict__ x, OT* __restrict__ cols, uint32_t thresh, float scale,
+                                 uint64_t seed, int site, int step, int B, int H, int W, int C) {
+  const int c4n = C / 4;
+  const long long total = (long long)B * H * W * 9 * c4n;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c4 = (int)(i % c4n);
+  long long r = i / c4n;
+  const int tap = (int)(r % 9);
+  r /= 9;
+  const int w = (int)(r % W);
+  r /= W;
+  const int h = (int)(r % H), b = (int)(r / H);
+  const int hs = h + tap / 3 - 1, wsrc = w + tap % 3 - 1;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (hs >= 0 && hs < H && wsrc >= 0 && wsrc < W) {
+    const long long e = (((long long)b * H + hs) * W + wsrc) * C + c4 * 4;
+    v = __ldg(reinterpret_cast<const float4*>(x + e));
+    if (thresh) {
+      const Philox4 p = philox4x32_10(seed, (uint64_t)e >> 2, (uint32_t)site, (uint32_t)step);
+      v.x = ((p.x >> 8) >= thresh) ? v.x * scale : 0.f;
+      v.y = ((p.y >> 8) >= thresh) ? v.y * scale : 0.f;
+      v.z = ((p.z >> 8) >= thresh) ? v.z * scale : 0.f;
+      v.w = ((p.w >> 8) >= thresh) ? v.w * scale : 0.f;
+    }
+  }
+  const long long o = ((((long long)b * H + h) * W + w) * 9 + tap) * C + c4 * 4;
+  if constexpr (sizeof(OT) == 2) {
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 q;
+    q.x = *reinterpret_cast<uint32_t*>(&lo);
+    q.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(cols + o) = q;
+  } else {
+    *reinterpret_cast<float4*>(cols + o) = v;
+  }
+}
+}  // namespace mac
+
+extern "C" int mac_im2col3x3(const float* x, void* cols, int cols_bf16, float keep, uint64_t seed, int site, int step,
+                             int B, int H, int W, int C, mac_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!x || !cols || B <= 0 || H <= 0 || W <= 0 || C <= 0 || (C & 3) || !(keep > 0.f && keep <= 1.f)) return MAC_ERR_INVALID;
+  const uint32_t thr = keep < 1.f ? keep_threshold(keep) : 0u;
+  const float scale = keep < 1.f ? 1.f / keep : 1.f;
+  const long long total = (long long)B * H * W * 9 * (C / 4);
+  const unsigned grid = (unsigned)((total + 255) / 256);
+  if (cols_bf16)
+    im2col3x3_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(cols), thr, scale, seed,
+                                                             site, step, B, H, W, C);
+  else
+    im2col3x3_kernel<float><<<grid, 256, 0, stream>>>(x, reinterpret_cast<float*>(cols), thr, scale, seed, site, step, B, H,
+                                                     W, C);
+  MAC_LAUNCH_CHECK();
+  return MAC_OK;
+}

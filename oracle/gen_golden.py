@@ -203,6 +203,33 @@ def run_output_case(name, train, seed=17, B=6, d=16, A=12, hidden=(8,)):
     return out
 
 
+def run_stem_case(name, train, seed=23, B=2, H=5, W=4, cin=8, cout=8):
+    """Image stem through the reference's own `ops.CNNLayer` as `MACnet.stem` calls it (model.py:165-204, ops.py:380-438)."""
+    set_reference_config("@args.txt", ["--stemDim", str(cout)], dict(L=1, d=cout), train)
+    rc = _ref_config.config
+    from mac_network_b200.stem import stem_specs, init_stem_params
+    specs = stem_specs(cin, cout, rc.stemNumLayers, rc.stemKernelSize)
+    params = init_stem_params(specs, seed=seed, dtype=np.float64)
+    images = np.maximum(np.random.RandomState(seed + 1).standard_normal((B, H, W, cin)), 0)    # post-ReLU ResNet features
+    keep = rc.stemDropout if train else 1.0
+    store = tf.reset_shim(values=params, seed=seed + 2, dtype=np.float64)
+    dims = [cin] + [rc.stemDim] * (rc.stemNumLayers - 1) + [cout]
+    with tf.variable_scope("stem"):
+        feats = _ref_ops.CNNLayer(tf.constant(images), dims, batchNorm=None, dropout=keep,
+                                  kernelSizes=rc.stemKernelSizes, strides=rc.stemStrideSizes)
+        kb = tf.reshape(feats, (B, -1, cout))
+    created = {k: list(v.shape) for k, v in store.vars.items()}
+    assert created == {k: list(v[0]) for k, v in specs.items()}, (created, specs)
+    out = {"images": images, "kb": np.asarray(kb)}
+    for i, u in enumerate(store.uniform_draws):
+        out["uniform_%03d" % i] = u.astype(np.float64)
+    meta = {"case": name, "train": train, "keep": keep, "shape": [B, H, W, cin, cout], "layers": rc.stemNumLayers,
+            "ksize": rc.stemKernelSize, "param_seed": seed, "relu": rc.relu, "variables": created,
+            "n_uniform": len(store.uniform_draws)}
+    out["meta_json"] = np.frombuffer(json.dumps(meta, sort_keys=True).encode(), dtype=np.uint8)
+    return out
+
+
 def main():
     outdir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(outdir, exist_ok=True)
@@ -216,6 +243,13 @@ def main():
         print("%-22s %8.1f KB  vars=%d draws=%d" % (name, os.path.getsize(path) / 1024.0,
                                                      len(json.loads(bytes(out["meta_json"]).decode())["variables"]),
                                                      sum(k.startswith("uniform_") for k in out)))
+    for name, train in (("stem_eval", False), ("stem_train", True)):
+        if only and name not in only:
+            continue
+        out = run_stem_case(name, train)
+        path = os.path.join(outdir, name + ".npz")
+        np.savez_compressed(path, **out)
+        print("%-22s %8.1f KB" % (name, os.path.getsize(path) / 1024.0))
     for name, train in (("output_eval", False), ("output_train", True)):
         if only and name not in only:
             continue

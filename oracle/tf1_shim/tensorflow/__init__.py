@@ -281,6 +281,22 @@ class _nn(object):
         return sigmoid(x)
 
     @staticmethod
+    def conv2d(inp, filter=None, strides=None, padding="SAME", **kw):
+        # NHWC input, HWIO filter, SAME padding (TF: pad_total = k - 1 for stride 1, extra on the bottom/right)
+        x, k = np.asarray(inp), np.asarray(filter)
+        assert padding == "SAME" and tuple(strides) == (1, 1, 1, 1), "only what the default stem uses"
+        kh, kw = k.shape[0], k.shape[1]
+        pt, pl = (kh - 1) // 2, (kw - 1) // 2
+        B, H, W, _ = x.shape
+        xp = np.zeros((B, H + kh - 1, W + kw - 1, x.shape[3]), dtype=x.dtype)
+        xp[:, pt:pt + H, pl:pl + W, :] = x
+        out = np.zeros((B, H, W, k.shape[3]), dtype=x.dtype)
+        for i in range(kh):
+            for j in range(kw):
+                out += np.einsum("bhwc,co->bhwo", xp[:, i:i + H, j:j + W, :], k[i, j])
+        return _t(out)
+
+    @staticmethod
     def sparse_softmax_cross_entropy_with_logits(labels=None, logits=None, **kw):
         # TF: -log_softmax(logits)[label], computed as logsumexp(logits) - logits[label]
         m = np.max(logits, axis=-1, keepdims=True)
