@@ -309,7 +309,27 @@ def kernel_rooflines(shape, prec, pk):
                                 "traffic": ncu_traffic("tc_gemm_memKbProj"), "us": t * 1e6, "algorithmic_flops": flops,
                                 "note": "tcgen05 UMMA, H = ELU([12544,1024] @ [1024,512] + b) bf16 in / bf16 out, "
                                         "fp32 accumulate in TMEM; A rotates over 6 buffers (154 MB > L2); burst peak"}
-    del xb
+    # ---- the per-step form of the same projection in inference: P and Q = P @ Wm[d:2d] + bm are hoisted out of the
+    #      netLength loop (mac_read_invariant), each step runs H = ELU((P*y) @ Wm[0:d] + Q): K = d.  With bf16 in/out this
+    #      GEMM is below the ridge point (AI = 2MKN / 2(MK + 2MN) = K/3 ... 171 FLOP/B < peak_tensor / peak_hbm), i.e.
+    #      HBM-bound on the roofline; both views are reported.
+    Kh = d
+    xh = [x[:, :Kh].contiguous() for x in xb]                                            # 6 x 12.8 MB
+    Wth = Wt[:, :Kh].contiguous()
+    t = time_kernel([(lambda x=x: L.check(lib.mac_linear_tc_fwd(L.ptr(x), L.ptr(Wth), L.ptr(bias), 3, L.ptr(yb), 1, M, Kh,
+                                                                 d, L.stream_ptr()))) for x in xh], iters=30)
+    hflops = 2.0 * M * Kh * d
+    hbytes = 2.0 * (M * Kh + 2 * M * d + Kh * d)          # A in, addend Q in, H out, weights (bf16)
+    t_hbm, t_tc = hbytes / (pk["hbm"] * 1e9), hflops / (pk["tensor_burst"] * 1e12)
+    out["memKbProj_step_gemm_tc"] = {
+        "bound": "hbm" if t_hbm >= t_tc else "tensor",
+        "achieved": hbytes / t / 1e9 if t_hbm >= t_tc else hflops / t / 1e12,
+        "peak": pk["hbm"] if t_hbm >= t_tc else pk["tensor_burst"], "unit": "GB/s" if t_hbm >= t_tc else "TFLOP/s",
+        "frac": max(t_hbm, t_tc) / t, "traffic": ncu_traffic("tc_gemm_memKbProj_step"), "us": t * 1e6,
+        "algorithmic_bytes": hbytes, "algorithmic_flops": hflops, "tflops": hflops / t / 1e12,
+        "note": "tcgen05 UMMA, ELU([12544,512] @ [512,512] (+ Q)) bf16 in / bf16 out; timed through mac_linear_tc_fwd "
+                "(same kernel template, bias instead of the Q addend); A rotates over 6 buffers"}
+    del xb, xh
     # ---- "next" row: the image stem that produces the knowledge base (2 x conv3x3 as im2col + tcgen05 GEMM)
     try:
         from mac_network_b200.stem import Stem, stem_specs, init_stem_params
@@ -400,36 +420,23 @@ def run_ours(args):
     #      final state + attention maps.  ND device slots, each on its own stream, so the copies of one pass overlap the
     #      compute of the others (the public-API pattern for streaming batches).
     ND = max(2, nstreams)
+    from mac_network_b200.serving import HostPipeline, usable_cpus
     host = []
     for s in range(4):
         inp = make_inputs(B, S, N, d, seed=777 + 1000 * rank + s)
-        host.append({k: torch.from_numpy(v).pin_memory() for k, v in inp.items()})
-    dev = [Slot(cfg, params, shape, 0, args.prec, use_graph, host_inputs={k: v.numpy() for k, v in host[0].items()})
-           for _ in range(ND)]
-    outs_host = [[torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in dv.outputs()] for dv in dev]
-    h2d_bytes = sum(v.numel() * v.element_size() for k, v in host[0].items() if k != "questionWords")
-    d2h_bytes = sum(t.numel() * t.element_size() for t in outs_host[0])
-    estreams = [torch.cuda.Stream() for _ in range(ND)]
+        host.append({k: torch.from_numpy(v).pin_memory() for k, v in inp.items() if k != "questionWords"})
+    del slots
+    torch.cuda.empty_cache()
+    pipe = HostPipeline(cfg, params, shape, prec=args.prec, slots=ND, use_graph=use_graph,
+                        cast_threads=max(1, min(12, (usable_cpus() - 1) // max(1, world))))
+    h2d_bytes, d2h_bytes = pipe.h2d_bytes, pipe.d2h_bytes
+    e2e_host_cast, e2e_cast_threads, pipe_cast_ms = pipe.host_kb_bf16, pipe.cast_threads, pipe.cast_ms
 
     def e2e_passes(n):
-        fork = torch.cuda.Event()
-        fork.record(main_stream)
-        for st in estreams:
-            st.wait_event(fork)
+        pipe.after(main_stream)
         for k in range(n):
-            sl = k % ND
-            hb = host[k % len(host)]
-            with torch.cuda.stream(estreams[sl]):
-                for key, t in dev[sl].x.items():
-                    if key != "questionWords":             # unused when controlContextual (mac_cell.py:570)
-                        t.copy_(hb[key], non_blocking=True)
-                dev[sl].run()
-                for src, dst in zip(dev[sl].outputs(), outs_host[sl]):
-                    dst.copy_(src, non_blocking=True)
-        for st in estreams:
-            ev = torch.cuda.Event()
-            ev.record(st)
-            main_stream.wait_event(ev)
+            pipe.submit(host[k % len(host)], next_batch=host[(k + 1) % len(host)])
+        pipe.wait_streams(main_stream)
 
     e2e_passes(max(args.warmup, ND))
     barrier()
@@ -448,7 +455,7 @@ def run_ours(args):
     # ---- data-parallel training arm (all ranks take part: it contains the path's one collective)
     train = None
     if not args.skip_train:
-        del dev, slots
+        del pipe
         torch.cuda.empty_cache()
         train = train_arm(min(args.steps, 4), 2, rank, world, dist)
 
@@ -460,7 +467,7 @@ def run_ours(args):
         else:
             cpu, _ = cpu_reference(cfg, shape, pv)
         value = args.steps * L * world / t_dev
-        dom = "memKbProj_gemm_fp32" if args.prec == "fp32" else "memKbProj_gemm_tc"
+        dom = "memKbProj_gemm_fp32" if args.prec == "fp32" else "memKbProj_step_gemm_tc"
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True,
@@ -475,7 +482,13 @@ def run_ours(args):
                        "data-path collective in inference)" % world},
             "sample_steps_per_sec": value * B,
             "e2e": {"value": args.steps * L * world / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
-                    "d2h_bytes_per_step": d2h_bytes, "ms_per_step": t_e2e / args.steps * 1e3},
+                    "d2h_bytes_per_step": d2h_bytes, "ms_per_step": t_e2e / args.steps * 1e3,
+                    "api": "mac_network_b200.serving.HostPipeline.submit (pinned host fp32 in, pinned host out)",
+                    "host_cast": ("knowledge base fp32 -> bf16 on %d host threads inside the timed region (%.2f ms "
+                                  "per batch when timed alone); H2D moves 2 B per KB element"
+                                  % (e2e_cast_threads, pipe_cast_ms or 0.0)) if e2e_host_cast
+                                 else "off (fp32 knowledge base over PCIe; host cast alone took %s ms on %d threads)"
+                                      % (pipe_cast_ms, e2e_cast_threads)},
             "gpu_launches": int(launches_per_pass) * args.steps,
             "clocks": clocks,
             "roofline": roofs.get(dom, roofs["memKbProj_gemm_fp32"]),

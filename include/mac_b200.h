@@ -123,6 +123,23 @@ int mac_read_fwd(const float* kb, const void* kb_bf16, const float* memory_in, c
                  void* workspace, size_t workspace_bytes, int B, int N, int d, mac_stream_t stream);
 size_t mac_read_workspace_bytes(int B, int N, int d, int prec);
 
+/* Inference form of the read unit.  With readDropout == 1 (eval: mac_cell.py:209-277 runs with keep = 1.0) the
+ * dropout on the knowledge base is the identity and the read weights are the same variables at every one of the
+ * netLength steps, so two of the three big projections do not depend on the step:
+ *   P = KB @ Wx + bx                 (ops.py:688)
+ *   Q = P @ Wm[d:2d, :] + bm         (the un-scaled half of the [P*y, P] concat, mac_cell.py:236-238)
+ * mac_read_invariant computes `inv` = [P | Q] once per forward (fp32 for MAC_PREC_FP32, bf16 for MAC_PREC_BF16);
+ * mac_read_fwd_inv is mac_read_fwd(keep_read = 1, save = NULL) with H = ELU((P*y) @ Wm[0:d, :] + Q): the same
+ * function with 2d instead of 4d multiply-adds per knowledge-base element and step. */
+size_t mac_read_invariant_bytes(int B, int N, int d, int prec);
+int mac_read_invariant(const float* kb, const void* kb_bf16, const mac_read_weights* w, int prec, void* inv,
+                       size_t inv_bytes, int B, int N, int d, mac_stream_t stream);
+int mac_read_fwd_inv(const float* kb, const void* kb_bf16, const void* inv, const float* y_pre,
+                     const float* memory_in, const float* control, const mac_read_weights* w, int prec,
+                     float* info, float* att, void* workspace, size_t workspace_bytes, int B, int N, int d,
+                     mac_stream_t stream);
+/* y_pre (may be NULL): y = memory_in @ Wy + by [B, d] when the caller already has it, see mac_write_fwd_next_y. */
+
 /* The HBM-bound tail of the read unit on its own (ops.py:143, 149-150):
  *   att[b,:] = softmax_n( sum_p logit_parts[(b*N+n)*nparts + p] + br );  info[b,:] = sum_n att[b,n] * KB[b,n,:]
  * kb_is_bf16 != 0: `kb` points at bf16 data. */
@@ -141,6 +158,17 @@ int mac_write_fwd(const float* memory, const float* info, const float* self_smry
                   float* new_memory, float* gate_out,
                   void* workspace, size_t workspace_bytes, int B, int d, mac_stream_t stream);
 size_t mac_write_workspace_bytes(int B, int d);
+
+/* Inference, plain write unit (writeInputs=BOTH, writeMemProj; no self-attention, no gate, no activation): the new
+ * memory and the NEXT step's read-unit memory projection are both linear in [memory, info] (no dropout in between
+ * when memoryDropout == readDropout == 1), so one GEMM against the folded weight gives both:
+ *   new_memory = [memory, info] @ Wf[:, 0:d]  + bf[0:d]         Wf[:, 0:d]  = Ww          (mac_cell.py:339-352)
+ *   y_next     = [memory, info] @ Wf[:, d:2d] + bf[d:2d]        Wf[:, d:2d] = Ww @ Wy, bf[d:2d] = bw @ Wy + by
+ *                                                                (= new_memory @ Wy + by, ops.py:689)
+ * Wf is [2d, 2d] row-major, built by the caller once per parameter update. */
+int mac_write_fwd_next_y(const float* memory, const float* info, const float* Wf, const float* bf,
+                         float* new_memory, float* y_next, void* workspace, size_t workspace_bytes, int B, int d,
+                         mac_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Elementwise helpers used by the Python-composed (non-fused) flag combinations and by state init.
@@ -166,6 +194,16 @@ int mac_dropout_fwd(const float* x, float keep, uint64_t seed, int site, int ste
 int mac_dropout_uniform(uint64_t seed, int site, int step, float* u, long long n, mac_stream_t stream);
 /* fp32 -> bf16 (round-to-nearest-even), plain row-major; used once per forward for KB and per weight update */
 int mac_cast_bf16(const float* x, void* out_bf16, long long n, mac_stream_t stream);
+
+/* HOST-side twin of mac_cast_bf16 for the host-buffer front end (mac_network_b200/serving.py): src and dst are host
+ * pointers; round-to-nearest-even, bit-identical to the device cast for finite inputs; `nthreads` worker threads of a
+ * persistent pool inside the library (<= 1: the calling thread).  Lets the bf16 path copy 2 instead of 4 bytes per
+ * knowledge-base element over PCIe. */
+int mac_host_cast_bf16(const float* src, void* dst_bf16, long long n, int nthreads);
+/* asynchronous form: _begin posts the job to the pool and returns (one job in flight; a second _begin first waits for
+ * the previous job), _end blocks until the posted job is done.  The caller keeps src/dst alive in between. */
+int mac_host_cast_bf16_begin(const float* src, void* dst_bf16, long long n, int nthreads);
+int mac_host_cast_bf16_end(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Tensor-core (MAC_PREC_BF16) helpers.

@@ -43,6 +43,12 @@ PROTOTYPES = {
     "mac_read_fwd": (c_int, [c_fp, c_fp, c_fp, c_fp, ctypes.POINTER(ReadWeights), c_f, c_u64, c_int, c_int, c_fp,
                              c_fp, c_fp, c_fp, c_sz, c_int, c_int, c_int, c_fp]),
     "mac_read_workspace_bytes": (c_sz, [c_int, c_int, c_int, c_int]),
+    "mac_read_invariant_bytes": (c_sz, [c_int, c_int, c_int, c_int]),
+    "mac_read_invariant": (c_int, [c_fp, c_fp, ctypes.POINTER(ReadWeights), c_int, c_fp, c_sz, c_int, c_int, c_int,
+                                   c_fp]),
+    "mac_read_fwd_inv": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, ctypes.POINTER(ReadWeights), c_int, c_fp, c_fp,
+                                 c_fp, c_sz, c_int, c_int, c_int, c_fp]),
+    "mac_write_fwd_next_y": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_sz, c_int, c_int, c_fp]),
     "mac_kb_attend_fwd": (c_int, [c_fp, c_int, c_f, c_fp, c_int, c_fp, c_fp, c_int, c_int, c_int, c_fp]),
     "mac_write_fwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_f, c_fp, c_fp, c_fp, c_sz, c_int,
                               c_int, c_fp]),
@@ -52,6 +58,9 @@ PROTOTYPES = {
     "mac_dropout_fwd": (c_int, [c_fp, c_f, c_u64, c_int, c_int, c_fp, c_ll, c_fp]),
     "mac_dropout_uniform": (c_int, [c_u64, c_int, c_int, c_fp, c_ll, c_fp]),
     "mac_cast_bf16": (c_int, [c_fp, c_fp, c_ll, c_fp]),
+    "mac_host_cast_bf16": (c_int, [c_fp, c_fp, c_ll, c_int]),
+    "mac_host_cast_bf16_begin": (c_int, [c_fp, c_fp, c_ll, c_int]),
+    "mac_host_cast_bf16_end": (c_int, []),
     "mac_linear_bwd": (c_int, [ctypes.POINTER(c_fp), ctypes.POINTER(c_int), ctypes.POINTER(c_int), c_int, c_fp, c_fp, c_int,
                                ctypes.POINTER(c_fp), ctypes.POINTER(c_int), ctypes.POINTER(c_int), c_fp, c_fp, c_int, c_int,
                                c_fp, c_sz, c_fp]),

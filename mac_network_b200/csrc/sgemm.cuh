@@ -27,6 +27,7 @@ struct SgemmParams {
   int nseg;
   const float* rowvec;   // A_ROWSCALE_CONCAT: y[B, K/2]; row m belongs to batch m / rows_per_batch
   int rows_per_batch;
+  int rs_half;           // A_ROWSCALE_CONCAT: width of the scaled part (0 -> K/2; == K -> A = x*y, nothing concatenated)
   uint32_t a_thresh;     // A_DROPOUT
   float a_scale;
   uint64_t seed;
@@ -44,7 +45,9 @@ struct SgemmParams {
   float* Y;              // EPI_BIAS_ACT / EPI_GATE output; EPI_READ_LOGITS: optional I1 store (may be NULL)
   int ldy;
   int accumulate;        // EPI_BIAS_ACT: Y += result (parameter-gradient accumulation over the steps)
-  const float* aux;      // EPI_MUL_ELUGRAD: saved activation [M, ldaux]
+  float* Y2;             // EPI_BIAS_ACT: columns >= n_split go to Y2[m, n - n_split] (same ldy) when Y2 != NULL
+  int n_split;
+  const float* aux;      // EPI_MUL_ELUGRAD: saved activation [M, ldaux]; EPI_BIAS_ACT: optional pre-activation addend
   int ldaux;
   // EPI_READ_LOGITS: t = (acc+bias)*ctrl[b]; i2 = elu(t) (dropout) ; parts[m, blockIdx.x] = sum_n i2*wr[n]
   const float* ctrl;
@@ -78,7 +81,7 @@ __device__ __forceinline__ float4 sg_load_a(const SgemmParams& p, int m, int k) 
       }
     }
   } else if (p.a_mode == A_ROWSCALE_CONCAT) {
-    const int half = p.K >> 1;
+    const int half = p.rs_half ? p.rs_half : (p.K >> 1);
     if (k < half) {
       v = __ldg(reinterpret_cast<const float4*>(p.a[0] + (size_t)m * p.lda[0] + k));
       const float4 y = __ldg(reinterpret_cast<const float4*>(p.rowvec + (size_t)(m / p.rows_per_batch) * half + k));
@@ -299,9 +302,11 @@ __global__ void __launch_bounds__(256, SGEMM_MIN_BLOCKS) sgemm_kernel(const Sgem
         for (int q = 0; q < 4; ++q) {
           float t = acc[i][j + q] + p.bias_const;
           if (p.bias) t += __ldg(p.bias + n + q);
+          if (p.aux) t += __ldg(p.aux + (size_t)m * p.ldaux + n + q);
           v[q] = apply_act(p.act, t);
         }
-        float4* dst = reinterpret_cast<float4*>(p.Y + (size_t)m * p.ldy + n);
+        float4* dst = (p.Y2 && n >= p.n_split) ? reinterpret_cast<float4*>(p.Y2 + (size_t)m * p.ldy + (n - p.n_split))
+                                               : reinterpret_cast<float4*>(p.Y + (size_t)m * p.ldy + n);
         if (p.accumulate) {
           const float4 o = *dst;
           v[0] += o.x; v[1] += o.y; v[2] += o.z; v[3] += o.w;

@@ -123,7 +123,8 @@ static __global__ void __launch_bounds__(SK_THREADS) skinny_gemm_kernel(const Sg
         p.Y[o] = p.gnew[o] * z + p.gold[o] * (1.f - z);
       } else {
         t = apply_act(p.act, t);
-        p.Y[o] = p.accumulate ? p.Y[o] + t : t;
+        float* dst = (p.Y2 && n >= p.n_split) ? p.Y2 + (size_t)m * p.ldy + (n - p.n_split) : p.Y + o;
+        *dst = p.accumulate ? *dst + t : t;
       }
     }
   }
@@ -132,7 +133,7 @@ static __global__ void __launch_bounds__(SK_THREADS) skinny_gemm_kernel(const Sg
 
 // usable when M <= 64, K splits evenly into 8 slices of whole float4s, and the slice fits in shared memory
 inline bool skinny_ok(const SgemmParams& p) {
-  if (p.M > SK_BM || (p.epi != EPI_BIAS_ACT && p.epi != EPI_GATE) || p.a_mode != A_SEGS) return false;
+  if (p.M > SK_BM || (p.epi != EPI_BIAS_ACT && p.epi != EPI_GATE) || p.a_mode != A_SEGS || p.aux) return false;
   if (p.K % (SK_CLUSTER * 4)) return false;
   const int ks = p.K / SK_CLUSTER;
   if (ks > 256) return false;

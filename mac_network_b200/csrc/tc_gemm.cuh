@@ -17,6 +17,8 @@
 //   TC_EPI_LOGITS  I1 = acc + bm2; t = ELU(I1 * control[b]); (dropout); parts[m, ntile] = sum_n t * wr[n]
 //                                                                                (ops.py:325-328, mac_cell.py:248-266)
 //   TC_EPI_F32     act(acc + b)            -> fp32                               (generic ops.linear)
+//   TC_EPI_ADDACT  act(acc + b + add[m,n]) -> bf16, add = bf16 [M, N]           (eval-mode read: step-invariant half of
+//                                                                                 the memKbProj concat, mac_cell.py:236-238)
 #pragma once
 #include "common.cuh"
 #include "tmap.cuh"
@@ -24,7 +26,7 @@
 
 namespace mac {
 
-enum { TC_EPI_P = 0, TC_EPI_ACT = 1, TC_EPI_LOGITS = 2, TC_EPI_F32 = 3 };
+enum { TC_EPI_P = 0, TC_EPI_ACT = 1, TC_EPI_LOGITS = 2, TC_EPI_F32 = 3, TC_EPI_ADDACT = 4 };
 
 struct TcGemmParams {
   int M, N, K;
@@ -34,6 +36,7 @@ struct TcGemmParams {
   __nv_bfloat16* out0;     // bf16 output 0 (P / act / I1-save), may be NULL for TC_EPI_LOGITS
   __nv_bfloat16* out1;     // bf16 output 1 (P*y)
   float* outf;             // fp32 output (TC_EPI_F32)
+  const __nv_bfloat16* add;   // TC_EPI_ADDACT: pre-activation addend [M, ldo]
   int ldo;
   const float* y;          // [B, N] row scale for TC_EPI_P
   const float* ctrl;       // [B, N] for TC_EPI_LOGITS
@@ -91,6 +94,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor) for a K-major tile stored as rows of 128 bytes with
@@ -113,8 +124,10 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
 
 constexpr int TC_BK = 64;                 // 64 bf16 = 128 B = one swizzle atom row
 constexpr int TC_MAX_VEC = 4;              // a 128-row tile spans at most this many samples on the smem-parameter path
-constexpr int TC_EPI_WARPS = 8;            // two per TMEM lane quarter: each handles half of the tile's columns
+constexpr int TC_EPI_WARPS = 8;            // cta_group::2 kernel: two per TMEM lane quarter
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
+constexpr int TC_EW = 16;                  // single-CTA kernel: four epilogue warps per TMEM lane quarter
+constexpr int TC_THREADS1 = 64 + 32 * TC_EW;
 
 // Tile shapes.  The measured per-SM TMA fill rate is ~64 B/clk (profiles/r1/NOTES.md): a k-block of a BM x BN tile
 // brings (BM + BN) * 128 B and feeds BM * BN / 64 MMA cycles, so
@@ -132,11 +145,11 @@ struct TcCfg {
   static constexpr int NBUF = BM == 256 ? 1 : 2;            // accumulator buffers
   static constexpr int BUF_COLS = NMS * BN;
   static constexpr int TMEM_COLS = 512 / (BM == 128 && BN == 128 ? 2 : 1);   // NBUF * BUF_COLS, a power of two
-  static constexpr int STG_WORDS = 32 * 16;                 // per epilogue warp: 32 rows x 16 words, XOR-swizzled
+  static constexpr int STG_WORDS = 32 * 8;                  // per epilogue warp: 32 rows x 8 words (32 B), XOR-swizzled
   static constexpr int PAR_ROWS = 2 + TC_MAX_VEC;           // bias, wr, and up to TC_MAX_VEC per-sample rows (y / control)
   static constexpr int PAR_WORDS = NBUF * PAR_ROWS * BN;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ +
-                                    TC_EPI_WARPS * STG_WORDS * 4 + PAR_WORDS * 4;
+                                    TC_EW * STG_WORDS * 4 + PAR_WORDS * 4;
 };
 
 // fast ELU for the tensor-core path: x > 0 ? x : exp(x) - 1 with the SFU exponential (abs error ~1e-7 near 0,
@@ -156,7 +169,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 }
 
 template <int BM, int BN, int EPI, int ACT>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS1, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                const __grid_constant__ CUtensorMap map_b, const TcGemmParams p) {
   using C = TcCfg<BM, BN>;
@@ -173,7 +186,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   uint64_t* tempty = tfull + 2;                // [2]       epilogue -> MMA
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
   uint32_t* stg_all = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(bars) + 256);
-  float* par_all = reinterpret_cast<float*>(stg_all + TC_EPI_WARPS * C::STG_WORDS);
+  float* par_all = reinterpret_cast<float*>(stg_all + TC_EW * C::STG_WORDS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = (p.M + TC_BM - 1) / TC_BM;
@@ -192,8 +205,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     }
     mbar_init(&tfull[0], 1);
     mbar_init(&tfull[1], 1);
-    mbar_init(&tempty[0], TC_EPI_WARPS);
-    mbar_init(&tempty[1], TC_EPI_WARPS);
+    mbar_init(&tempty[0], TC_EW);
+    mbar_init(&tempty[1], TC_EW);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr, C::TMEM_COLS);
@@ -264,50 +277,58 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       }
     }
   } else {
-    // ===================================================== epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1)
-    // thread == one output row of the tile; 32 fp32 columns per tcgen05.ld
+    // ===================================================== epilogue: TC_EW = 16 warps, four per TMEM lane quarter
+    // thread == one output row of the tile (TMEM lane); the warp walks its share of the tile's columns 16 at a time
+    // (one tcgen05.ld 32x32b.x16).  With two warps per scheduler (the 8-warp version) the ELU/pack/store chain was
+    // issue-latency bound and its ~4 us per 128x256 tile was the largest non-MMA term of the K=512 projections;
+    // four warps per scheduler overlap those chains.
     const int q = warp & 3;
-    uint32_t* stg = stg_all + (warp - 2) * C::STG_WORDS;
-    const int grp = (warp - 2) >> 2;                // BM=128: which half of the tile's columns; BM=256: which M sub-tile
-    const int ms = C::NMS == 2 ? grp : 0;
-    const int c_begin = C::NMS == 2 ? 0 : grp * (BN / 2), c_end = C::NMS == 2 ? BN : (grp + 1) * (BN / 2);
-    // Row-per-thread registers -> coalesced 128-bit global stores.  The warp's 32-row chunk goes through a private
-    // shared-memory patch whose 16-byte groups are XOR-swizzled with the row (conflict-free both ways): thread == row
-    // writes 16-B groups, then lane l reads group (l % G) of row (i*32/G + l / G) and stores 16 B to global, so one
-    // store instruction covers 32/G whole row segments (G = 4: 64-B bf16 rows; G = 8: 128-B fp32 rows).
-    auto store_bf16_chunk = [&](const uint32_t (&w)[16], __nv_bfloat16* out, int row0, int col0) {
+    const int ew = warp - 2;
+    uint32_t* stg = stg_all + ew * C::STG_WORDS;    // 1 KB patch: 32 rows x 32 B
+    const int grp = ew >> 2;                        // 0..3
+    const int ms = C::NMS == 2 ? (grp >> 1) : 0;    // BM=256: which M sub-tile
+    constexpr int CW = C::NMS == 2 ? BN / 2 : BN / 4;                 // columns per warp
+    constexpr int NSUB = C::NMS == 2 ? 2 : 4;                         // logit partial sums per (row, n-tile)
+    const int sub = C::NMS == 2 ? (grp & 1) : grp;
+    const int c_begin = sub * CW, c_end = c_begin + CW;
+    // Row-per-thread registers -> coalesced 128-bit global stores through the warp's private patch.  A patch row is
+    // 32 B = two 16-B groups; group g of row r lives at slot (g ^ ((r >> 2) & 1)), which makes both the row-wise
+    // writes (thread == row) and the read-back (lane l -> group l & 1 of row i*16 + l/2) bank-conflict free.  One
+    // store instruction then covers 16 rows x 32 B (whole sectors).
+    uint4* s4 = reinterpret_cast<uint4*>(stg);
+    const int sw = (lane >> 2) & 1;
+    const int rb_g = lane & 1;
+    auto store_bf16_chunk = [&](const uint32_t (&w)[8], __nv_bfloat16* out, int row0, int col0) {
       __syncwarp();
-      uint4* s4 = reinterpret_cast<uint4*>(stg);
-#pragma unroll
-      for (int g = 0; g < 4; ++g) s4[lane * 4 + (g ^ (lane & 3))] = make_uint4(w[4 * g], w[4 * g + 1], w[4 * g + 2], w[4 * g + 3]);
+      s4[lane * 2 + (0 ^ sw)] = make_uint4(w[0], w[1], w[2], w[3]);
+      s4[lane * 2 + (1 ^ sw)] = make_uint4(w[4], w[5], w[6], w[7]);
       __syncwarp();
-      const int g = lane & 3;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int rr = i * 8 + (lane >> 2);
-        const uint4 v = s4[rr * 4 + (g ^ (rr & 3))];
-        if (row0 + rr < p.M) *reinterpret_cast<uint4*>(out + (size_t)(row0 + rr) * p.ldo + col0 + 8 * g) = v;
+      for (int i = 0; i < 2; ++i) {
+        const int rr = i * 16 + (lane >> 1);
+        const uint4 v = s4[rr * 2 + (rb_g ^ ((rr >> 2) & 1))];
+        if (row0 + rr < p.M) *reinterpret_cast<uint4*>(out + (size_t)(row0 + rr) * p.ldo + col0 + 8 * rb_g) = v;
       }
     };
-    auto store_f32_chunk = [&](const float (&w)[32], float* out, int row0, int col0) {
-      float4* s4 = reinterpret_cast<float4*>(stg);
+    auto store_f32_chunk = [&](const float (&w)[16], float* out, int row0, int col0) {
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {            // two 16-column halves through the 2 KB patch
+      for (int h = 0; h < 2; ++h) {            // two 8-column halves through the 1 KB patch
+        __syncwarp();
+        s4[lane * 2 + (0 ^ sw)] = make_uint4(__float_as_uint(w[8 * h]), __float_as_uint(w[8 * h + 1]),
+                                             __float_as_uint(w[8 * h + 2]), __float_as_uint(w[8 * h + 3]));
+        s4[lane * 2 + (1 ^ sw)] = make_uint4(__float_as_uint(w[8 * h + 4]), __float_as_uint(w[8 * h + 5]),
+                                             __float_as_uint(w[8 * h + 6]), __float_as_uint(w[8 * h + 7]));
         __syncwarp();
 #pragma unroll
-        for (int g = 0; g < 4; ++g)
-          s4[lane * 4 + (g ^ (lane & 3))] = make_float4(w[16 * h + 4 * g], w[16 * h + 4 * g + 1], w[16 * h + 4 * g + 2], w[16 * h + 4 * g + 3]);
-        __syncwarp();
-        const int g = lane & 3;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int rr = i * 8 + (lane >> 2);
-          const float4 v = s4[rr * 4 + (g ^ (rr & 3))];
-          if (row0 + rr < p.M) *reinterpret_cast<float4*>(out + (size_t)(row0 + rr) * p.ldo + col0 + 16 * h + 4 * g) = v;
+        for (int i = 0; i < 2; ++i) {
+          const int rr = i * 16 + (lane >> 1);
+          const uint4 v = s4[rr * 2 + (rb_g ^ ((rr >> 2) & 1))];
+          if (row0 + rr < p.M)
+            *reinterpret_cast<uint4*>(out + (size_t)(row0 + rr) * p.ldo + col0 + 8 * h + 4 * rb_g) = v;
         }
       }
     };
-    const int etid = threadIdx.x - 64;              // 0..255 among the epilogue threads
+    const int etid = threadIdx.x - 64;              // 0..511 among the epilogue threads
     const float* vec_src = (EPI == TC_EPI_P) ? p.y : (EPI == TC_EPI_LOGITS ? p.ctrl : nullptr);
     int it = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
@@ -323,33 +344,54 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       const bool vec_smem = nvec <= TC_MAX_VEC;
       {
         const int nb = nt * BN;
-        for (int i = etid; i < BN; i += 32 * TC_EPI_WARPS) {
+        for (int i = etid; i < BN; i += 32 * TC_EW) {
           par[i] = p.bias ? __ldg(p.bias + nb + i) : 0.f;
           if constexpr (EPI == TC_EPI_LOGITS) par[BN + i] = __ldg(p.wr + nb + i);
         }
         if (vec_src && vec_smem)
-          for (int i = etid; i < nvec * BN; i += 32 * TC_EPI_WARPS)
+          for (int i = etid; i < nvec * BN; i += 32 * TC_EW)
             par[2 * BN + i] = __ldg(vec_src + (size_t)(b_lo + i / BN) * p.N + nb + (i % BN));
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EW) : "memory");
       }
-      mbar_wait(&tfull[acc], acc_phase);
-      tc_fence_after();
       const int row0 = mt * TC_BM + ms * 128 + q * 32;
       const int row = row0 + lane;
       const bool row_ok = row < p.M;
       const int bidx = row_ok ? row / p.rows_per_batch : b_lo;
       const float* vrow = vec_smem ? par + (2 + bidx - b_lo) * BN : nullptr;   // this row's y / control vector (tile-local)
       const uint32_t taddr = tmem_base + acc * C::BUF_COLS + ms * BN + ((uint32_t)(q * 32) << 16);
+      // TC_EPI_ADDACT: the bf16 addend of up to ADD_WIN chunks, in the coalesced (read-back) mapping.  It does not
+      // depend on the accumulator, so the loads are issued before the wait on it and overlap this tile's MMAs
+      // (with a one-chunk look-ahead the epilogue paid one DRAM/L2 round trip per chunk: 24.7 -> 21.1 us -> see NOTES).
+      constexpr int NCH = CW / 16;
+      constexpr int ADD_WIN = (EPI == TC_EPI_ADDACT) ? (NCH < 4 ? NCH : 4) : 1;
+      uint4 addq[ADD_WIN][2];
+      auto load_addend = [&](int slot, int c0) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int rr = i * 16 + (lane >> 1);
+          addq[slot][i] = (row0 + rr < p.M)
+              ? __ldg(reinterpret_cast<const uint4*>(p.add + (size_t)(row0 + rr) * p.ldo + nt * BN + c0 + 8 * rb_g))
+              : make_uint4(0u, 0u, 0u, 0u);
+        }
+      };
+      if constexpr (EPI == TC_EPI_ADDACT) {
+#pragma unroll
+        for (int k = 0; k < ADD_WIN; ++k) load_addend(k, c_begin + 16 * k);
+      }
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
       float part = 0.f;
-#pragma unroll 1
-      for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+      // the ADDACT variant is fully unrolled so that the addend window is indexed statically
+#pragma unroll (EPI == TC_EPI_ADDACT ? NCH : 1)
+      for (int ch = 0; ch < NCH; ++ch) {
+        const int c0 = c_begin + 16 * ch;
         if (p.debug & 1) break;
-        uint32_t r[32];
+        uint32_t r[16];
         if (p.debug & 8) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) r[j] = (uint32_t)(c0 + j);
+          for (int j = 0; j < 16; ++j) r[j] = (uint32_t)(c0 + j);
         } else {
-          tmem_ld32(taddr + c0, r);
+          tmem_ld16(taddr + c0, r);
           tmem_ld_wait();
         }
         const int n0 = nt * BN + c0;
@@ -357,9 +399,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         if constexpr (EPI == TC_EPI_P) {
           const float4* y4 = vec_smem ? reinterpret_cast<const float4*>(vrow + c0)
                                       : reinterpret_cast<const float4*>(p.y + (size_t)bidx * p.N + n0);
-          uint32_t w0[16], w1[16];
+          uint32_t w0[8], w1[8];
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
+          for (int j = 0; j < 16; j += 4) {
             const float4 b0 = bias4[j / 4], y0 = y4[j / 4];
             const float x0 = __uint_as_float(r[j]) + b0.x, x1 = __uint_as_float(r[j + 1]) + b0.y;
             const float x2 = __uint_as_float(r[j + 2]) + b0.z, x3 = __uint_as_float(r[j + 3]) + b0.w;
@@ -371,33 +413,55 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           store_bf16_chunk(w0, p.out0, row0, n0);
           store_bf16_chunk(w1, p.out1, row0, n0);
         } else if constexpr (EPI == TC_EPI_ACT) {
-          uint32_t w0[16];
+          uint32_t w0[8];
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
+          for (int j = 0; j < 16; j += 4) {
             const float4 b0 = bias4[j / 4];
             w0[j / 2] = pack_bf16(act_ct<ACT>(__uint_as_float(r[j]) + b0.x), act_ct<ACT>(__uint_as_float(r[j + 1]) + b0.y));
             w0[j / 2 + 1] = pack_bf16(act_ct<ACT>(__uint_as_float(r[j + 2]) + b0.z), act_ct<ACT>(__uint_as_float(r[j + 3]) + b0.w));
           }
           store_bf16_chunk(w0, p.out0, row0, n0);
-        } else if constexpr (EPI == TC_EPI_F32) {
-          float w0[32];
+        } else if constexpr (EPI == TC_EPI_ADDACT) {
+          // addend chunk -> patch (coalesced mapping) -> own row back into registers
+          __syncwarp();
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
+          for (int i = 0; i < 2; ++i) {
+            const int rr = i * 16 + (lane >> 1);
+            s4[rr * 2 + (rb_g ^ ((rr >> 2) & 1))] = addq[ch % ADD_WIN][i];
+          }
+          __syncwarp();
+          const uint4 qa = s4[lane * 2 + (0 ^ sw)], qb = s4[lane * 2 + (1 ^ sw)];
+          if (ch + ADD_WIN < NCH) load_addend(ch % ADD_WIN, c0 + 16 * ADD_WIN);   // refill the slot just consumed
+          const uint32_t qw[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+          uint32_t w0[8];
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            const float4 b0 = bias4[j / 4];
+            // bf16 -> fp32 is a 16-bit shift
+            const float q0 = __uint_as_float(qw[j / 2] << 16), q1 = __uint_as_float(qw[j / 2] & 0xffff0000u);
+            const float q2 = __uint_as_float(qw[j / 2 + 1] << 16), q3 = __uint_as_float(qw[j / 2 + 1] & 0xffff0000u);
+            w0[j / 2] = pack_bf16(act_ct<ACT>(__uint_as_float(r[j]) + b0.x + q0), act_ct<ACT>(__uint_as_float(r[j + 1]) + b0.y + q1));
+            w0[j / 2 + 1] = pack_bf16(act_ct<ACT>(__uint_as_float(r[j + 2]) + b0.z + q2), act_ct<ACT>(__uint_as_float(r[j + 3]) + b0.w + q3));
+          }
+          store_bf16_chunk(w0, p.out0, row0, n0);
+        } else if constexpr (EPI == TC_EPI_F32) {
+          float w0[16];
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
             const float4 b0 = bias4[j / 4];
             w0[j] = act_ct<ACT>(__uint_as_float(r[j]) + b0.x);
             w0[j + 1] = act_ct<ACT>(__uint_as_float(r[j + 1]) + b0.y);
             w0[j + 2] = act_ct<ACT>(__uint_as_float(r[j + 2]) + b0.z);
             w0[j + 3] = act_ct<ACT>(__uint_as_float(r[j + 3]) + b0.w);
           }
-          if (!(p.debug & 32)) store_f32_chunk(w0, p.outf, row0, n0);
-          else if (w0[lane] == 123.456f) p.outf[0] = 1.f;
+          store_f32_chunk(w0, p.outf, row0, n0);
         } else {  // TC_EPI_LOGITS
           const float4* c4 = vec_smem ? reinterpret_cast<const float4*>(vrow + c0)
                                       : reinterpret_cast<const float4*>(p.ctrl + (size_t)bidx * p.N + n0);
           const float4* w4 = reinterpret_cast<const float4*>(par + BN + c0);
-          uint32_t w0[16];
+          uint32_t w0[8];
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
+          for (int j = 0; j < 16; j += 4) {
             const float4 b0 = bias4[j / 4], cc = c4[j / 4], ww = w4[j / 4];
             const float i0 = __uint_as_float(r[j]) + b0.x, i1 = __uint_as_float(r[j + 1]) + b0.y;
             const float i2 = __uint_as_float(r[j + 2]) + b0.z, i3 = __uint_as_float(r[j + 3]) + b0.w;
@@ -421,11 +485,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         }
       }
       if constexpr (EPI == TC_EPI_LOGITS) {
-        // BM=128: two partial sums per (row, n-tile), one per column half; BM=256: one
-        if (row_ok) {
-          if (C::NMS == 2) p.parts[(size_t)row * n_tiles + nt] = part;
-          else p.parts[((size_t)row * n_tiles + nt) * 2 + grp] = part;
-        }
+        // NSUB partial sums per (row, n-tile): one per epilogue warp that shares the row
+        if (row_ok) p.parts[((size_t)row * n_tiles + nt) * NSUB + sub] = part;
       }
       // release the accumulator buffer to the MMA warp
       tc_fence_before();
@@ -804,7 +865,7 @@ inline int tc_gemm_launch_t(const CUtensorMap& ma0, const CUtensorMap& ma1, cons
   // tiles (epilogue of the first overlaps the MMAs of the second) and leave 50 SMs to concurrent streams
   const int rounds = (tiles + tc_num_sms() - 1) / tc_num_sms();
   const int grid = (tiles + rounds - 1) / rounds;
-  kern<<<grid, TC_THREADS, TcCfg<BM, BN>::SMEM_BYTES, stream>>>(ma0, ma1, mb, p);
+  kern<<<grid, TC_THREADS1, TcCfg<BM, BN>::SMEM_BYTES, stream>>>(ma0, ma1, mb, p);
   MAC_LAUNCH_CHECK();
   return MAC_OK;
 }
@@ -814,6 +875,9 @@ inline int tc_gemm_dispatch(const CUtensorMap& ma0, const CUtensorMap& ma1, cons
                             const TcGemmParams& p, cudaStream_t stream) {
   switch (p.epi) {
     case TC_EPI_P: return tc_gemm_launch_t<BM, BN, TC_EPI_P, MAC_ACT_NON>(ma0, ma1, mb, p, stream);
+    case TC_EPI_ADDACT:
+      if (p.act == MAC_ACT_ELU) return tc_gemm_launch_t<BM, BN, TC_EPI_ADDACT, MAC_ACT_ELU>(ma0, ma1, mb, p, stream);
+      return MAC_ERR_UNSUPPORTED;
     case TC_EPI_LOGITS: return tc_gemm_launch_t<BM, BN, TC_EPI_LOGITS, MAC_ACT_NON>(ma0, ma1, mb, p, stream);
     case TC_EPI_ACT:
       if (p.act == MAC_ACT_ELU) return tc_gemm_launch_t<BM, BN, TC_EPI_ACT, MAC_ACT_ELU>(ma0, ma1, mb, p, stream);
@@ -897,7 +961,8 @@ inline int tc_pick_tile(int M, int N) {
 
 // A = [a0 (K0 cols) | a1 (K1 cols)] bf16 row-major (ld = own K), Wt bf16 [N, K0+K1]
 inline int tc_gemm_launch(const void* a0, int K0, const void* a1, int K1, const void* wt, TcGemmParams p,
-                          cudaStream_t stream, int* nparts_per_row = nullptr) {
+                          cudaStream_t stream, int* nparts_per_row = nullptr, int ldw = 0) {
+  if (ldw == 0) ldw = K0 + K1;                  // row pitch of Wt in elements (> K: a column block of a wider weight)
   if (p.M <= 0 || p.N <= 0 || (p.N % 128) || (K0 % TC_BK) || (K1 % TC_BK) || K0 <= 0) return MAC_ERR_UNSUPPORTED;
   if (!mac_aligned16(a0) || !mac_aligned16(wt)) return MAC_ERR_ALIGN;
   int tile = tc_pick_tile(p.M, p.N);
@@ -908,7 +973,7 @@ inline int tc_gemm_launch(const void* a0, int K0, const void* a1, int K1, const 
   if (const char* e = getenv("MAC_TC_DEBUG")) p.debug = atoi(e);
   // cta_group::2 pair kernel (opt-in while it is being qualified): MAC_TC_PAIR=1
   bool pair = false;
-  if (const char* e = getenv("MAC_TC_PAIR")) pair = atoi(e) != 0 && (p.N % 256 == 0) && p.M > 128;
+  if (const char* e = getenv("MAC_TC_PAIR")) pair = atoi(e) != 0 && (p.N % 256 == 0) && p.M > 128 && p.epi != TC_EPI_ADDACT;
   if (pair) {
     if (nparts_per_row) *nparts_per_row = (p.N / 256) * 2;
     p.K = K0 + K1;
@@ -922,12 +987,12 @@ inline int tc_gemm_launch(const void* a0, int K0, const void* a1, int K1, const 
     } else {
       ma1 = ma0;
     }
-    st = make_tmap_2d(&mb, wt, 1, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)p.K * 2, 128, TC_BK, 1);
+    st = make_tmap_2d(&mb, wt, 1, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)ldw * 2, 128, TC_BK, 1);
     if (st != MAC_OK) return st;
     return tc2_gemm_dispatch(ma0, ma1, mb, p, stream);
   }
   const int BM = tile / 1000, BN = tile % 1000;
-  if (nparts_per_row) *nparts_per_row = (p.N / BN) * (BM == 256 ? 1 : 2);
+  if (nparts_per_row) *nparts_per_row = (p.N / BN) * (BM == 256 ? 2 : 4);
   p.K = K0 + K1;
   p.kblocks0 = K0 / TC_BK;
   CUtensorMap ma0, ma1, mb;
@@ -939,7 +1004,7 @@ inline int tc_gemm_launch(const void* a0, int K0, const void* a1, int K1, const 
   } else {
     ma1 = ma0;
   }
-  st = make_tmap_2d(&mb, wt, 1, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)p.K * 2, (uint32_t)BN, TC_BK, 1);
+  st = make_tmap_2d(&mb, wt, 1, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)ldw * 2, (uint32_t)BN, TC_BK, 1);
   if (st != MAC_OK) return st;
   if (tile == 256256) return tc_gemm_dispatch<256, 256>(ma0, ma1, mb, p, stream);
   if (tile == 128256) return tc_gemm_dispatch<128, 256>(ma0, ma1, mb, p, stream);
@@ -1018,6 +1083,94 @@ inline int tc_read_chain(const float* kb_f32, const void* kb_bf16, const float* 
   st = tc_gemm_launch(H, d, nullptr, 0, w->Wm2_bf16, p, stream, nparts);
   if (st != MAC_OK) return st;
   return MAC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Eval-mode read (readDropout == 1): dropout(KB) == KB at every step and the read weights are shared over the steps
+// (mac_cell.py:209-277 is called with the same variables for each of the netLength cells), so
+//   P = KB @ Wx + bx                (ops.py:688)                       and
+//   Q = P @ Wm[d:2d, :] + bm        (the projected-KB half of the [P*y, P] concat, mac_cell.py:236-238)
+// do not depend on the step.  They are computed once per forward into `inv` = [P | Q] (bf16), and each step runs
+//   PY = P * y_b ;  H = ELU(PY @ Wm[0:d, :] + Q) ;  logits = ... (unchanged)
+// i.e. 2 x d instead of 4 x d MACs per knowledge-base element and step.
+inline size_t tc_read_invariant_bytes(int B, int N, int d) {
+  return (size_t)2 * (((size_t)B * N * d * 2 + 1023) & ~(size_t)1023) + 1024;
+}
+
+// PY[m, :] = P[m, :] * y[m / rows_per_batch, :]   (8 bf16 per thread)
+__global__ void scale_rows_bf16_kernel(const uint4* __restrict__ P, const float* __restrict__ y, uint4* __restrict__ out,
+                                       int rows_per_batch, int d, long long n8) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  const long long e = i * 8;
+  const int c = (int)(e % d);
+  const long long b = (e / d) / rows_per_batch;
+  const uint4 v = P[i];
+  const float4 y0 = __ldg(reinterpret_cast<const float4*>(y + b * d + c));
+  const float4 y1 = __ldg(reinterpret_cast<const float4*>(y + b * d + c + 4));
+  auto lo = [](uint32_t w) { return __uint_as_float(w << 16); };
+  auto hi = [](uint32_t w) { return __uint_as_float(w & 0xffff0000u); };
+  out[i] = make_uint4(pack_bf16(lo(v.x) * y0.x, hi(v.x) * y0.y), pack_bf16(lo(v.y) * y0.z, hi(v.y) * y0.w),
+                      pack_bf16(lo(v.z) * y1.x, hi(v.z) * y1.y), pack_bf16(lo(v.w) * y1.z, hi(v.w) * y1.w));
+}
+
+inline char* tc_align1k(void* p) {
+  return reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~(uintptr_t)1023);
+}
+
+inline int tc_read_invariant(const void* kb_bf16, const mac_read_weights* w, void* inv, size_t inv_bytes, int B, int N,
+                             int d, cudaStream_t stream) {
+  if (!kb_bf16 || !w->Wx_bf16 || !w->Wm_bf16 || !inv) return MAC_ERR_INVALID;
+  if (d % 128) return MAC_ERR_UNSUPPORTED;
+  if (inv_bytes < tc_read_invariant_bytes(B, N, d)) return MAC_ERR_WORKSPACE;
+  const int M = B * N;
+  const size_t slab = (((size_t)M * d * 2 + 1023) & ~(size_t)1023);
+  char* base = tc_align1k(inv);
+  __nv_bfloat16* P = reinterpret_cast<__nv_bfloat16*>(base);
+  __nv_bfloat16* Q = reinterpret_cast<__nv_bfloat16*>(base + slab);
+  TcGemmParams p{};
+  p.M = M; p.N = d; p.rows_per_batch = N; p.ldo = d;
+  p.epi = TC_EPI_ACT; p.act = MAC_ACT_NON; p.bias = w->bx; p.out0 = P;
+  int st = tc_gemm_launch(kb_bf16, d, nullptr, 0, w->Wx_bf16, p, stream);
+  if (st != MAC_OK) return st;
+  p.bias = w->bm; p.out0 = Q;
+  return tc_gemm_launch(P, d, nullptr, 0, reinterpret_cast<const __nv_bfloat16*>(w->Wm_bf16) + d, p, stream, nullptr, 2 * d);
+}
+
+inline int tc_read_chain_inv(const void* inv, const float* y, const float* control, const mac_read_weights* w, float* parts,
+                             int* nparts, void* ws, size_t ws_bytes, int B, int N, int d, cudaStream_t stream) {
+  if (!inv || !w->Wm_bf16 || !w->Wm2_bf16) return MAC_ERR_INVALID;
+  if (d % 128) return MAC_ERR_UNSUPPORTED;
+  if (ws_bytes < tc_read_extra_workspace_bytes(B, N, d)) return MAC_ERR_WORKSPACE;
+  const int M = B * N;
+  const size_t slab = (((size_t)M * d * 2 + 1023) & ~(size_t)1023);
+  const char* ibase = tc_align1k(const_cast<void*>(inv));
+  const __nv_bfloat16* P = reinterpret_cast<const __nv_bfloat16*>(ibase);
+  const __nv_bfloat16* Q = reinterpret_cast<const __nv_bfloat16*>(ibase + slab);
+  char* base = tc_align1k(ws);
+  __nv_bfloat16* PY = reinterpret_cast<__nv_bfloat16*>(base + slab);
+  __nv_bfloat16* H = reinterpret_cast<__nv_bfloat16*>(base + 2 * slab);
+  const long long n8 = (long long)M * d / 8;
+  scale_rows_bf16_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, stream>>>(
+      reinterpret_cast<const uint4*>(P), y, reinterpret_cast<uint4*>(PY), N, d, n8);
+  MAC_LAUNCH_CHECK();
+  TcGemmParams p{};
+  p.M = M; p.N = d; p.rows_per_batch = N; p.ldo = d;
+  int st;
+  static const bool q_hoist = !(getenv("MAC_READ_QHOIST") && atoi(getenv("MAC_READ_QHOIST")) == 0);
+  if (q_hoist) {
+    // H = ELU(PY @ Wm[0:d] + Q)      (bm is inside Q)
+    p.epi = TC_EPI_ADDACT; p.act = MAC_ACT_ELU; p.bias = nullptr; p.out0 = H; p.add = Q;
+    st = tc_gemm_launch(PY, d, nullptr, 0, w->Wm_bf16, p, stream, nullptr, 2 * d);
+  } else {
+    // experiment switch: keep the concatenated K = 2d form, H = ELU([PY, P] @ Wm + bm), with only P hoisted
+    p.epi = TC_EPI_ACT; p.act = MAC_ACT_ELU; p.bias = w->bm; p.out0 = H;
+    st = tc_gemm_launch(PY, d, P, d, w->Wm_bf16, p, stream);
+  }
+  if (st != MAC_OK) return st;
+  p.epi = TC_EPI_LOGITS; p.act = MAC_ACT_NON; p.bias = w->bm2; p.out0 = nullptr; p.add = nullptr;
+  p.ctrl = control; p.wr = w->wr; p.parts = parts;
+  return tc_gemm_launch(H, d, nullptr, 0, w->Wm2_bf16, p, stream, nparts);
 }
 
 }  // namespace mac

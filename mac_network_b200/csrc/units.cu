@@ -113,7 +113,7 @@ extern "C" int mac_linear_fwd(const float* const* x_segs, const int* k_segs, con
 }
 
 // ------------------------------------------------------------------------------------------------ read unit
-// workspace layout: [header 4 KB | md [B,d] | y [B,d] | P [BN,d] | H [BN,d] | logit parts [BN, d/128.. <=8] | split-K]
+// workspace layout: [header 4 KB | md [B,d] | y [B,d] | P [BN,d] | H [BN,d] | logit parts [BN, <=32] | split-K]
 static size_t read_ws_layout(int B, int N, int d, size_t* off_md, size_t* off_y, size_t* off_P, size_t* off_H,
                              size_t* off_parts, size_t* off_splitk) {
   size_t o = WS_HEADER;
@@ -122,7 +122,7 @@ static size_t read_ws_layout(int B, int N, int d, size_t* off_md, size_t* off_y,
   *off_y = take((size_t)B * d * 4);
   *off_P = take((size_t)B * N * d * 4);
   *off_H = take((size_t)B * N * d * 4);
-  *off_parts = take((size_t)B * N * 16 * 4);
+  *off_parts = take((size_t)B * N * 32 * 4);
   *off_splitk = o;
   o += sgemm_workspace_bytes(B, d, d);
   return o;
@@ -135,15 +135,69 @@ extern "C" size_t mac_read_workspace_bytes(int B, int N, int d, int prec) {
   return fp32;
 }
 
+// ---- step-invariant part of the eval-mode read unit (see tc_read_invariant in tc_gemm.cuh): inv = [P | Q]
+static size_t read_inv_fp32_bytes(int B, int N, int d) { return (size_t)2 * B * N * d * 4 + 256; }
+
+extern "C" size_t mac_read_invariant_bytes(int B, int N, int d, int prec) {
+  return prec == MAC_PREC_BF16 ? tc_read_invariant_bytes(B, N, d) : read_inv_fp32_bytes(B, N, d);
+}
+
+extern "C" int mac_read_invariant(const float* kb, const void* kb_bf16, const mac_read_weights* w, int prec, void* inv,
+                                  size_t inv_bytes, int B, int N, int d, mac_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  // the bf16 path reads only kb_bf16: the fp32 knowledge base may be absent (host-cast front end)
+  if ((!kb && !(prec == MAC_PREC_BF16 && kb_bf16)) || !w || !inv || B <= 0 || N <= 0 || d <= 0 || (d & 3))
+    return MAC_ERR_INVALID;
+  if ((kb && !mac_aligned16(kb)) || !mac_aligned16(inv)) return MAC_ERR_ALIGN;
+  if (inv_bytes < mac_read_invariant_bytes(B, N, d, prec)) return MAC_ERR_WORKSPACE;
+  if (prec == MAC_PREC_BF16) return tc_read_invariant(kb_bf16, w, inv, inv_bytes, B, N, d, stream);
+  const int M = B * N;
+  float* P = reinterpret_cast<float*>(inv);
+  float* Q = P + (size_t)M * d;
+  SgemmParams p{};
+  // P = KB @ Wx + bx   (ops.py:688)
+  p.a_mode = A_SEGS; p.nseg = 1; p.a[0] = kb; p.ak[0] = d; p.lda[0] = d;
+  p.W = w->Wx; p.ldw = d; p.M = M; p.N = d; p.K = d;
+  p.epi = EPI_BIAS_ACT; p.bias = w->bx; p.act = MAC_ACT_NON; p.Y = P; p.ldy = d;
+  int st = sgemm_launch(p, nullptr, nullptr, 0, stream, false);
+  if (st != MAC_OK) return st;
+  // Q = P @ Wm[d:2d, :] + bm   (the un-scaled half of the concat, mac_cell.py:236-238)
+  p.a[0] = P; p.W = w->Wm + (size_t)d * d; p.bias = w->bm; p.Y = Q;
+  return sgemm_launch(p, nullptr, nullptr, 0, stream, false);
+}
+
+static int read_fwd_impl(const float* kb, const void* kb_bf16, const void* inv, const float* y_pre,
+                         const float* memory_in, const float* control, const mac_read_weights* w, float keep_read,
+                         uint64_t seed, int step, int prec, float* info, float* att, float* save, void* workspace,
+                         size_t workspace_bytes, int B, int N, int d, mac_stream_t stream_);
+
 extern "C" int mac_read_fwd(const float* kb, const void* kb_bf16, const float* memory_in, const float* control,
                             const mac_read_weights* w, float keep_read, uint64_t seed, int step, int prec, float* info,
                             float* att, float* save, void* workspace, size_t workspace_bytes, int B, int N, int d,
                             mac_stream_t stream_) {
+  return read_fwd_impl(kb, kb_bf16, nullptr, nullptr, memory_in, control, w, keep_read, seed, step, prec, info, att,
+                       save, workspace, workspace_bytes, B, N, d, stream_);
+}
+
+extern "C" int mac_read_fwd_inv(const float* kb, const void* kb_bf16, const void* inv, const float* y_pre,
+                                const float* memory_in, const float* control, const mac_read_weights* w, int prec,
+                                float* info, float* att, void* workspace, size_t workspace_bytes, int B, int N, int d,
+                                mac_stream_t stream_) {
+  if (!inv || !mac_aligned16(inv) || (y_pre && !mac_aligned16(y_pre))) return MAC_ERR_INVALID;
+  return read_fwd_impl(kb, kb_bf16, inv, y_pre, memory_in, control, w, 1.f, 0, 0, prec, info, att, nullptr, workspace,
+                       workspace_bytes, B, N, d, stream_);
+}
+
+static int read_fwd_impl(const float* kb, const void* kb_bf16, const void* inv, const float* y_pre,
+                         const float* memory_in, const float* control, const mac_read_weights* w, float keep_read,
+                         uint64_t seed, int step, int prec, float* info, float* att, float* save, void* workspace,
+                         size_t workspace_bytes, int B, int N, int d, mac_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  if (!kb || !memory_in || !control || !w || !info || !att || !workspace) return MAC_ERR_INVALID;
+  const bool kb_opt = inv && prec == MAC_PREC_BF16 && kb_bf16;     // eval bf16 path: only the bf16 copy is read
+  if ((!kb && !kb_opt) || !memory_in || !control || !w || !info || !att || !workspace) return MAC_ERR_INVALID;
   if (B <= 0 || N <= 0 || d <= 0 || (d & 3)) return MAC_ERR_INVALID;
   if (!(keep_read > 0.f && keep_read <= 1.f)) return MAC_ERR_INVALID;
-  if (!mac_aligned16(kb) || !mac_aligned16(memory_in) || !mac_aligned16(control) || !mac_aligned16(workspace))
+  if ((kb && !mac_aligned16(kb)) || !mac_aligned16(memory_in) || !mac_aligned16(control) || !mac_aligned16(workspace))
     return MAC_ERR_ALIGN;
   if (workspace_bytes < mac_read_workspace_bytes(B, N, d, prec)) return MAC_ERR_WORKSPACE;
   size_t o_md, o_y, o_P, o_H, o_parts, o_sk;
@@ -170,8 +224,10 @@ extern "C" int mac_read_fwd(const float* kb, const void* kb_bf16, const float* m
     MAC_LAUNCH_CHECK();
     mem = md;
   }
-  // y = md @ Wy + by   (ops.py:689)
-  {
+  // y = md @ Wy + by   (ops.py:689) -- unless the caller already has it (mac_write_fwd_next_y of the previous step)
+  if (y_pre) {
+    y = const_cast<float*>(y_pre);
+  } else {
     SgemmParams p{};
     p.a_mode = A_SEGS; p.nseg = 1; p.a[0] = mem; p.ak[0] = d; p.lda[0] = d;
     p.W = w->Wy; p.ldw = d; p.M = B; p.N = d; p.K = d;
@@ -181,7 +237,33 @@ extern "C" int mac_read_fwd(const float* kb, const void* kb_bf16, const float* m
     if (st != MAC_OK) return st;
   }
   int nparts = 0;
-  if (prec == MAC_PREC_BF16) {
+  if (inv && prec == MAC_PREC_BF16) {
+    int st = tc_read_chain_inv(inv, y, control, w, parts, &nparts, ws + fp32_total, workspace_bytes - fp32_total, B, N,
+                               d, stream);
+    if (st != MAC_OK) return st;
+  } else if (inv) {
+    const float* Pi = reinterpret_cast<const float*>(inv);
+    const float* Qi = Pi + (size_t)M * d;
+    // H = ELU((P*y) @ Wm[0:d, :] + Q)   (bm is inside Q)
+    {
+      SgemmParams p{};
+      p.a_mode = A_ROWSCALE_CONCAT; p.rs_half = d; p.nseg = 1; p.a[0] = Pi; p.lda[0] = d; p.rowvec = y; p.rows_per_batch = N;
+      p.W = w->Wm; p.ldw = d; p.M = M; p.N = d; p.K = d;
+      p.epi = EPI_BIAS_ACT; p.bias = nullptr; p.aux = Qi; p.ldaux = d; p.act = MAC_ACT_ELU; p.Y = H; p.ldy = d;
+      int st = sgemm_launch(p, nullptr, nullptr, 0, stream, false);
+      if (st != MAC_OK) return st;
+    }
+    {
+      SgemmParams p{};
+      p.a_mode = A_SEGS; p.nseg = 1; p.a[0] = H; p.ak[0] = d; p.lda[0] = d;
+      p.W = w->Wm2; p.ldw = d; p.M = M; p.N = d; p.K = d; p.rows_per_batch = N;
+      p.epi = EPI_READ_LOGITS; p.bias = w->bm2; p.Y = nullptr; p.ldy = d;
+      p.ctrl = control; p.wr = w->wr; p.logit_parts = parts; p.e_thresh = 0u; p.e_scale = 1.f;
+      int st = sgemm_launch(p, nullptr, nullptr, 0, stream, false);
+      if (st != MAC_OK) return st;
+      nparts = (M >= 512) ? (d + 127) / 128 : (d + 63) / 64;
+    }
+  } else if (prec == MAC_PREC_BF16) {
     int st = tc_read_chain(kb, kb_bf16, y, control, w, thr, scale, seed, step, P, H, I1, parts, &nparts,
                            ws + fp32_total, workspace_bytes - fp32_total, B, N, d, save != nullptr, stream);
     if (st != MAC_OK) return st;
@@ -218,7 +300,7 @@ extern "C" int mac_read_fwd(const float* kb, const void* kb_bf16, const float* m
       nparts = (M >= 512) ? (d + 127) / 128 : (d + 63) / 64;
     }
   }
-  if (nparts > 16) return MAC_ERR_UNSUPPORTED;
+  if (nparts > 32) return MAC_ERR_UNSUPPORTED;
   // att = softmax(logits); info = sum_n att * KB   (original, un-dropped KB: mac_cell.py:271-275)
   if (prec == MAC_PREC_BF16 && kb_bf16 != nullptr)
     return mac_kb_attend_fwd(parts, nparts, w->br, kb_bf16, 1, att, info, B, N, d, stream_);
@@ -227,7 +309,27 @@ extern "C" int mac_read_fwd(const float* kb, const void* kb_bf16, const float* m
 
 // ------------------------------------------------------------------------------------------------ write unit
 extern "C" size_t mac_write_workspace_bytes(int B, int d) {
-  return WS_HEADER + (size_t)B * d * 4 + 256 + sgemm_workspace_bytes(B, d, 3 * d);
+  return WS_HEADER + (size_t)B * d * 4 + 256 + sgemm_workspace_bytes(B, 2 * d, 3 * d);
+}
+
+// plain write unit + the next step's memory projection in one GEMM (inference; see mac_b200.h)
+extern "C" int mac_write_fwd_next_y(const float* memory, const float* info, const float* Wf, const float* bf,
+                                    float* new_memory, float* y_next, void* workspace, size_t workspace_bytes, int B,
+                                    int d, mac_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!memory || !info || !Wf || !new_memory || !y_next || !workspace || B <= 0 || d <= 0 || (d & 3)) return MAC_ERR_INVALID;
+  if (workspace_bytes < mac_write_workspace_bytes(B, d)) return MAC_ERR_WORKSPACE;
+  char* ws = reinterpret_cast<char*>(workspace);
+  const size_t o_sk = WS_HEADER + (((size_t)B * d * 4 + 255) & ~(size_t)255);
+  SgemmParams p{};
+  p.a_mode = A_SEGS; p.nseg = 2;
+  p.a[0] = memory; p.ak[0] = d; p.lda[0] = d;
+  p.a[1] = info; p.ak[1] = d; p.lda[1] = d;
+  p.W = Wf; p.ldw = 2 * d; p.M = B; p.N = 2 * d; p.K = 2 * d;
+  p.epi = EPI_BIAS_ACT; p.bias = bf; p.act = MAC_ACT_NON;
+  p.Y = new_memory; p.ldy = d; p.Y2 = y_next; p.n_split = d;
+  return sgemm_launch(p, reinterpret_cast<unsigned int*>(ws), reinterpret_cast<float*>(ws + o_sk),
+                      workspace_bytes - o_sk, stream);
 }
 
 extern "C" int mac_write_fwd(const float* memory, const float* info, const float* self_smry, const float* control,

@@ -20,6 +20,7 @@ plus the three units with the reference signatures (`control` 133-187, `read` 20
 """
 import collections
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -154,9 +155,13 @@ class MACCell(object):
         self._fused_write = (c.writeInputs == "BOTH" and c.writeMemProj and not c.writeConcatMul and not c.writeInfoProj
                              and c.writeInfoAct == "NON" and not c.writeMergeCtrl and c.writeMemAct == "NON")
         self._fused_control = not (c.controlConcatWords or c.controlProj)
-        for t in (vecQuestions, questionCntxWords, knowledgeBase):
+        # the knowledge base may arrive already in bf16 (host-cast front end, serving.py): bf16 eval path only
+        self._kb_given_bf16 = knowledgeBase.dtype == torch.bfloat16
+        for t in (vecQuestions, questionCntxWords) + (() if self._kb_given_bf16 else (knowledgeBase,)):
             if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
                 raise ValueError("inputs must be contiguous CUDA float32 tensors")
+        if self._kb_given_bf16 and not (knowledgeBase.is_cuda and knowledgeBase.is_contiguous()):
+            raise ValueError("a bf16 knowledge base must be a contiguous CUDA tensor")
         self.vecQuestions = vecQuestions
         self.questionWords = questionWords
         self.questionCntxWords = questionCntxWords
@@ -179,6 +184,15 @@ class MACCell(object):
         self._hoist = (not (c.controlFeedPrev or c.controlWholeQ or c.controlContinuous or c.unsharedCells)
                        and self._fused_control)
         self._rw = {}
+        self._read_inv = {}
+        # eval-mode hoist of the step-invariant read projections (shared cells only; env MAC_NO_READ_HOIST=1 disables)
+        self._read_hoist = (self._fused_read and not c.unsharedCells and not save_for_backward
+                            and os.environ.get("MAC_NO_READ_HOIST", "0") != "1")
+        # plain write unit: its GEMM also produces the next step's memory projection (env MAC_NO_FOLD_Y=1 disables)
+        self._fold_y = (self._read_hoist and self._fused_write and not (c.writeSelfAtt or c.writeGate)
+                        and not (c.writeDropout < 1.0 and float(writeDropout) < 1.0)
+                        and os.environ.get("MAC_NO_FOLD_Y", "0") != "1")
+        self._y_for = -1
         self.kb_bf16 = None
         self.save_for_backward = bool(save_for_backward)
         recurrent_ctrl_ok = (c.controlFeedPrev and self._fused_control and not (c.controlWholeQ or c.controlContinuous
@@ -188,6 +202,8 @@ class MACCell(object):
             raise NotImplementedError("backward is implemented on the fused fp32 path (DESIGN.md section 9)")
         if self.prec != PREC["fp32"] and not self._fused_read:
             raise NotImplementedError("the tensor-core projections cover the fused read unit only")
+        if self._kb_given_bf16 and not (self.prec == PREC["bf16"] and self._read_hoist and float(readDropout) >= 1.0):
+            raise NotImplementedError("a bf16 knowledge base is accepted by the bf16 inference path only")
 
     # ------------------------------------------------------------------ reference properties
     @property
@@ -238,6 +254,7 @@ class MACCell(object):
     def zero_state(self, batchSize=None, dtype=None):
         c, B, d, L = self.cfg, self.B, self.d, self.L
         self.attentions = {"kb": [], "question": [], "self": [], "gate": []}        # mac_cell.py:541
+        self._read_inv = {}
         # step-major histories [L+1, B, d]; the reference's [B, i+1, d] tensors are permuted views of these
         self._hc = self._new(L + 1, B, d)
         self._hm = self._new(L + 1, B, d)
@@ -258,11 +275,15 @@ class MACCell(object):
         self._att_q = self._new(L, B, words.shape[1])
         self._att_kb = self._new(L, B, self.N)
         self._gate = self._new(L, B, d) if c.writeGate else None
-        if self.prec == PREC["bf16"]:
+        if self._kb_given_bf16:
+            self.kb_bf16 = self.knowledgeBase
+        elif self.prec == PREC["bf16"]:
             self.kb_bf16 = torch.empty(self.knowledgeBase.shape, dtype=torch.bfloat16, device=self.device)
             check(self.lib.mac_cast_bf16(ptr(self.knowledgeBase), ptr(self.kb_bf16), self.knowledgeBase.numel(),
                                          stream_ptr()), "mac_cast_bf16")
         self._mem_in = self._new(B, d)
+        self._y_next = self._new(B, d)
+        self._y_for = -1
         if self.save_for_backward:
             self._ctrl_saved = {}
             M = B * self.N
@@ -375,7 +396,8 @@ class MACCell(object):
         self._rw[name] = rw
         return rw
 
-    def read(self, knowledgeBase, memory, control, name="", reuse=None, _att_out=None, _out=None, _save=None):
+    def read(self, knowledgeBase, memory, control, name="", reuse=None, _att_out=None, _out=None, _save=None,
+             _y_pre=None):
         """mac_cell.py:209-277 (returns the retrieved information [B, memDim])."""
         c, B, N, d = self.cfg, self.B, self.N, self.d
         i = self.iteration
@@ -393,6 +415,21 @@ class MACCell(object):
             _save = self._save[i]
             self._mem_in_hist[i].copy_(memory)
         rw = self._read_weights(name)
+        if self._read_hoist and self.dropouts["read"] >= 1.0 and _save is None:
+            # eval mode: P and Q = P @ Wm[d:2d] + bm do not depend on the step -> once per forward (mac_b200.h)
+            kb32 = None if knowledgeBase.dtype == torch.bfloat16 else ptr(knowledgeBase)
+            if name not in self._read_inv:
+                nbytes = self.lib.mac_read_invariant_bytes(B, N, d, self.prec)
+                inv = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+                check(self.lib.mac_read_invariant(kb32, ptr(self.kb_bf16), ctypes.byref(rw), self.prec,
+                                                  ptr(inv), nbytes, B, N, d, stream_ptr()), "mac_read_invariant")
+                self._read_inv[name] = inv
+            check(self.lib.mac_read_fwd_inv(kb32, ptr(self.kb_bf16), ptr(self._read_inv[name]), ptr(_y_pre),
+                                            ptr(memory), ptr(control), ctypes.byref(rw), self.prec, ptr(info), ptr(att),
+                                            ptr(self.ws.read), self.ws.read_bytes, B, N, d, stream_ptr()),
+                  "mac_read_fwd_inv")
+            self.attentions["kb"].append(att)
+            return info
         check(self.lib.mac_read_fwd(ptr(knowledgeBase), ptr(self.kb_bf16), ptr(memory), ptr(control),
                                     ctypes.byref(rw), float(self.dropouts["read"]), self.seed, i, self.prec,
                                     ptr(info), ptr(att), ptr(_save), ptr(self.ws.read), self.ws.read_bytes, B, N, d,
@@ -401,13 +438,37 @@ class MACCell(object):
         return info
 
     # ------------------------------------------------------------------ write unit
-    def write(self, memory, info, control, contControl=None, name="", reuse=None, _out=None, _gate_out=None):
+    def _folded_write_weights(self, name):
+        """[Ww | Ww @ Wy], [bw | bw @ Wy + by]: the plain write unit and the next step's memory projection as one
+        linear map of [memory, info] (mac_b200.h, mac_write_fwd_next_y); rebuilt when the parameters change."""
+        def build():
+            d = self.d
+            Ww, bw = self.params.lin("MACCell/write" + name + "/", "newMemory")
+            Wy, by = self.params.lin("MACCell/read" + name + "/mulmemInter/", "projY")
+            Wf = self._new(2 * d, 2 * d)
+            bf = self._new(2 * d)
+            Wf[:, :d].copy_(Ww)
+            bf[:d].copy_(bw)
+            self._linear([Ww], Wy, None, Wf[:, d:])                       # Ww @ Wy        (ldy = 2d)
+            self._linear([bw.view(1, d)], Wy, by, bf[d:].view(1, d))      # bw @ Wy + by
+            return Wf, bf
+        return self.params.derived(("foldY", name), build)
+
+    def write(self, memory, info, control, contControl=None, name="", reuse=None, _out=None, _gate_out=None,
+              _y_next=None):
         """mac_cell.py:305-375 (returns the new memory [B, memDim])."""
         c, B, d = self.cfg, self.B, self.d
         sc = "MACCell/write" + name + "/"
         i = self.iteration
         if not self._fused_write:
             return self._write_general(memory, info, control, contControl, name, _out, _gate_out)
+        if _y_next is not None:
+            Wf, bf = self._folded_write_weights(name)
+            out = _out if _out is not None else self._new(B, d)
+            check(self.lib.mac_write_fwd_next_y(ptr(memory), ptr(info), ptr(Wf), ptr(bf), ptr(out), ptr(_y_next),
+                                                ptr(self.ws.write), self.ws.write_bytes, B, d, stream_ptr()),
+                  "mac_write_fwd_next_y")
+            return out
         selfSmry = None
         if c.writeSelfAtt:
             selfControl = contControl if c.writeSelfAttMod == "CONT" else control
@@ -614,11 +675,14 @@ class MACCell(object):
             self._hc[i + 1].copy_(self.vecQuestions)
             newControl = self._hc[i + 1]
         info = self.read(self.knowledgeBase, memory, newControl, name=cellName, _att_out=self._att_kb[i],
-                         _out=self._hi[i + 1])
+                         _out=self._hi[i + 1], _y_pre=self._y_next if self._y_for == i else None)
         if c.writeDropout < 1.0 and self.dropouts["write"] < 1.0:                      # mac_cell.py:461-463
             info = self._dropout(info, self.dropouts["write"], _lib.SITE_WRITE_INFO, i, self._hi[i + 1])
+        fold = self._fold_y and i + 1 < self.L and self.dropouts["read"] >= 1.0 and self.dropouts["memory"] >= 1.0
         newMemory = self.write(memory, info, newControl, self.contControl, name=cellName, _out=self._hm[i + 1],
-                               _gate_out=None if self._gate is None else self._gate[i])
+                               _gate_out=None if self._gate is None else self._gate[i],
+                               _y_next=self._y_next if fold else None)
+        self._y_for = i + 1 if fold else -1
         self._set_histories(i + 1)                                                     # mac_cell.py:472-474
         return self.none, MACCellTuple(newControl, newMemory)
 

@@ -1,0 +1,177 @@
+"""Host-buffer front end of the inference path: what a caller with numpy / pinned-host batches uses.
+
+The reference feeds each batch from host memory through feed_dict (model.py:1001-1049: createFeedDict); here a batch
+goes   host fp32 -> [host cast of the knowledge base to bf16, bf16 path only] -> pinned staging -> H2D on the slot's
+stream -> the captured netLength unroll -> D2H of the final state and the attention maps into pinned host memory.
+`slots` batches are in flight at once, each on its own CUDA stream, so the PCIe copies of one batch overlap the kernels
+of the others.  The knowledge base is 83 % of a batch's bytes; the bf16 read unit only ever reads its bf16 copy
+(mac_cast_bf16 would make it on the device), so casting on the host (mac_host_cast_bf16, a thread pool inside the
+C library; same bits) halves the H2D traffic -- PCIe, not the GPU, bounds this path.
+"""
+import ctypes
+import os
+import torch
+
+from . import _lib
+from .mac_cell import MACCell, mac_network
+
+
+def usable_cpus():
+    """CPUs this process may use: affinity mask capped by the cgroup quota (containers)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            quota, period = f.read().split()
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return max(1, n)
+
+
+class _Slot(object):
+    def __init__(self, cfg, params, shape, prec, host_kb_bf16, use_graph):
+        B, S, N, d, L = shape
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.stream = torch.cuda.Stream()
+        self.x = {
+            "vecQuestions": torch.zeros(B, d, device=dev),
+            "questionCntxWords": torch.zeros(B, S, d, device=dev),
+            "questionLengths": torch.full((B,), S, dtype=torch.int32, device=dev),
+            "knowledgeBase": torch.zeros(B, N, d, device=dev, dtype=torch.bfloat16 if host_kb_bf16 else torch.float32),
+        }
+        x = self.x
+        # questionWords is unused with controlContextual (mac_cell.py:570); the cell takes the contextual words for both
+        self.cell = MACCell(x["vecQuestions"], x["questionCntxWords"], x["questionCntxWords"], x["questionLengths"],
+                            x["knowledgeBase"], 1.0, 1.0, 1.0, B, False, config=cfg, params=params, prec=prec)
+        self.L = L
+        self.graph = None
+        with torch.cuda.stream(self.stream):
+            mac_network(self.cell, L)                      # warm-up: packed weights, folded weights, attributes
+            self.stream.synchronize()
+            if use_graph:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=self.stream):
+                    mac_network(self.cell, L)
+                self.graph = g
+        c = self.cell
+        self.outs_dev = {"control": c._hc[L], "memory": c._hm[L], "att_kb": c._att_kb, "att_question": c._att_q}
+        self.outs_host = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in self.outs_dev.items()}
+        self.kb_stage = (torch.empty(B, N, d, dtype=torch.bfloat16).pin_memory() if host_kb_bf16 else None)
+        self.h2d_done = torch.cuda.Event()
+        self.done = torch.cuda.Event()
+        self.busy = False
+
+
+class HostPipeline(object):
+    """`submit(batch)` takes one batch of HOST tensors (fp32; pinned for asynchronous copies) with the keys
+    vecQuestions [B,d], questionCntxWords [B,S,d], questionLengths [B] (int32) and knowledgeBase [B,N,d]; it returns a
+    ticket.  `result(ticket)` blocks until that batch is done and returns pinned host tensors (final control / memory
+    state, per-step KB and question attention maps) that stay valid until the slot is reused `slots` submits later."""
+
+    def __init__(self, cfg, params, shape, prec="bf16", slots=4, use_graph=True, cast_threads=None):
+        self.lib = _lib.load()
+        self.shape = shape
+        self.prec = prec
+        self.host_kb_bf16 = (prec == "bf16" and os.environ.get("MAC_NO_HOST_CAST", "0") != "1"
+                             and os.environ.get("MAC_NO_READ_HOIST", "0") != "1" and cfg.is_fast_path
+                             and not cfg.unsharedCells)
+        self.cast_threads = int(cast_threads) if cast_threads else max(1, min(12, usable_cpus() - 2))
+        if os.environ.get("MAC_HOST_CAST_THREADS"):
+            self.cast_threads = max(1, int(os.environ["MAC_HOST_CAST_THREADS"]))
+        self.cast_ms = None
+        if self.host_kb_bf16 and os.environ.get("MAC_NO_HOST_CAST", "") != "0":
+            # the cast pays off only if it is faster than the PCIe time of the bytes it saves (2 B per KB element at a
+            # conservative 25 GB/s); with few host threads per rank (torchrun on a small CPU quota) it is not
+            self.cast_ms = self._time_cast(shape)
+            saved_ms = shape[0] * shape[2] * shape[3] * 2 / 25e9 * 1e3
+            if self.cast_ms > 0.8 * saved_ms:
+                self.host_kb_bf16 = False
+        self.slots = [_Slot(cfg, params, shape, prec, self.host_kb_bf16, use_graph) for _ in range(max(1, slots))]
+        self._cast_for = None
+        self._next = 0
+        B, S, N, d, L = shape
+        kb_bytes = B * N * d * (2 if self.host_kb_bf16 else 4)
+        self.h2d_bytes = kb_bytes + B * S * d * 4 + B * d * 4 + B * 4
+        self.d2h_bytes = sum(v.numel() * v.element_size() for v in self.slots[0].outs_host.values())
+
+    def _time_cast(self, shape):
+        import time
+        n = shape[0] * shape[2] * shape[3]
+        src = torch.zeros(n, dtype=torch.float32).pin_memory()
+        dst = torch.empty(n, dtype=torch.bfloat16).pin_memory()
+        best = float("inf")
+        for _ in range(4):
+            t0 = time.perf_counter()
+            self.lib.mac_host_cast_bf16(ctypes.c_void_p(src.data_ptr()), ctypes.c_void_p(dst.data_ptr()), n, self.cast_threads)
+            best = min(best, time.perf_counter() - t0)
+        return best * 1e3
+
+    # -- host cast of the knowledge base, one batch ahead of the GPU work, on the library's thread pool
+    #    (mac_host_cast_bf16_begin returns at once; no Python threads, so no GIL hand-offs in the submit loop)
+    def prefetch(self, batch):
+        """Optional: start the host cast for the batch that the NEXT submit() will take."""
+        if not self.host_kb_bf16:
+            return
+        kb = batch["knowledgeBase"]
+        if self._cast_for is not None:
+            if self._cast_for[0] == self._next and self._cast_for[1] is kb:
+                return
+            self.lib.mac_host_cast_bf16_end()
+        slot = self.slots[self._next % len(self.slots)]
+        if slot.busy:
+            slot.h2d_done.synchronize()                # the previous copy out of this staging buffer has finished
+        st = self.lib.mac_host_cast_bf16_begin(ctypes.c_void_p(kb.data_ptr()), ctypes.c_void_p(slot.kb_stage.data_ptr()),
+                                               kb.numel(), self.cast_threads)
+        if st != 0:
+            raise _lib.MacB200Error("mac_host_cast_bf16_begin failed: %d" % st)
+        self._cast_for = (self._next, kb)
+
+    def submit(self, batch, next_batch=None):
+        t = self._next
+        slot = self.slots[t % len(self.slots)]
+        if self.host_kb_bf16:
+            self.prefetch(batch)
+            self.lib.mac_host_cast_bf16_end()
+            self._cast_for = None
+        self._next = t + 1
+        if next_batch is not None:
+            self.prefetch(next_batch)
+        with torch.cuda.stream(slot.stream):
+            slot.x["vecQuestions"].copy_(batch["vecQuestions"], non_blocking=True)
+            slot.x["questionCntxWords"].copy_(batch["questionCntxWords"], non_blocking=True)
+            slot.x["questionLengths"].copy_(batch["questionLengths"], non_blocking=True)
+            slot.x["knowledgeBase"].copy_(slot.kb_stage if self.host_kb_bf16 else batch["knowledgeBase"], non_blocking=True)
+            slot.h2d_done.record(slot.stream)
+            if slot.graph is not None:
+                slot.graph.replay()
+            else:
+                mac_network(slot.cell, slot.L)
+            for k, src in slot.outs_dev.items():
+                slot.outs_host[k].copy_(src, non_blocking=True)
+            slot.done.record(slot.stream)
+        slot.busy = True
+        return t
+
+    def result(self, ticket):
+        slot = self.slots[ticket % len(self.slots)]
+        slot.done.synchronize()
+        return slot.outs_host
+
+    def drain(self):
+        for s in self.slots:
+            if s.busy:
+                s.done.synchronize()
+
+    def after(self, stream):
+        """Make every slot's stream wait for what has been enqueued on `stream` so far (device-side fork)."""
+        ev = torch.cuda.Event()
+        ev.record(stream)
+        for s in self.slots:
+            s.stream.wait_event(ev)
+
+    def wait_streams(self, stream):
+        """Make `stream` wait for everything submitted so far (device-side join, for event timing)."""
+        for s in self.slots:
+            if s.busy:
+                stream.wait_event(s.done)

@@ -246,3 +246,53 @@ def test_checkpoint_roundtrip_and_attention_export(tmp_path):
     assert np.asarray(recs[0]["attentions"]["kb"][0]).shape == (14, 14)       # visualization.py:121 reshapes to the grid
     assert abs(np.asarray(recs[1]["attentions"]["kb"][1]).sum() - 1.0) < 1e-5
     assert len(recs[0]["attentions"]["self"]) == L and len(recs[0]["attentions"]["gate"]) == L
+
+
+@pytest.mark.parametrize("prec,variant,shape", [
+    ("fp32", "args", (16, 20, 196, 512, 4)),
+    ("fp32", "gqa", (5, 7, 49, 128, 3)),
+    ("bf16", "args", (8, 12, 196, 512, 4)),
+    ("bf16", "gqa", (64, 30, 49, 512, 6)),
+])
+def test_step_invariant_read_hoist_is_the_same_function(monkeypatch, prec, variant, shape):
+    """Eval mode computes P = KB@Wx+bx and Q = P@Wm[d:2d]+bm once per forward (mac_read_invariant / mac_read_fwd_inv).
+    The per-step form (mac_read_fwd, what training uses) must stay the same function: both against the oracle, and
+    against each other."""
+    B, S, N, d, L = shape
+    cfg = MACConfig.args(variant, netLength=L, memDim=d, ctrlDim=d, attDim=d)
+    inputs = make_inputs(B, S, N, d, seed=61, dtype=np.float64)
+    params = perturb_biases(init_params(cfg, L, seed=62, dtype=np.float64), seed=63)
+    hoisted, _ = run_gpu(cfg, params, inputs, L, prec=prec)
+    monkeypatch.setenv("MAC_NO_READ_HOIST", "1")
+    stepwise, _ = run_gpu(cfg, params, inputs, L, prec=prec)
+    ref = run_oracle(cfg, params, inputs, L)
+    tol = 1e-4 if prec == "fp32" else 3e-2
+    for k in ("memory", "info", "att_kb"):
+        assert max_rel(hoisted[k], ref[k]) < tol, (k, "hoisted")
+        assert max_rel(stepwise[k], ref[k]) < tol, (k, "stepwise")
+        assert max_rel(hoisted[k], stepwise[k]) < (2e-5 if prec == "fp32" else 2e-2), k
+    print(prec, variant, {k: (max_rel(hoisted[k], ref[k]), max_rel(stepwise[k], ref[k])) for k in ("memory", "info")})
+
+
+@pytest.mark.parametrize("prec", ["bf16", "fp32"])
+def test_host_pipeline_matches_direct_cell(prec):
+    """serving.HostPipeline (host fp32 in -> [host bf16 cast] -> H2D -> graph -> D2H) returns what the cell computes from
+    device-resident inputs; in-flight slots do not mix batches up."""
+    from mac_network_b200.mac_cell import MACParams
+    from mac_network_b200.serving import HostPipeline
+    B, S, N, d, L = 8, 6, 49, 128, 3
+    cfg = MACConfig.args("args", netLength=L, memDim=d, ctrlDim=d, attDim=d)
+    pv = perturb_biases(init_params(cfg, L, seed=82), seed=83)
+    params = MACParams(cfg, L, values=pv)
+    pipe = HostPipeline(cfg, params, (B, S, N, d, L), prec=prec, slots=2, cast_threads=3)
+    batches = [make_inputs(B, S, N, d, seed=90 + i) for i in range(5)]
+    host = [{k: torch.from_numpy(v).pin_memory() for k, v in b.items() if k != "questionWords"} for b in batches]
+    got = []
+    for i, hb in enumerate(host):
+        t = pipe.submit(hb, next_batch=host[(i + 1) % len(host)])
+        got.append({k: v.clone() for k, v in pipe.result(t).items()})
+    for b, g in zip(batches, got):
+        ref, _ = run_gpu(cfg, pv, b, L, prec=prec)
+        assert np.array_equal(g["memory"].numpy(), ref["memory"][-1]), prec       # same kernels, same bits
+        assert np.array_equal(g["control"].numpy(), ref["control"][-1])
+        assert np.array_equal(g["att_kb"].numpy(), ref["att_kb"])
