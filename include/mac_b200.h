@@ -282,6 +282,33 @@ int mac_softmax_xent(const float* logits, const int32_t* labels, float* losses, 
 int mac_im2col3x3(const float* x, void* cols, int cols_bf16, float keep, uint64_t seed, int site, int step,
                   int B, int H, int W, int C, mac_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Question input unit ("next" row, model.py:208-220, 279-307; ops.py:859-905): embedding lookup + bi-LSTM encoder.
+ * mac_embed_fwd: out[b,s,:] = dropout( idx[b,s] == 0 ? 0 : emb[idx[b,s]-1, :] )  (the reference prepends a zero padding
+ *   row to the variable `qEmbeddings/emb` [V,E], model.py:217-218; ids outside 0..V read as zero); out_raw (may be NULL)
+ *   receives the undropped words (`questionWords`).  E % 4 == 0.
+ * mac_embed_bwd: d_emb[v,:] += sum_{(b,s): idx == v+1} d_out[b,s,:] * keep-mask / keep, positions in a fixed order.
+ * mac_lstm_fwd: tf.nn.(bidirectional_)dynamic_rnn over BasicLSTMCell (gate order i,j,f,o; TF kernel [E+h, 4h]) with
+ *   sequence_length = lengths.  The caller supplies the hoisted input projection gx_dir [B*S, 4h] = X @ kernel[0:E] + bias
+ *   (mac_linear_fwd) and Wh_dir = kernel + E*4h (the recurrent rows).  Direction 1 walks t = len-1 .. 0 (reverse_sequence).
+ *   out_seq [B,S,ndir*h] = [fw | bw] outputs, zero for t >= len; vecq [B,ndir*h] (may be NULL) = the final h of each
+ *   direction (ops.py:893-898).  save_gates [ndir,B*S,4h], save_c / save_hprev [ndir,B*S,h] (all or none NULL) keep what
+ *   the backward needs, indexed by time.  Issues S launches (one per step, both directions) on `stream`.
+ * mac_lstm_bwd: BPTT.  dG_dir [B*S, 4h] receives the gradient w.r.t. the pre-activation gates; parameter and input
+ *   gradients are then GEMMs over all steps: mac_linear_bwd(x_segs = [dropout(X), save_hprev_dir], dy = dG_dir).
+ * --------------------------------------------------------------------------------------------- */
+int mac_embed_fwd(const float* emb, const int32_t* idx, float keep, uint64_t seed, int site, int step, float* out_raw,
+                  float* out, int B, int S, int V, int E, mac_stream_t stream);
+int mac_embed_bwd(const float* d_out, const int32_t* idx, float keep, uint64_t seed, int site, int step, float* d_emb,
+                  int B, int S, int V, int E, mac_stream_t stream);
+size_t mac_lstm_workspace_bytes(int B, int h, int ndir);
+int mac_lstm_fwd(const float* gx_fw, const float* gx_bw, const float* Wh_fw, const float* Wh_bw, const int32_t* lengths,
+                 float forget_bias, float* out_seq, float* vecq, float* save_gates, float* save_c, float* save_hprev,
+                 void* workspace, size_t workspace_bytes, int B, int S, int h, int ndir, mac_stream_t stream);
+int mac_lstm_bwd(const float* Wh_fw, const float* Wh_bw, const int32_t* lengths, const float* save_gates,
+                 const float* save_c, const float* d_out_seq, const float* d_vecq, float* dG_fw, float* dG_bw,
+                 void* workspace, size_t workspace_bytes, int B, int S, int h, int ndir, mac_stream_t stream);
+
 /* dropout sites (the `site` word of the Philox counter) */
 enum { MAC_SITE_MEM_VAR = 0, MAC_SITE_READ_KB = 1, MAC_SITE_READ_MEM = 2, MAC_SITE_READ_INTER = 3,
        MAC_SITE_WRITE_INFO = 4, MAC_SITE_MEM_PLAIN = 5 };

@@ -230,6 +230,45 @@ def run_stem_case(name, train, seed=23, B=2, H=5, W=4, cin=8, cout=8):
     return out
 
 
+def run_encoder_case(name, train, proj, seed=29, B=5, S=7, V=11, E=12, enc_dim=16):
+    """Question input unit through the reference's own `MACnet.qEmbeddingsOp` + `MACnet.encoder` (model.py:208-220, 279-307)
+    -> `ops.RNNLayer` / `biRNNLayer` (ops.py:859-952) on the shim's BasicLSTMCell / bidirectional_dynamic_rnn."""
+    import types
+    ref_model = importlib.import_module("model")
+    ctrl = enc_dim + 4 if proj else enc_dim
+    set_reference_config("@args.txt", ["--encDim", str(enc_dim), "--wrdEmbDim", str(E)] + (["--encProj"] if proj else []),
+                         dict(L=1, d=ctrl), train)
+    rc = _ref_config.config
+    assert rc.encBi and rc.encType == "LSTM" and rc.encNumLayers == 1 and not rc.encVariationalDropout
+    from mac_network_b200.encoder import encoder_specs, init_encoder_params
+    specs = encoder_specs(V, E, enc_dim, ctrl_dim=ctrl, bi=True, proj=proj)
+    params = init_encoder_params(specs, seed=seed, dtype=np.float64)
+    rng = np.random.RandomState(seed + 1)
+    lengths = rng.randint(1, S + 1, size=(B,)).astype(np.int32)
+    lengths[0] = S                                             # the batch is trimmed to its longest question (model.py:681-687)
+    lengths[1] = 1
+    q = rng.randint(1, V + 1, size=(B, S)).astype(np.int32)
+    q[np.arange(S)[None, :] >= lengths[:, None]] = 0           # padding id
+    keep_in, keep_q = (rc.encInputDropout, rc.qDropout) if train else (1.0, 1.0)
+    store = tf.reset_shim(values=params, seed=seed + 2, dtype=np.float64)
+    me = types.SimpleNamespace(dropouts={"encInput": keep_in, "question": keep_q, "stateInput": 1.0})
+    emb_init = params["qEmbeddings/emb"]
+    words, _ = ref_model.MACnet.qEmbeddingsOp(me, q, emb_init)
+    projFlag = (rc.encDim != rc.ctrlDim) or rc.encProj                                   # model.py:786
+    cntx, vecq = ref_model.MACnet.encoder(me, words, lengths, projFlag, projFlag, rc.ctrlDim)
+    created = {k: list(v.shape) for k, v in store.vars.items()}
+    assert created == {k: list(v[0]) for k, v in specs.items()}, (created, specs)
+    out = {"qIndices": q, "questionLengths": lengths, "questionWords": np.asarray(words),
+           "questionCntxWords": np.asarray(cntx), "vecQuestions": np.asarray(vecq)}
+    for i, u in enumerate(store.uniform_draws):
+        out["uniform_%03d" % i] = u.astype(np.float64)
+    meta = {"case": name, "train": train, "proj": proj, "keep_input": keep_in, "keep_question": keep_q,
+            "shape": {"B": B, "S": S, "V": V, "E": E, "encDim": enc_dim, "ctrlDim": ctrl}, "param_seed": seed,
+            "variables": created, "n_uniform": len(store.uniform_draws)}
+    out["meta_json"] = np.frombuffer(json.dumps(meta, sort_keys=True).encode(), dtype=np.uint8)
+    return out
+
+
 def main():
     outdir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(outdir, exist_ok=True)
@@ -247,6 +286,13 @@ def main():
         if only and name not in only:
             continue
         out = run_stem_case(name, train)
+        path = os.path.join(outdir, name + ".npz")
+        np.savez_compressed(path, **out)
+        print("%-22s %8.1f KB" % (name, os.path.getsize(path) / 1024.0))
+    for name, train, proj in (("encoder_eval", False, False), ("encoder_train", True, False), ("encoder_proj", False, True)):
+        if only and name not in only:
+            continue
+        out = run_encoder_case(name, train, proj)
         path = os.path.join(outdir, name + ".npz")
         np.savez_compressed(path, **out)
         print("%-22s %8.1f KB" % (name, os.path.getsize(path) / 1024.0))

@@ -13,6 +13,7 @@ restated here from their published definitions.
 Everything is an `np.ndarray` in `WORK_DTYPE` (float64 for golden generation).
 Nothing under `mac_network_b200/` may import this module.
 """
+import collections
 import contextlib
 import numpy as np
 
@@ -96,10 +97,16 @@ def get_variable(name, shape=None, initializer=None, dtype=None, **kw):
     full = "/".join(_store.scope + [name])
     if full in _store.vars:
         return _store.vars[full]
+    if shape is None and initializer is not None and not callable(initializer):
+        shape = np.shape(initializer)          # tf.get_variable(name, initializer=<tensor>): the shape is the tensor's
     shape = tuple(int(s) for s in (shape if shape is not None else ()))
     if full in _store.provided:
         val = _t(_store.provided[full], dtype=WORK_DTYPE)
         assert val.shape == shape, (full, val.shape, shape)
+    elif initializer is None:
+        val = _t(_xavier_uniform()(shape, _store.rng), dtype=WORK_DTYPE)   # TF default: glorot_uniform_initializer
+    elif not callable(initializer):
+        val = _t(np.array(initializer, dtype=WORK_DTYPE))
     else:
         val = _t(initializer(shape, _store.rng), dtype=WORK_DTYPE)
     _store.vars[full] = val
@@ -253,13 +260,111 @@ class _RNNCell(object):
     pass
 
 
+LSTMStateTuple = collections.namedtuple("LSTMStateTuple", ("c", "h"))
+
+
+class BasicLSTMCell(_RNNCell):
+    """tf.nn.rnn_cell.BasicLSTMCell as published in TF 1.x `rnn_cell_impl.py`: variables `basic_lstm_cell/kernel`
+    [input_depth + num_units, 4 * num_units] (default glorot-uniform initialiser) and `basic_lstm_cell/bias` (zeros);
+        gate_inputs = concat([inputs, h], 1) @ kernel + bias;   i, j, f, o = split(gate_inputs, 4, axis=1)
+        new_c = c * sigmoid(f + forget_bias) + sigmoid(i) * act(j);   new_h = act(new_c) * sigmoid(o)
+    forget_bias defaults to 1.0, the activation to tanh, state_is_tuple to True."""
+
+    def __init__(self, num_units, forget_bias=1.0, state_is_tuple=True, activation=None, reuse=None, name=None):
+        self._num_units = int(num_units)
+        self._forget_bias = float(forget_bias)
+        self._activation = activation or tanh
+        self._name = name or "basic_lstm_cell"
+
+    @property
+    def state_size(self):
+        return LSTMStateTuple(self._num_units, self._num_units)
+
+    @property
+    def output_size(self):
+        return self._num_units
+
+    def zero_state(self, batch_size, dtype):
+        z = np.zeros((int(batch_size), self._num_units), dtype=WORK_DTYPE)
+        return LSTMStateTuple(_t(z), _t(z.copy()))
+
+    def __call__(self, inputs, state):
+        c, h = state
+        n = self._num_units
+        with variable_scope(self._name):
+            kernel = get_variable("kernel", shape=(inputs.shape[1] + n, 4 * n))
+            bias = get_variable("bias", shape=(4 * n,), initializer=zeros_initializer())
+        gate_inputs = np.concatenate([np.asarray(inputs), np.asarray(h)], axis=1) @ kernel + bias
+        i, j, f, o = np.split(gate_inputs, 4, axis=1)
+        new_c = c * sigmoid(f + self._forget_bias) + sigmoid(i) * self._activation(j)
+        new_h = self._activation(new_c) * sigmoid(o)
+        return _t(new_h), LSTMStateTuple(_t(new_c), _t(new_h))
+
+
+def _unsupported_cell(kind):
+    class _Cell(_RNNCell):
+        def __init__(self, *a, **k):
+            raise NotImplementedError("%s is outside the restated slice (encType defaults to LSTM, config.py:262)" % kind)
+    return _Cell
+
+
 class _rnn_cell(object):
     RNNCell = _RNNCell
-    LSTMStateTuple = tuple
+    LSTMStateTuple = LSTMStateTuple
+    BasicLSTMCell = BasicLSTMCell
+    BasicRNNCell = _unsupported_cell("BasicRNNCell")      # named in ops.createCell's table (ops.py:762-768)
+    GRUCell = _unsupported_cell("GRUCell")
+    LSTMCell = _unsupported_cell("LSTMCell")
+
+
+def _reverse_sequence(x, lengths):
+    """tf.reverse_sequence(x, lengths, seq_axis=1, batch_axis=0): the first lengths[b] steps reversed, the rest kept."""
+    out = np.array(x, copy=True)
+    for b, n in enumerate(np.asarray(lengths).astype(np.int64)):
+        out[b, :n] = np.asarray(x)[b, :n][::-1]
+    return out
+
+
+def _dynamic_rnn(cell, inputs, sequence_length=None, initial_state=None, dtype=None, scope=None, **kw):
+    """tf.nn.dynamic_rnn (batch-major) as published: step t runs the cell on every row; rows with t >= sequence_length
+    emit a zero output and carry their state through unchanged (`_rnn_step` with `copy_through`); variables live in
+    `scope or "rnn"`."""
+    x = np.asarray(inputs)
+    B, T = x.shape[0], x.shape[1]
+    lengths = np.full((B,), T, np.int64) if sequence_length is None else np.asarray(sequence_length).astype(np.int64)
+    state = initial_state if initial_state is not None else cell.zero_state(B, dtype)
+    outs = []
+    with variable_scope(scope or "rnn"):
+        for t in range(T):
+            out, new_state = cell(_t(x[:, t]), state)
+            live = (t < lengths)[:, None]
+            outs.append(np.where(live, out, 0.0))
+            state = type(state)(*[_t(np.where(live, n_, o_)) for n_, o_ in zip(new_state, state)])
+    return _t(np.stack(outs, axis=1)), state
+
+
+def _bidirectional_dynamic_rnn(cell_fw, cell_bw, inputs, sequence_length=None, initial_state_fw=None,
+                               initial_state_bw=None, dtype=None, scope=None, **kw):
+    """tf.nn.bidirectional_dynamic_rnn as published: forward pass in scope "<bidirectional_rnn>/fw"; backward pass on
+    `reverse_sequence(inputs, sequence_length)` in "<bidirectional_rnn>/bw", its outputs reversed back the same way."""
+    with variable_scope(scope or "bidirectional_rnn"):
+        out_fw, st_fw = _dynamic_rnn(cell_fw, inputs, sequence_length, initial_state_fw, dtype, scope="fw")
+        x = np.asarray(inputs)
+        lengths = np.full((x.shape[0],), x.shape[1]) if sequence_length is None else sequence_length
+        out_bw, st_bw = _dynamic_rnn(cell_bw, _reverse_sequence(x, lengths), sequence_length, initial_state_bw, dtype,
+                                     scope="bw")
+        out_bw = _t(_reverse_sequence(out_bw, lengths))
+    return (out_fw, out_bw), (st_fw, st_bw)
 
 
 class _nn(object):
     rnn_cell = _rnn_cell
+    dynamic_rnn = staticmethod(_dynamic_rnn)
+    bidirectional_dynamic_rnn = staticmethod(_bidirectional_dynamic_rnn)
+
+    @staticmethod
+    def embedding_lookup(params, ids, **kw):
+        return _t(np.asarray(params)[np.asarray(ids).astype(np.int64)])
 
     @staticmethod
     def softmax(x, axis=-1):

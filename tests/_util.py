@@ -15,7 +15,7 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 def golden_cases():
     """Cell fixtures (the output-unit fixtures `output_*.npz` have their own tests)."""
     names = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
-    return [n for n in names if not n.startswith(("output_", "stem_"))]
+    return [n for n in names if not n.startswith(("output_", "stem_", "encoder_"))]
 
 
 def load_golden(case):
