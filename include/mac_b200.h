@@ -281,6 +281,10 @@ int mac_softmax_xent(const float* logits, const int32_t* labels, float* losses, 
  * --------------------------------------------------------------------------------------------- */
 int mac_im2col3x3(const float* x, void* cols, int cols_bf16, float keep, uint64_t seed, int site, int step,
                   int B, int H, int W, int C, mac_stream_t stream);
+/* backward of mac_im2col3x3 (fp32): dx[b,h,w,c] = keep-mask/keep * sum of the <= 9 entries of dcols that copied x[b,h,w,c]
+ * (gather form, fixed order: deterministic).  The weight / bias gradients of the convolution are mac_linear_bwd on cols. */
+int mac_col2im3x3(const float* dcols, float* dx, float keep, uint64_t seed, int site, int step, int B, int H, int W, int C,
+                  mac_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Question input unit ("next" row, model.py:208-220, 279-307; ops.py:859-905): embedding lookup + bi-LSTM encoder.

@@ -658,3 +658,54 @@ extern "C" int mac_im2col3x3(const float* x, void* cols, int cols_bf16, float ke
   MAC_LAUNCH_CHECK();
   return MAC_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ stem: col2im (backward)
+// dx[b,h,w,c] = keep-mask(b,h,w,c)/keep * sum_{kh,kw} dcols[(b, h-kh+1, w-kw+1), (kh*3+kw)*C + c]   (taps whose output
+// position falls outside the image contribute nothing).  Gather form: each thread owns four channels of one input pixel and
+// adds its <= 9 copies in a fixed order, so the gradient is deterministic and needs no atomics.
+namespace mac {
+__global__ void col2im3x3_kernel(const float* __restrict__ dcols, float* __restrict__ dx, uint32_t thresh, float scale,
+                                 uint64_t seed, int site, int step, int B, int H, int W, int C) {
+  const int c4n = C / 4;
+  const long long total = (long long)B * H * W * c4n;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c4 = (int)(i % c4n);
+  long long r = i / c4n;
+  const int w = (int)(r % W);
+  r /= W;
+  const int h = (int)(r % H), b = (int)(r / H);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const int ho = h - (tap / 3 - 1), wo = w - (tap % 3 - 1);      // the output pixel whose tap `tap` read (h, w)
+    if (ho >= 0 && ho < H && wo >= 0 && wo < W) {
+      const long long o = ((((long long)b * H + ho) * W + wo) * 9 + tap) * C + c4 * 4;
+      const float4 v = __ldg(reinterpret_cast<const float4*>(dcols + o));
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  }
+  const long long e = (((long long)b * H + h) * W + w) * C + c4 * 4;
+  if (thresh) {
+    const Philox4 p = philox4x32_10(seed, (uint64_t)e >> 2, (uint32_t)site, (uint32_t)step);
+    acc.x = ((p.x >> 8) >= thresh) ? acc.x * scale : 0.f;
+    acc.y = ((p.y >> 8) >= thresh) ? acc.y * scale : 0.f;
+    acc.z = ((p.z >> 8) >= thresh) ? acc.z * scale : 0.f;
+    acc.w = ((p.w >> 8) >= thresh) ? acc.w * scale : 0.f;
+  }
+  *reinterpret_cast<float4*>(dx + e) = acc;
+}
+}  // namespace mac
+
+extern "C" int mac_col2im3x3(const float* dcols, float* dx, float keep, uint64_t seed, int site, int step, int B, int H,
+                             int W, int C, mac_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!dcols || !dx || B <= 0 || H <= 0 || W <= 0 || C <= 0 || (C & 3) || !(keep > 0.f && keep <= 1.f)) return MAC_ERR_INVALID;
+  if (!mac_aligned16(dcols) || !mac_aligned16(dx)) return MAC_ERR_ALIGN;
+  const uint32_t thr = keep < 1.f ? keep_threshold(keep) : 0u;
+  const float scale = keep < 1.f ? 1.f / keep : 1.f;
+  const long long total = (long long)B * H * W * (C / 4);
+  col2im3x3_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(dcols, dx, thr, scale, seed, site, step, B, H, W, C);
+  MAC_LAUNCH_CHECK();
+  return MAC_OK;
+}

@@ -65,13 +65,19 @@ class Stem(object):
             return W, self._packed[i]
         return W, None
 
-    def forward(self, images, keep=1.0, step=0):
+    def forward(self, images, keep=1.0, step=0, save_for_backward=False):
         """images: [B,H,W,C] fp32 NHWC (the reference transposes the NCHW h5 features first, model.py:~770).
         Returns the knowledge base [B, H*W, outDim] fp32."""
         x = images
         B, H, Wd, C = x.shape
         act = ACT["ELU"] if self.relu == "ELU" else ACT["RELU_STD"]
+        if save_for_backward:
+            if self.prec != "fp32":
+                raise NotImplementedError("stem backward runs on the fp32 path (DESIGN.md section 9)")
+            self._saved = {"xs": [], "ys": [], "keep": float(keep), "step": int(step), "act": act}
         for i in range(self.nlayers):
+            if save_for_backward:
+                self._saved["xs"].append(x)
             W, Wt = self._weights(i)
             b = self.p["stem/cnnLayercnn_%d/biases/bias" % i]
             C = x.shape[3]
@@ -89,5 +95,46 @@ class Stem(object):
                 arr_k = (ctypes.c_int * 1)(K)
                 check(self.lib.mac_linear_fwd(arr_p, arr_k, arr_k, 1, ptr(W), ptr(b), 0.0, act, ptr(y), Nout, M, Nout, None,
                                               0, stream_ptr()), "mac_linear_fwd")
+            if save_for_backward:
+                self._saved["ys"].append(y)
             x = y.view(B, H, Wd, Nout)
         return x.view(B, H * Wd, x.shape[3])
+
+    def backward(self, d_kb, grads, need_d_images=False):
+        """Backward of `forward(save_for_backward=True)` (the reference differentiates the graph with TF autodiff,
+        model.py:626-636).  d_kb [B, H*W, outDim]; accumulates (+=) into `grads` (dict TF-name -> tensor shaped like the
+        parameter).  Per layer, last to first:  dZ = dY * act'(Y);  dKernel += cols^T @ dZ, dBias += colsum(dZ)
+        (`mac_linear_bwd` on the re-generated patch matrix);  dcols = dZ @ Kernel^T;  dX = col2im(dcols) * dropout mask.
+        The gradient w.r.t. the images (and with it layer 0's largest GEMM) is skipped unless asked for."""
+        sv = getattr(self, "_saved", None)
+        if sv is None:
+            raise RuntimeError("forward(save_for_backward=True) must run first")
+        B, H, Wd, _ = sv["xs"][0].shape
+        M = B * H * Wd
+        dy = d_kb.contiguous().view(M, -1)
+        dx = None
+        for i in reversed(range(self.nlayers)):
+            x, y = sv["xs"][i], sv["ys"][i]
+            C, Nout = x.shape[3], y.shape[1]
+            K = 9 * C
+            W, _ = self._weights(i)
+            dz = torch.empty_like(y)
+            check(self.lib.mac_activation_bwd(ptr(y), ptr(dy), sv["act"], ptr(dz), dz.numel(), stream_ptr()), "mac_activation_bwd")
+            cols = torch.empty((M, K), dtype=torch.float32, device=self.device)
+            check(self.lib.mac_im2col3x3(ptr(x), ptr(cols), 0, sv["keep"], self.seed, SITE_STEM + i, sv["step"], B, H, Wd, C,
+                                         stream_ptr()), "mac_im2col3x3")
+            need_dx = need_d_images or i > 0
+            dcols = torch.empty((M, K), dtype=torch.float32, device=self.device) if need_dx else None
+            Wt = W.t().contiguous() if need_dx else None
+            one = lambda v, t=ctypes.c_int: (t * 1)(v)
+            check(self.lib.mac_linear_bwd(one(cols.data_ptr(), ctypes.c_void_p), one(K), one(K), 1, ptr(Wt), ptr(dz), Nout,
+                                          one(None if dcols is None else dcols.data_ptr(), ctypes.c_void_p), one(K), one(0),
+                                          ptr(grads["stem/cnnLayercnn_%d/kernels/kernel" % i]),
+                                          ptr(grads["stem/cnnLayercnn_%d/biases/bias" % i]), M, Nout, None, 0, stream_ptr()),
+                  "mac_linear_bwd")
+            if need_dx:
+                dx = torch.empty_like(x)
+                check(self.lib.mac_col2im3x3(ptr(dcols), ptr(dx), sv["keep"], self.seed, SITE_STEM + i, sv["step"], B, H, Wd,
+                                             C, stream_ptr()), "mac_col2im3x3")
+                dy = dx.view(M, C)
+        return dx if need_d_images else None
