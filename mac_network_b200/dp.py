@@ -35,9 +35,13 @@ def allreduce_sum_(bucket, group=None):
 
 class DPTrainer(object):
     def __init__(self, cfg, netLength, param_values=None, seed=0, rank=0, world=1, lr=1e-4, clip=8.0, ema_decay=0.999,
-                 beta1=0.9, beta2=0.999, eps=1e-8, dropouts=None, device="cuda", classifier=None, output_dropout=0.85):
+                 beta1=0.9, beta2=0.999, eps=1e-8, dropouts=None, device="cuda", classifier=None, output_dropout=0.85,
+                 encoder=None, stem=None, enc_dropouts=(0.85, 0.92), stem_dropout=0.82):
         """`classifier=(answerWordsNum, outClassifierDims)` adds the reference's output unit + answer loss
-        (model.py:512-528, 547-576, 593-596); its variables join the same flat buckets."""
+        (model.py:512-528, 547-576, 593-596); `encoder=(vocabulary rows, wrdEmbDim)` the question input unit
+        (model.py:208-220, 279-307) and `stem=(imageInDim, stemNumLayers)` the image stem (model.py:165-204), with the
+        reference's training dropouts (config.py:202-206).  All variables join the same flat buckets, so the one
+        all-reduce and the one fused optimizer pass cover the whole model (`train_step_full`)."""
         from .mac_cell import MACParams, views_of
         from .params import init_params
         self.cfg, self.L, self.rank, self.world = cfg, netLength, rank, world
@@ -47,15 +51,40 @@ class DPTrainer(object):
             from .output_unit import output_specs, init_output_params
             extra_specs = output_specs(cfg.ctrlDim, cfg.memDim, list(classifier[1]), classifier[0])
             extra_values = init_output_params(extra_specs, seed=seed + 17, bias_scale=0.0)
-            if param_values is None:
-                param_values = init_params(cfg, netLength, seed=seed)
+        self._enc_specs = self._stem_specs = None
+        if encoder is not None or stem is not None:
+            import collections
+            if classifier is None or encoder is None or stem is None:
+                raise ValueError("the full model needs classifier=, encoder= and stem= together")
+            from .encoder import encoder_specs, init_encoder_params
+            from .stem import stem_specs, init_stem_params
+            self._enc_specs = encoder_specs(encoder[0], encoder[1], cfg.ctrlDim, ctrl_dim=cfg.ctrlDim, bi=True)
+            self._stem_specs = stem_specs(stem[0], cfg.memDim, num_layers=stem[1])
+            extra_specs = collections.OrderedDict(list(extra_specs.items()) + list(self._enc_specs.items())
+                                                  + list(self._stem_specs.items()))
+            extra_values = dict(extra_values)
+            extra_values.update(init_encoder_params(self._enc_specs, seed=seed + 19, bias_scale=0.0))   # TF: zero biases
+            extra_values.update(init_stem_params(self._stem_specs, seed=seed + 23, bias_scale=0.0))
+        if extra_specs is not None and param_values is None:
+            param_values = init_params(cfg, netLength, seed=seed)
         self.params = MACParams(cfg, netLength, values=param_values, seed=seed, device=device, extra_specs=extra_specs,
                                 extra_values=extra_values)   # replicated
         self.out = None
         if classifier is not None:
             from .output_unit import OutputUnit
-            self.out = OutputUnit({k: self.params.t[k] for k in extra_specs}, relu=cfg.relu, keep=output_dropout, seed=seed)
+            self.out = OutputUnit({k: self.params.t[k] for k in extra_specs
+                                   if k.startswith(("outputUnit/", "classifier/"))}, relu=cfg.relu, keep=output_dropout,
+                                  seed=seed)
             self._views_of = views_of
+        self.enc = self.stem = None
+        if self._enc_specs is not None:
+            from .encoder import QuestionEncoder
+            from .stem import Stem
+            self.enc = QuestionEncoder({k: self.params.t[k] for k in self._enc_specs}, keep_input=enc_dropouts[0],
+                                       keep_question=enc_dropouts[1], seed=seed)
+            self.stem = Stem({k: self.params.t[k] for k in self._stem_specs}, relu=cfg.relu, prec="fp32", seed=seed)
+            self.stem_dropout = float(stem_dropout)
+            self._full_bufs = {}
         n = self.params.numel
         z = lambda: torch.zeros(n, dtype=torch.float32, device=self.params.device)
         self.bucket, self.adam_m, self.adam_v = z(), z(), z()
@@ -123,6 +152,56 @@ class DPTrainer(object):
         mac_backward(cell, None, d_mem, bucket=self.bucket, zero_bucket=False, d_vecq=d_q)
         self.apply()
         self.out.invalidate()
+        return logits, losses
+
+    def full_forward_backward(self, key, data, global_batch):
+        """The reference's whole training graph (`MACnet.build`, model.py:774-821) on the local shard, gradients into the
+        flat bucket (not yet reduced):  embeddings + bi-LSTM encoder -> stem -> netLength MAC steps -> output unit ->
+        classifier -> mean softmax-CE over the GLOBAL batch, then the hand-written backward of each in reverse order.
+        `data`: questions int32 [B,S] (0 = padding), questionLengths int32 [B], images fp32 [B,H,W,C] (NHWC: the
+        reference transposes its NCHW feed first, model.py:68), answers int32 [B].  Returns (logits, per-sample losses)."""
+        from .autograd import mac_backward
+        from .mac_cell import mac_network
+        if self.enc is None:
+            raise RuntimeError("construct the trainer with classifier=, encoder= and stem=")
+        seed = (self.base_seed * 1000003 + self.step_id * 7919 + self.rank * 104729 + 1) & 0x7FFFFFFFFFFFFFFF
+        self.enc.seed = self.stem.seed = self.out.seed = seed
+        words, cntx, vecq = self.enc.forward(data["questions"], data["questionLengths"], step=self.step_id,
+                                             save_for_backward=True)
+        kb = self.stem.forward(data["images"], keep=self.stem_dropout, step=self.step_id, save_for_backward=True)
+        # the cell captures its inputs at construction (mac_cell.py:59-79): persistent buffers, refreshed per step
+        bufs = self._full_bufs.get(key)
+        if bufs is None:
+            bufs = {"vecQuestions": torch.empty_like(vecq), "questionWords": torch.empty_like(words),
+                    "questionCntxWords": torch.empty_like(cntx), "knowledgeBase": torch.empty_like(kb),
+                    "questionLengths": torch.empty_like(data["questionLengths"], dtype=torch.int32)}
+            self._full_bufs[key] = bufs
+        for name, src in (("vecQuestions", vecq), ("questionWords", words), ("questionCntxWords", cntx),
+                          ("knowledgeBase", kb), ("questionLengths", data["questionLengths"])):
+            bufs[name].copy_(src)
+        cell = self.cell_for(key, bufs)
+        cell._rw.clear()
+        cell.seed = seed
+        control, memory = mac_network(cell, self.L)
+        self.bucket.zero_()
+        gviews = self._views_of(self.bucket, self.params.specs, self.params.offsets)
+        logits, losses, _ = self.out.forward(memory, bufs["vecQuestions"], data["answers"], step=self.step_id,
+                                             loss_scale=1.0 / float(global_batch))
+        d_mem, d_q = torch.zeros_like(memory), torch.zeros_like(memory)
+        self.out.backward(gviews, d_mem, d_q)
+        g = mac_backward(cell, None, d_mem, bucket=self.bucket, zero_bucket=False, d_vecq=d_q)
+        self.stem.backward(g["knowledgeBase"], gviews)
+        if not self.cfg.controlContextual:
+            raise NotImplementedError("the raw-word control inputs (controlContextual off) need wrdEmbDim == ctrlDim")
+        self.enc.backward(g["questionCntxWords"], g["vecQuestions"], gviews)
+        return logits, losses
+
+    def train_step_full(self, key, data, global_batch):
+        """One data-parallel step of the whole model: `full_forward_backward` -> all-reduce -> clip / Adam / EMA."""
+        logits, losses = self.full_forward_backward(key, data, global_batch)
+        self.apply()
+        self.out.invalidate()
+        self.stem._packed.clear()
         return logits, losses
 
     def train_step(self, key, batch, t_control, t_memory, global_batch):

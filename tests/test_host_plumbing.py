@@ -1,0 +1,81 @@
+"""Host-side plumbing of the GPU-only paths on a box without a GPU: the encoder / stem / output unit / full-model trainer
+run against a dry-run library (tests/_mocklib.py) that validates every C-ABI call against the prototype table.  Numerics
+are the business of the `-m gpu` tests; this catches marshalling mistakes (arity, pointer kinds, buffer shapes, call order)."""
+import numpy as np
+import pytest
+import torch
+
+from tests import _mocklib
+
+
+def _params(specs_values):
+    return {k: torch.from_numpy(np.ascontiguousarray(v, dtype=np.float32)) for k, v in specs_values.items()}
+
+
+def test_encoder_host_calls(monkeypatch):
+    mock = _mocklib.install(monkeypatch)
+    from mac_network_b200.encoder import QuestionEncoder, encoder_specs, init_encoder_params
+    for proj, keeps in ((False, (1.0, 1.0)), (True, (0.85, 0.92))):
+        pv = init_encoder_params(encoder_specs(11, 12, 16, ctrl_dim=20 if proj else 16, proj=proj), seed=1)
+        p = _params(pv)
+        enc = QuestionEncoder(p, keep_input=keeps[0], keep_question=keeps[1], seed=3)
+        q = torch.randint(0, 12, (5, 7), dtype=torch.int32)
+        lens = torch.randint(1, 8, (5,), dtype=torch.int32)
+        mock.calls.clear()
+        # the mock cannot tell a CPU tensor from a CUDA one; bypass the device check only
+        monkeypatch.setattr(torch.Tensor, "is_cuda", property(lambda self: True), raising=False)
+        words, cntx, vecq = enc.forward(q, lens, step=2, save_for_backward=True)
+        assert words.shape == (5, 7, 12) and cntx.shape == (5, 7, 20 if proj else 16) and vecq.shape == (5, 20 if proj else 16)
+        assert mock.calls.count("mac_lstm_fwd") == 1 and mock.calls.count("mac_embed_fwd") == 1
+        assert mock.calls.count("mac_linear_fwd") == (4 if proj else 2)
+        grads = {k: torch.zeros_like(v) for k, v in p.items()}
+        enc.backward(torch.zeros_like(cntx), torch.zeros_like(vecq), grads)
+        assert mock.calls.count("mac_lstm_bwd") == 1 and mock.calls.count("mac_embed_bwd") == 1
+        assert mock.calls.count("mac_linear_bwd") == (4 if proj else 2)
+        assert len(enc.dropout_uniforms(5, 7, step=2)) == (2 if keeps[0] < 1 else 0)
+
+
+def test_stem_host_calls(monkeypatch):
+    mock = _mocklib.install(monkeypatch)
+    from mac_network_b200.stem import Stem, stem_specs, init_stem_params
+    p = _params(init_stem_params(stem_specs(8, 16), seed=1))
+    st = Stem(p, relu="ELU", prec="fp32", seed=1)
+    kb = st.forward(torch.zeros(2, 5, 4, 8), keep=0.82, step=1, save_for_backward=True)
+    assert kb.shape == (2, 20, 16)
+    grads = {k: torch.zeros_like(v) for k, v in p.items()}
+    assert st.backward(torch.zeros_like(kb), grads) is None
+    assert mock.calls.count("mac_col2im3x3") == 1            # layer 1 only: the image gradient is not needed
+    d_img = st.backward(torch.zeros_like(kb), grads, need_d_images=True)
+    assert d_img.shape == (2, 5, 4, 8)
+    assert mock.calls.count("mac_linear_bwd") == 4
+
+
+def test_full_model_trainer_host_calls(monkeypatch):
+    """DPTrainer.train_step_full up to (and after) the cell, with the already GPU-validated cell stubbed out."""
+    mock = _mocklib.install(monkeypatch)
+    monkeypatch.setattr(torch.Tensor, "is_cuda", property(lambda self: True), raising=False)
+    from mac_network_b200 import autograd, dp, mac_cell
+    from mac_network_b200.config import MACConfig
+    B, S, V, E, d, H, W, C, A, L = 4, 6, 9, 12, 32, 3, 3, 8, 5, 2
+    cfg = MACConfig.args("args", netLength=L, memDim=d, ctrlDim=d, attDim=d)
+    tr = dp.DPTrainer(cfg, L, seed=1, device="cpu", classifier=(A, [16]), encoder=(V, E), stem=(C, 2))
+    names = list(tr.params.specs)
+    assert any(n.startswith("encoder/") for n in names) and any(n.startswith("stem/") for n in names)
+    assert any(n.startswith("MACnetwork/") for n in names) and "qEmbeddings/emb" in names
+
+    class _Cell(object):
+        _rw = {}
+        seed = 0
+    monkeypatch.setattr(tr, "cell_for", lambda key, batch: _Cell())
+    monkeypatch.setattr(mac_cell, "mac_network", lambda cell, L_: (torch.zeros(B, d), torch.zeros(B, d)))
+    monkeypatch.setattr(autograd, "mac_backward", lambda cell, dc, dm, bucket=None, zero_bucket=True, d_vecq=None: {
+        "knowledgeBase": torch.zeros(B, H * W, d), "questionCntxWords": torch.zeros(B, S, d), "vecQuestions": torch.zeros(B, d)})
+    data = {"questions": torch.randint(0, V + 1, (B, S), dtype=torch.int32),
+            "questionLengths": torch.randint(1, S + 1, (B,), dtype=torch.int32),
+            "images": torch.zeros(B, H, W, C), "answers": torch.randint(0, A, (B,), dtype=torch.int32)}
+    logits, losses = tr.train_step_full("k", data, global_batch=B)
+    assert logits.shape == (B, A) and losses.shape == (B,)
+    for name in ("mac_embed_fwd", "mac_lstm_fwd", "mac_im2col3x3", "mac_softmax_xent", "mac_lstm_bwd", "mac_embed_bwd",
+                 "mac_col2im3x3", "mac_clip_adam_ema_step"):
+        assert name in mock.calls, name
+    assert tr.step_id == 1
