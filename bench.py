@@ -453,11 +453,17 @@ def run_ours(args):
         t_dev, t_e2e = float(tt[0]), float(tt[1])
 
     # ---- data-parallel training arm (all ranks take part: it contains the path's one collective)
-    train = None
+    train = train_full = None
     if not args.skip_train:
         del pipe
         torch.cuda.empty_cache()
         train = train_arm(min(args.steps, 4), 2, rank, world, dist)
+        try:                                 # 'next' rows: never let them break the headline line
+            train_full = train_full_arm(min(args.steps, 3), 2, rank, world, dist)
+        except Exception as exc:
+            train_full = {"error": repr(exc)[:300]}
+            if dist is not None:             # a rank-local failure must not leave the others in a collective
+                raise
 
     if rank == 0:
         roofs = kernel_rooflines(shape, args.prec, pk)
@@ -497,6 +503,7 @@ def run_ours(args):
             "peaks": pk,
             "cpu_baseline": cpu,
             "train": train,
+            "train_full": train_full,
         }
         print(json.dumps(line))
     if dist is not None:
@@ -542,6 +549,55 @@ def train_arm(steps, warmup, rank, world, dist):
                    "backward + all-reduce of the flat gradient bucket (%.1f MB, NCCL) + fused clip/Adam/EMA; B=%d per GPU, "
                    "fp32 path" % (tr.params.numel * 4 / 1e6, B),
            "replicas_in_sync": sync}
+    del tr
+    torch.cuda.empty_cache()
+    return out
+
+
+def train_full_arm(steps, warmup, rank, world, dist):
+    """DP-training step of the WHOLE reference model (SURVEY section 8(f) rows 1-3 around the cell): embeddings + bi-LSTM
+    question encoder -> 2 x conv3x3 stem on [B,14,14,1024] features -> 12 MAC steps -> output unit -> classifier -> loss,
+    hand-written backward of each, ONE all-reduce of the flat bucket, fused clip/Adam/EMA.  fp32 path."""
+    from mac_network_b200.dp import DPTrainer
+    shape = SHAPES[WORKLOAD]
+    B, S, N, d, L = shape
+    V, E, A, C = 90, 300, 28, 1024                     # CLEVR: ~90 question words, 300-d embeddings, 28 answers, ResNet-101 conv4
+    cfg = MACConfig.args("args", netLength=L)
+    tr = DPTrainer(cfg, L, seed=7, rank=rank, world=world, classifier=(A, [512]), encoder=(V, E), stem=(C, 2))
+    rng = np.random.RandomState(31 + rank)
+    lengths = rng.randint(S // 2, S + 1, size=(B,)).astype(np.int32)
+    lengths[0] = S
+    q = rng.randint(1, V + 1, size=(B, S)).astype(np.int32)
+    q[np.arange(S)[None, :] >= lengths[:, None]] = 0
+    data = {"questions": torch.from_numpy(q).cuda(), "questionLengths": torch.from_numpy(lengths).cuda(),
+            "images": torch.relu(torch.randn(B, 14, 14, C, device="cuda")),
+            "answers": torch.from_numpy(rng.randint(0, A, size=(B,)).astype(np.int32)).cuda()}
+    from mac_network_b200 import _lib
+    for _ in range(warmup):
+        tr.train_step_full(0, data, B * world)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    n0 = _lib.load().mac_b200_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        _, losses = tr.train_step_full(0, data, B * world)
+    e1.record()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = e0.elapsed_time(e1) * 1e-3
+    launches = _lib.load().mac_b200_launch_count() - n0
+    if dist is not None:
+        tt = torch.tensor([t], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t = float(tt[0])
+    out = {"value": steps * L * world / t, "unit": UNIT, "ms_per_step": t / steps * 1e3, "steps": steps,
+           "loss_last": float(losses.mean().item()), "gpu_launches": int(launches),
+           "what": "whole-model DP training step: embedding + bi-LSTM encoder (S=%d, 2x256) + stem (2 x conv3x3, 1024->512->512 on "
+                   "14x14) + %d MAC steps + output unit/classifier/softmax-CE, hand-written backward, all-reduce of %.1f MB, fused "
+                   "clip/Adam/EMA; B=%d per GPU, fp32 path, reference training dropouts" % (S, L, tr.params.numel * 4 / 1e6, B)}
     del tr
     torch.cuda.empty_cache()
     return out

@@ -79,3 +79,31 @@ def test_full_model_trainer_host_calls(monkeypatch):
                  "mac_col2im3x3", "mac_clip_adam_ema_step"):
         assert name in mock.calls, name
     assert tr.step_id == 1
+
+
+@pytest.mark.parametrize("flags,prec,train", [("args", "fp32", False), ("args", "bf16", False), ("gqa", "fp32", False),
+                                              ("gqa", "bf16", False), ("args1", "fp32", True), ("gqa", "fp32", True)])
+def test_cell_host_calls(monkeypatch, flags, prec, train):
+    """The cell's forward (hoisted eval form, per-step train form) and backward sweep against the prototype table."""
+    mock = _mocklib.install(monkeypatch)
+    monkeypatch.setattr(torch.Tensor, "is_cuda", property(lambda self: True), raising=False)
+    from mac_network_b200.autograd import mac_backward
+    from mac_network_b200.config import MACConfig
+    from mac_network_b200.mac_cell import MACCell, MACParams, mac_network
+    from mac_network_b200.synthetic import make_inputs
+    B, S, N, d, L = 4, 6, 9, 64, 3
+    cfg = MACConfig.args(flags, netLength=L, memDim=d, ctrlDim=d, attDim=d)
+    params = MACParams(cfg, L, seed=1, device="cpu")
+    x = {k: torch.from_numpy(v) for k, v in make_inputs(B, S, N, d, seed=2).items()}
+    keeps = (0.85, 0.85, 1.0) if train else (1.0, 1.0, 1.0)
+    cell = MACCell(x["vecQuestions"], x["questionWords"], x["questionCntxWords"], x["questionLengths"], x["knowledgeBase"],
+                   keeps[0], keeps[1], keeps[2], B, train, config=cfg, params=params, prec=prec, save_for_backward=train)
+    control, memory = mac_network(cell, L)
+    assert control.shape == (B, d) and memory.shape == (B, d)
+    assert len(cell.attentions["kb"]) == L and len(cell.attentions["question"]) == L
+    if train:
+        g = mac_backward(cell, torch.zeros(B, d), torch.zeros(B, d))
+        assert g["knowledgeBase"].shape == (B, N, d) and g["vecQuestions"].shape == (B, d)
+        assert mock.calls.count("mac_read_bwd") == L
+    else:
+        assert mock.calls.count("mac_read_invariant") == 1 and mock.calls.count("mac_read_fwd_inv") == L
