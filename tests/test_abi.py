@@ -41,3 +41,37 @@ def test_no_product_import_of_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt, f
+
+
+def test_argument_errors_are_status_codes_not_crashes():
+    """Error behaviour of the boundary (include/mac_b200.h): bad sizes / null pointers / misalignment / short workspaces come
+    back as negative MAC_ERR_* codes before any CUDA call is made, so this runs without a GPU."""
+    import ctypes
+    lib = _lib.load()
+    INVALID, ALIGN, WORKSPACE = -1, -2, -4
+    buf = (ctypes.c_float * 4096)()
+    p = ctypes.addressof(buf)
+    p = (p + 15) & ~15                                     # 16-byte aligned fake "device" pointer (never dereferenced)
+    arr_p = (ctypes.c_void_p * 1)(p)
+    one = lambda v: (ctypes.c_int * 1)(v)
+    # ops.linear: K not a multiple of 4, null weight, misaligned output
+    assert lib.mac_linear_fwd(arr_p, one(6), one(8), 1, p, None, 0.0, 0, p, 8, 4, 8, None, 0, None) == INVALID
+    assert lib.mac_linear_fwd(arr_p, one(8), one(8), 1, None, None, 0.0, 0, p, 8, 4, 8, None, 0, None) == INVALID
+    assert lib.mac_linear_fwd(arr_p, one(8), one(8), 1, p, None, 0.0, 0, p + 4, 8, 4, 8, None, 0, None) == ALIGN
+    # dropout keep outside (0, 1]
+    assert lib.mac_dropout_fwd(p, 0.0, 1, 0, 0, p, 16, None) == INVALID
+    assert lib.mac_dropout_fwd(p, 1.5, 1, 0, 0, p, 16, None) == INVALID
+    # question input unit: embedding width not a multiple of 4; hidden size not a multiple of 8; short workspace
+    assert lib.mac_embed_fwd(p, p, 1.0, 1, 0, 0, None, p, 2, 3, 5, 6, None) == INVALID
+    assert lib.mac_lstm_fwd(p, p, p, p, p, 1.0, p, None, None, None, None, p, 1 << 20, 2, 3, 12, 2, None) == INVALID
+    assert lib.mac_lstm_fwd(p, None, p, None, p, 1.0, p, None, None, None, None, p, 1 << 20, 2, 3, 8, 2, None) == INVALID
+    assert lib.mac_lstm_fwd(p, p, p, p, p, 1.0, p, None, None, None, None, p, 16, 2, 3, 8, 2, None) == WORKSPACE
+    assert lib.mac_lstm_workspace_bytes(64, 256, 2) >= 3 * 2 * 64 * 256 * 4
+    # stem: channel count not a multiple of 4
+    assert lib.mac_im2col3x3(p, p, 0, 1.0, 1, 0, 0, 1, 3, 3, 6, None) == INVALID
+    assert lib.mac_col2im3x3(p, p, 1.0, 1, 0, 0, 1, 3, 3, 6, None) == INVALID
+    assert lib.mac_col2im3x3(p, p + 4, 1.0, 1, 0, 0, 1, 3, 3, 8, None) == ALIGN
+    # loss / attention helpers
+    assert lib.mac_kb_attend_bwd(None, p, p, p, p, None, None, 2, 3, 8, None) == INVALID
+    for code in (INVALID, ALIGN, -3, WORKSPACE, -5):
+        assert len(lib.mac_b200_strerror(code)) > 3
