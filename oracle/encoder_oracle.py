@@ -19,6 +19,7 @@ reversed copies there, per-row index arithmetic here)."""
 import numpy as np
 
 ENC = "encoder/birnnLayer/bidirectional_rnn/"
+ENC_UNI = "encoder/rnnLayer/rnn/"      # ops.fwRNNLayer (`encBi` off, ops.py:797-829): scope "rnnLayer", dynamic_rnn's "rnn"
 
 
 def _sigmoid(x):
@@ -68,16 +69,18 @@ def encoder_forward(params, qIndices, questionLengths, keep_input=1.0, keep_ques
 
     words = embed(p["qEmbeddings/emb"], qIndices, dtype)
     x = dropout(words, keep_input)                                                      # ops.py:877
-    fw, h_fw = lstm_direction(x, questionLengths, p[ENC + "fw/basic_lstm_cell/kernel"], p[ENC + "fw/basic_lstm_cell/bias"], False)
-    bw, h_bw = lstm_direction(x, questionLengths, p[ENC + "bw/basic_lstm_cell/kernel"], p[ENC + "bw/basic_lstm_cell/bias"], True)
-    cntx = np.concatenate([fw, bw], axis=-1)                                            # ops.py:897
-    vecq = np.concatenate([h_fw, h_bw], axis=-1)                                        # ops.py:898
+    if ENC_UNI + "basic_lstm_cell/kernel" in p:                                          # ops.py:797-829, hDim = encDim
+        cntx, vecq = lstm_direction(x, questionLengths, p[ENC_UNI + "basic_lstm_cell/kernel"],
+                                    p[ENC_UNI + "basic_lstm_cell/bias"], False)
+    else:
+        fw, h_fw = lstm_direction(x, questionLengths, p[ENC + "fw/basic_lstm_cell/kernel"], p[ENC + "fw/basic_lstm_cell/bias"], False)
+        bw, h_bw = lstm_direction(x, questionLengths, p[ENC + "bw/basic_lstm_cell/kernel"], p[ENC + "bw/basic_lstm_cell/bias"], True)
+        cntx = np.concatenate([fw, bw], axis=-1)                                        # ops.py:897
+        vecq = np.concatenate([h_fw, h_bw], axis=-1)                                    # ops.py:898
     vecq = dropout(vecq, keep_question)                                                 # model.py:297
     if proj:                                                                            # model.py:300-305
         cntx = cntx @ p["encoder/linearLayerprojCW/weights/weight"] + p["encoder/linearLayerprojCW/biases/bias"]
         vecq = vecq @ p["encoder/linearLayerprojQ/weights/weight"] + p["encoder/linearLayerprojQ/biases/bias"]
-        if proj_q_act == "TANH":
-            vecq = np.tanh(vecq)
-        elif proj_q_act == "RELU":
-            raise NotImplementedError("encProjQAct=RELU goes through config.relu and a nested _2 layer; not restated")
+        if proj_q_act != "NON":          # ops.linear would add the activation AND a nested "projQ_2" layer (ops.py:325-328)
+            raise NotImplementedError("encProjQAct != NON (config.py:270 default) is not restated")
     return {"questionWords": words, "questionCntxWords": cntx, "vecQuestions": vecq}

@@ -27,8 +27,10 @@ def run(params_np, qIndices, lengths, keep_input=1.0, keep_question=1.0, uniform
     x = dropout(table[idx], keep_input)
     outs, finals = [], []
     ar = torch.arange(B)
-    for name, reverse in (("fw", False), ("bw", True)):
-        K, bias = p[ENC + name + "/basic_lstm_cell/kernel"], p[ENC + name + "/basic_lstm_cell/bias"]
+    uni = "encoder/rnnLayer/rnn/basic_lstm_cell/kernel" in p
+    for name, reverse in ((("", False),) if uni else (("fw", False), ("bw", True))):
+        sc = "encoder/rnnLayer/rnn/" if uni else ENC + name + "/"
+        K, bias = p[sc + "basic_lstm_cell/kernel"], p[sc + "basic_lstm_cell/bias"]
         hd = K.shape[1] // 4
         c = torch.zeros(B, hd, dtype=torch.float64)
         h = torch.zeros(B, hd, dtype=torch.float64)

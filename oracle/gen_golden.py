@@ -230,18 +230,21 @@ def run_stem_case(name, train, seed=23, B=2, H=5, W=4, cin=8, cout=8):
     return out
 
 
-def run_encoder_case(name, train, proj, seed=29, B=5, S=7, V=11, E=12, enc_dim=16):
+def run_encoder_case(name, train, proj, seed=29, B=5, S=7, V=11, E=12, enc_dim=16, bi=True):
     """Question input unit through the reference's own `MACnet.qEmbeddingsOp` + `MACnet.encoder` (model.py:208-220, 279-307)
     -> `ops.RNNLayer` / `biRNNLayer` (ops.py:859-952) on the shim's BasicLSTMCell / bidirectional_dynamic_rnn."""
     import types
     ref_model = importlib.import_module("model")
     ctrl = enc_dim + 4 if proj else enc_dim
-    set_reference_config("@args.txt", ["--encDim", str(enc_dim), "--wrdEmbDim", str(E)] + (["--encProj"] if proj else []),
-                         dict(L=1, d=ctrl), train)
+    extra = ["--encDim", str(enc_dim), "--wrdEmbDim", str(E)] + (["--encProj"] if proj else [])
+    if bi:
+        set_reference_config("@args.txt", extra, dict(L=1, d=ctrl), train)
+    else:                                                      # args.txt without --encBi: ops.fwRNNLayer (ops.py:797-829)
+        set_reference_config(None, [f for f in ARGS] + extra, dict(L=1, d=ctrl), train)
     rc = _ref_config.config
-    assert rc.encBi and rc.encType == "LSTM" and rc.encNumLayers == 1 and not rc.encVariationalDropout
+    assert rc.encBi == bi and rc.encType == "LSTM" and rc.encNumLayers == 1 and not rc.encVariationalDropout
     from mac_network_b200.encoder import encoder_specs, init_encoder_params
-    specs = encoder_specs(V, E, enc_dim, ctrl_dim=ctrl, bi=True, proj=proj)
+    specs = encoder_specs(V, E, enc_dim, ctrl_dim=ctrl, bi=bi, proj=proj)
     params = init_encoder_params(specs, seed=seed, dtype=np.float64)
     rng = np.random.RandomState(seed + 1)
     lengths = rng.randint(1, S + 1, size=(B,)).astype(np.int32)
@@ -262,7 +265,7 @@ def run_encoder_case(name, train, proj, seed=29, B=5, S=7, V=11, E=12, enc_dim=1
            "questionCntxWords": np.asarray(cntx), "vecQuestions": np.asarray(vecq)}
     for i, u in enumerate(store.uniform_draws):
         out["uniform_%03d" % i] = u.astype(np.float64)
-    meta = {"case": name, "train": train, "proj": proj, "keep_input": keep_in, "keep_question": keep_q,
+    meta = {"case": name, "train": train, "proj": proj, "bi": bi, "keep_input": keep_in, "keep_question": keep_q,
             "shape": {"B": B, "S": S, "V": V, "E": E, "encDim": enc_dim, "ctrlDim": ctrl}, "param_seed": seed,
             "variables": created, "n_uniform": len(store.uniform_draws)}
     out["meta_json"] = np.frombuffer(json.dumps(meta, sort_keys=True).encode(), dtype=np.uint8)
@@ -289,10 +292,11 @@ def main():
         path = os.path.join(outdir, name + ".npz")
         np.savez_compressed(path, **out)
         print("%-22s %8.1f KB" % (name, os.path.getsize(path) / 1024.0))
-    for name, train, proj in (("encoder_eval", False, False), ("encoder_train", True, False), ("encoder_proj", False, True)):
+    for name, train, proj, bi in (("encoder_eval", False, False, True), ("encoder_train", True, False, True),
+                                  ("encoder_proj", False, True, True), ("encoder_uni", False, False, False)):
         if only and name not in only:
             continue
-        out = run_encoder_case(name, train, proj)
+        out = run_encoder_case(name, train, proj, bi=bi)
         path = os.path.join(outdir, name + ".npz")
         np.savez_compressed(path, **out)
         print("%-22s %8.1f KB" % (name, os.path.getsize(path) / 1024.0))

@@ -80,3 +80,52 @@ def test_adam_reference_matches_textbook():
     p, m, v, ema, norm = adam_reference(np.ones(4), np.full(4, 10.0), np.zeros(4), np.zeros(4), np.ones(4), step=1)
     assert np.isclose(norm, 20.0)                      # clipped to 8: g = 4
     assert np.allclose(p, 1.0 - 1e-4, atol=1e-9)       # first Adam step moves by ~lr
+
+
+# ---- the question input unit's variables in the same flat bucket (SURVEY section 8(f) rank 3 under section 8(e)'s sharding)
+def _enc_problem():
+    from mac_network_b200.encoder import encoder_specs, init_encoder_params
+    B, S, V, E, D = 6, 5, 9, 8, 16
+    specs = encoder_specs(V, E, D)
+    params = init_encoder_params(specs, seed=71, dtype=np.float64)
+    rng = np.random.RandomState(72)
+    lengths = rng.randint(1, S + 1, size=(B,)).astype(np.int32)
+    lengths[0] = S
+    q = rng.randint(1, V + 1, size=(B, S)).astype(np.int32)
+    q[np.arange(S)[None, :] >= lengths[:, None]] = 0
+    return specs, params, q, lengths, rng.standard_normal((B, S, D)), rng.standard_normal((B, D))
+
+
+def _enc_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mac_network_b200.dp import shard_rows, allreduce_sum_
+    from mac_network_b200.mac_cell import flat_layout
+    from oracle import encoder_torch_autograd as EA
+    specs, params, q, lengths, dc, dq = _enc_problem()
+    B = q.shape[0]
+    rows = shard_rows(B, rank, world)
+    _, _, g = EA.run(params, q[rows], lengths[rows], d_cntx=dc[rows] / B, d_vecq=dq[rows] / B)
+    bucket = torch.from_numpy(_flat(g, specs, flat_layout(specs)))
+    allreduce_sum_(bucket)
+    np.save(os.path.join(out_dir, "enc_rank%d.npy" % rank), bucket.numpy())
+    dist.destroy_process_group()
+
+
+def test_two_rank_encoder_gradient_equals_single_process(tmp_path):
+    """Rows of different lengths land on different ranks; the summed bucket (embedding rows included: a word used on both
+    ranks gets both contributions) equals the gradient of the global-mean loss on the whole batch."""
+    from mac_network_b200.mac_cell import flat_layout
+    from oracle import encoder_torch_autograd as EA
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_enc_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    specs, params, q, lengths, dc, dq = _enc_problem()
+    B = q.shape[0]
+    _, _, g = EA.run(params, q, lengths, d_cntx=dc / B, d_vecq=dq / B)
+    full = _flat(g, specs, flat_layout(specs))
+    r0 = np.load(os.path.join(str(tmp_path), "enc_rank0.npy"))
+    r1 = np.load(os.path.join(str(tmp_path), "enc_rank1.npy"))
+    assert np.array_equal(r0, r1)
+    assert np.max(np.abs(r0 - full)) < 1e-12 * max(1.0, np.max(np.abs(full)))

@@ -12,7 +12,7 @@ from oracle import encoder_torch_autograd
 from mac_network_b200.encoder import encoder_specs, init_encoder_params
 from tests._util import GOLDEN_DIR, max_rel
 
-CASES = ["encoder_eval", "encoder_train", "encoder_proj"]
+CASES = ["encoder_eval", "encoder_train", "encoder_proj", "encoder_uni"]
 
 
 def _load(case):
@@ -23,7 +23,7 @@ def _load(case):
 
 def _rebuild(meta):
     sh = meta["shape"]
-    specs = encoder_specs(sh["V"], sh["E"], sh["encDim"], ctrl_dim=sh["ctrlDim"], bi=True, proj=meta["proj"])
+    specs = encoder_specs(sh["V"], sh["E"], sh["encDim"], ctrl_dim=sh["ctrlDim"], bi=meta.get("bi", True), proj=meta["proj"])
     return specs, init_encoder_params(specs, seed=meta["param_seed"], dtype=np.float64)
 
 
