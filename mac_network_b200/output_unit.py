@@ -54,6 +54,10 @@ class OutputUnit(object):
         self.p = params
         self.relu, self.keep, self.seed = relu, float(keep), int(seed)
         self.nfc = len([k for k in params if k.startswith("classifier/linearLayerfc_") and k.endswith("weights/weight")])
+        for k, v in params.items():
+            if k.endswith("weights/weight") and (v.shape[0] % 4 or v.shape[1] % 4):
+                raise ValueError("%s is %s: the fp32 GEMM needs every dimension to be a multiple of 4 (pad the answer "
+                                 "vocabulary / classifier width)" % (k, tuple(v.shape)))
         dev = next(iter(params.values())).device
         self.lws_bytes = 4096 + 32 * 64 * 2048 * 4
         self.lws = torch.zeros(self.lws_bytes, dtype=torch.uint8, device=dev)

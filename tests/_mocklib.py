@@ -8,6 +8,25 @@ import ctypes
 from mac_network_b200 import _lib
 
 
+def _semantic_checks(name, args):
+    """The cheap argument rules the C entry points enforce before launching (units.cu / backward.cu / encoder.cu), so that a
+    host-side shape that the library would reject with MAC_ERR_INVALID / MAC_ERR_ALIGN fails here too."""
+    if name == "mac_linear_fwd":
+        k_segs, ldx, nseg, ldy, n_out = args[1], args[2], args[3], args[9], args[11]
+        assert 1 <= nseg <= 4 and n_out % 4 == 0 and ldy % 4 == 0, (name, nseg, n_out, ldy)
+        assert all(k_segs[i] % 4 == 0 and ldx[i] % 4 == 0 for i in range(nseg)), (name, list(k_segs), list(ldx))
+    elif name == "mac_linear_bwd":
+        k_segs, nseg, n_out = args[1], args[3], args[13]
+        assert 1 <= nseg <= 4 and n_out % 4 == 0 and all(k_segs[i] % 4 == 0 for i in range(nseg)), (name, n_out)
+    elif name == "mac_embed_fwd":
+        assert args[11] % 4 == 0, (name, "E", args[11])
+    elif name in ("mac_lstm_fwd", "mac_lstm_bwd"):
+        h, ndir = args[-3], args[-2]
+        assert h % 8 == 0 and ndir in (1, 2), (name, h, ndir)
+    elif name in ("mac_im2col3x3", "mac_col2im3x3"):
+        assert args[-2] % 4 == 0, (name, "C", args[-2])
+
+
 class MockLib(object):
     def __init__(self):
         self.calls = []
@@ -36,6 +55,7 @@ class MockLib(object):
                     assert isinstance(a, (int, float)), (where, type(a))
                 else:
                     raise AssertionError("unhandled prototype type %r in %s" % (t, name))
+            _semantic_checks(name, args)
             self.calls.append(name)
             if restype is ctypes.c_size_t:
                 return 1 << 16

@@ -45,7 +45,7 @@ def test_full_model_forward_and_gradient(flags):
     import torch
     from mac_network_b200.config import MACConfig
     from mac_network_b200.dp import DPTrainer
-    B, S, V, E, d, H, W, C, A, L = 6, 7, 13, 12, 64, 4, 3, 16, 9, 3
+    B, S, V, E, d, H, W, C, A, L = 6, 7, 13, 12, 64, 4, 3, 16, 12, 3      # A % 4 == 0 (mac_linear_fwd: n_out % 4)
     _, data = _make(B, S, V, E, d, H, W, C, A, L, seed=11)
     cfg = MACConfig.args(flags, netLength=L, memDim=d, ctrlDim=d, attDim=d)
     tr = DPTrainer(cfg, L, seed=5, dropouts=(1.0, 1.0, 1.0), classifier=(A, [32]), output_dropout=1.0, encoder=(V, E),
@@ -94,7 +94,7 @@ def test_full_model_train_steps_reduce_loss():
     and every sub-model's variables move."""
     import torch
     from mac_network_b200.dp import DPTrainer
-    B, S, V, E, d, H, W, C, A, L = 16, 9, 20, 20, 64, 5, 5, 32, 7, 3
+    B, S, V, E, d, H, W, C, A, L = 16, 9, 20, 20, 64, 5, 5, 32, 8, 3
     cfg, data = _make(B, S, V, E, d, H, W, C, A, L, seed=21)
     tr = DPTrainer(cfg, L, seed=6, lr=3e-3, classifier=(A, [32]), encoder=(V, E), stem=(C, 2))
     dev = {k: torch.from_numpy(v).cuda() for k, v in data.items()}

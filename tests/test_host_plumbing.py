@@ -56,7 +56,7 @@ def test_full_model_trainer_host_calls(monkeypatch):
     monkeypatch.setattr(torch.Tensor, "is_cuda", property(lambda self: True), raising=False)
     from mac_network_b200 import autograd, dp, mac_cell
     from mac_network_b200.config import MACConfig
-    B, S, V, E, d, H, W, C, A, L = 4, 6, 9, 12, 32, 3, 3, 8, 5, 2
+    B, S, V, E, d, H, W, C, A, L = 4, 6, 9, 12, 32, 3, 3, 8, 8, 2
     cfg = MACConfig.args("args", netLength=L, memDim=d, ctrlDim=d, attDim=d)
     tr = dp.DPTrainer(cfg, L, seed=1, device="cpu", classifier=(A, [16]), encoder=(V, E), stem=(C, 2))
     names = list(tr.params.specs)
