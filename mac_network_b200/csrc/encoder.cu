@@ -16,9 +16,12 @@
 // Backward (BPTT) mirrors it: lstm_step_bwd_kernel computes dh = dgates(step s+1) @ Wh^T for its unit chunk as the prologue
 // and the gate derivatives of step s as the epilogue; the parameter and input gradients of all steps are then two GEMMs per
 // direction over the [B*S, 4h] gate-gradient matrix (mac_linear_bwd on the segments [dropout(X), h_prev]).
+#include <cooperative_groups.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace mac {
+namespace cg = cooperative_groups;
 
 constexpr int LS_HC = 8;        // hidden units per CTA (x 4 gates = 32 weight columns)
 constexpr int LS_ROWS = 64;     // batch rows per CTA
@@ -167,6 +170,98 @@ __global__ void __launch_bounds__(LS_THREADS) lstm_step_kernel(const LstmFwdPara
     p.h_next[sidx] = hnew;
     if (p.vecq && p.s == p.S - 1) p.vecq[(size_t)b * W2 + dir * h + col] = hnew;
   }
+}
+
+// ------------------------------------------------------------------------------------------------ LSTM, persistent form
+// The whole recurrence of one (direction, 8 batch rows) in ONE launch by a thread-block cluster of 8 CTAs (h == 256).
+// CTA `rank` owns hidden units [32*rank, 32*rank + 32): its [256 x 128] slice of the recurrent weights is loaded into shared
+// memory ONCE (128 KB) and stays there for all S steps; the cell state lives in a register of the thread that owns
+// (row, unit); what the CTAs exchange per step is h: each CTA stages its [8 x 32] block and copies it with 16-byte stores
+// into the next-step h buffer of the seven other CTAs over distributed shared memory, then one cluster barrier (which is
+// also the release/acquire point for those remote stores).  Double-buffered h: a CTA can only run ahead into step s+1 after
+// every CTA has passed the barrier of step s, i.e. after all reads of the buffer it is about to overwrite.
+// Thread mapping: warp w owns units 4w..4w+3, lane = (unit & 3) + 4*row  ->  per k the warp reads 64 B of weights (broadcast
+// over the 8 rows) and 8 x 16 B of h (conflict-free with the +4 row pad): 5 shared-memory wavefronts per 16 FMAs per thread.
+constexpr int LP_CL = 8, LP_RB = 8, LP_THREADS = 256, LP_HU = 32, LP_H = LP_CL * LP_HU;
+
+static __global__ void __launch_bounds__(LP_THREADS) lstm_seq_kernel(const LstmFwdParams p) {
+  extern __shared__ __align__(16) float lp_smem[];
+  constexpr int h = LP_H, G = 4 * LP_H, hp = LP_H + 4;
+  float* wsl = lp_smem;                          // [h][LP_HU][4]   (k, unit, gate)
+  float* hbuf = lp_smem + h * LP_HU * 4;         // [2][LP_RB][hp]
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();    // cluster spans gridDim.x
+  const int dir = blockIdx.y, b_base = blockIdx.z * LP_RB;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ul = warp * 4 + (lane & 3), row = lane >> 2;
+  const int gu = rank * LP_HU + ul;              // hidden unit this thread owns
+  const int b = b_base + row;
+  const float* __restrict__ Wh = dir ? p.Wh[1] : p.Wh[0];
+  for (int e = tid; e < h * 32; e += LP_THREADS) {
+    const int q = e & 7, g = (e >> 3) & 3, k = e >> 5;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(Wh + (size_t)k * G + g * h + rank * LP_HU + q * 4));
+    float* dst = wsl + (k * LP_HU + q * 4) * 4 + g;
+    dst[0] = v.x; dst[4] = v.y; dst[8] = v.z; dst[12] = v.w;
+  }
+  for (int e = tid; e < 2 * LP_RB * hp; e += LP_THREADS) hbuf[e] = 0.f;     // cell.zero_state
+  cluster.sync();                                // every CTA's buffers are zeroed before any remote store can land
+  const bool valid = b < p.B;
+  const int len = valid ? p.lengths[b] : 0;
+  const int W2 = p.ndir * h;
+  const float* __restrict__ gxd = dir ? p.gx[1] : p.gx[0];
+  const size_t dbase = (size_t)dir * p.B * p.S;
+  float c = 0.f, hcur = 0.f;
+  for (int s = 0; s < p.S; ++s) {
+    const float* hb = hbuf + (s & 1) * (LP_RB * hp) + row * hp;
+    const bool live = s < len;
+    const int t = dir ? (len - 1 - s) : s;
+    const size_t rowi = live ? ((size_t)b * p.S + t) : 0;
+    float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
+    if (live) {                                  // issued before the product so the L2 latency hides under it
+      const float* gx = gxd + rowi * G + gu;
+      g0 = __ldg(gx); g1 = __ldg(gx + h); g2 = __ldg(gx + 2 * h); g3 = __ldg(gx + 3 * h);
+    }
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+    for (int k = 0; k < h; k += 4) {
+      const float4 x = *reinterpret_cast<const float4*>(hb + k);
+      const float4 w0 = *reinterpret_cast<const float4*>(wsl + ((k + 0) * LP_HU + ul) * 4);
+      const float4 w1 = *reinterpret_cast<const float4*>(wsl + ((k + 1) * LP_HU + ul) * 4);
+      const float4 w2 = *reinterpret_cast<const float4*>(wsl + ((k + 2) * LP_HU + ul) * 4);
+      const float4 w3 = *reinterpret_cast<const float4*>(wsl + ((k + 3) * LP_HU + ul) * 4);
+      a0 = fmaf(x.x, w0.x, a0); a1 = fmaf(x.x, w0.y, a1); a2 = fmaf(x.x, w0.z, a2); a3 = fmaf(x.x, w0.w, a3);
+      a0 = fmaf(x.y, w1.x, a0); a1 = fmaf(x.y, w1.y, a1); a2 = fmaf(x.y, w1.z, a2); a3 = fmaf(x.y, w1.w, a3);
+      a0 = fmaf(x.z, w2.x, a0); a1 = fmaf(x.z, w2.y, a1); a2 = fmaf(x.z, w2.z, a2); a3 = fmaf(x.z, w2.w, a3);
+      a0 = fmaf(x.w, w3.x, a0); a1 = fmaf(x.w, w3.y, a1); a2 = fmaf(x.w, w3.z, a2); a3 = fmaf(x.w, w3.w, a3);
+    }
+    float hnew = hcur;                           // dynamic_rnn: state carried through past the sequence end
+    if (live) {
+      const float gi = sigmoid_f(a0 + g0), gj = tanhf(a1 + g1);
+      const float gf = sigmoid_f(a2 + g2 + p.forget_bias), go = sigmoid_f(a3 + g3);
+      c = c * gf + gi * gj;
+      hnew = tanhf(c) * go;
+      p.out_seq[rowi * W2 + dir * h + gu] = hnew;
+      if (p.save_gates) {
+        float* sg = p.save_gates + (dbase + rowi) * G + gu;
+        sg[0] = gi; sg[h] = gj; sg[2 * h] = gf; sg[3 * h] = go;
+        p.save_c[(dbase + rowi) * h + gu] = c;
+        p.save_hprev[(dbase + rowi) * h + gu] = hcur;
+      }
+    }
+    hcur = hnew;
+    // exchange: stage the CTA's [8 x 32] block in its own next buffer, then 16-byte copies into the 7 peers
+    float* nb = hbuf + ((s + 1) & 1) * (LP_RB * hp);
+    nb[row * hp + gu] = hnew;
+    __syncthreads();
+    for (int e = tid; e < (LP_CL - 1) * LP_RB * (LP_HU / 4); e += LP_THREADS) {
+      const int q = e & 7, r = (e >> 3) & 7, z = e >> 6;                     // float4 q of row r -> peer z (skipping self)
+      const int peer = z + (z >= rank ? 1 : 0);
+      float* src = nb + r * hp + rank * LP_HU + q * 4;
+      *reinterpret_cast<float4*>(cluster.map_shared_rank(src, peer)) = *reinterpret_cast<const float4*>(src);
+    }
+    cluster.sync();
+  }
+  if (valid && p.vecq) p.vecq[(size_t)b * W2 + dir * h + gu] = hcur;
 }
 
 // ------------------------------------------------------------------------------------------------ LSTM step, backward
@@ -323,18 +418,40 @@ extern "C" int mac_lstm_fwd(const float* gx_fw, const float* gx_bw, const float*
   if (workspace_bytes < mac_lstm_workspace_bytes(B, h, ndir)) return MAC_ERR_WORKSPACE;
   const size_t smem = ((size_t)LS_ROWS * (h + 4) + (size_t)h * LS_HC * 4) * sizeof(float);
   if (smem > 227u * 1024u) return MAC_ERR_UNSUPPORTED;
-  MAC_CUDA_TRY(cudaFuncSetAttribute(lstm_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const size_t sb = (lstm_state_bytes(B, h, ndir) + 255) & ~(size_t)255;
   char* ws = reinterpret_cast<char*>(workspace);
-  MAC_CUDA_TRY(cudaMemsetAsync(ws, 0, 2 * sb, stream));                                  // c = h = 0 (cell.zero_state)
   MAC_CUDA_TRY(cudaMemsetAsync(out_seq, 0, (size_t)B * S * ndir * h * sizeof(float), stream));
   LstmFwdParams p{};
   p.gx[0] = gx_fw; p.gx[1] = gx_bw; p.Wh[0] = Wh_fw; p.Wh[1] = Wh_bw;
-  p.c = reinterpret_cast<float*>(ws);
-  float* hbuf[2] = {reinterpret_cast<float*>(ws + sb), reinterpret_cast<float*>(ws + 2 * sb)};
   p.lengths = lengths; p.forget_bias = forget_bias; p.out_seq = out_seq; p.vecq = vecq;
   p.save_gates = save_gates; p.save_c = save_c; p.save_hprev = save_hprev;
   p.B = B; p.S = S; p.h = h; p.ndir = ndir;
+  // h == 256 (encDim 512, the reference default): the whole recurrence in one cluster launch.  Opt-in (MAC_LSTM_PERSIST=1)
+  // until it has been profiled against the per-step form; both are parity-tested.
+  const char* env = getenv("MAC_LSTM_PERSIST");
+  if (h == LP_H && env && env[0] == '1') {
+    const size_t psmem = ((size_t)LP_H * LP_HU * 4 + (size_t)2 * LP_RB * (LP_H + 4)) * sizeof(float);
+    MAC_CUDA_TRY(cudaFuncSetAttribute(lstm_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(LP_CL, ndir, (B + LP_RB - 1) / LP_RB);
+    cfg.blockDim = dim3(LP_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = psmem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = LP_CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    MAC_CUDA_TRY(cudaLaunchKernelEx(&cfg, lstm_seq_kernel, p));
+    MAC_LAUNCH_CHECK();
+    return MAC_OK;
+  }
+  MAC_CUDA_TRY(cudaFuncSetAttribute(lstm_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MAC_CUDA_TRY(cudaMemsetAsync(ws, 0, 2 * sb, stream));                                  // c = h = 0 (cell.zero_state)
+  p.c = reinterpret_cast<float*>(ws);
+  float* hbuf[2] = {reinterpret_cast<float*>(ws + sb), reinterpret_cast<float*>(ws + 2 * sb)};
   const dim3 grid(h / LS_HC, ndir, (B + LS_ROWS - 1) / LS_ROWS);
   for (int s = 0; s < S; ++s) {
     p.s = s;
