@@ -65,7 +65,6 @@ for tile in ("128128", "128256", "256256"):
     configs.append(({"MAC_TC_TILE": tile}, "tile=" + tile))
 configs.append(({"MAC_TC_PAIR": "1"}, "pair=1"))
 configs.append(({"MAC_NO_FOLD_Y": "1"}, "no_fold_y"))
-configs.append(({"MAC_READ_QHOIST": "0"}, "qhoist=0 (note: static, read once)"))
 for env, name in configs:
     for k in ("MAC_TC_TILE", "MAC_TC_PAIR", "MAC_NO_FOLD_Y", "MAC_READ_QHOIST"):
         os.environ.pop(k, None)
