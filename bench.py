@@ -157,14 +157,14 @@ def cpu_reference(cfg, shape, params_np, budget_s=15.0, max_forwards=8):
 class Slot(object):
     """One resident batch + its cell + the captured CUDA graph of the netLength unroll."""
 
-    def __init__(self, cfg, params, shape, seed, prec, use_graph, host_inputs=None):
+    def __init__(self, cfg, params, shape, seed, prec, use_graph, host_inputs=None, fold_y=None):
         from mac_network_b200.mac_cell import MACCell, mac_network
         B, S, N, d, L = shape
         inp = host_inputs if host_inputs is not None else make_inputs(B, S, N, d, seed=seed)
         self.x = {k: torch.from_numpy(v).cuda() for k, v in inp.items()}
         x = self.x
         self.cell = MACCell(x["vecQuestions"], x["questionWords"], x["questionCntxWords"], x["questionLengths"],
-                            x["knowledgeBase"], 1.0, 1.0, 1.0, B, False, config=cfg, params=params, prec=prec)
+                            x["knowledgeBase"], 1.0, 1.0, 1.0, B, False, config=cfg, params=params, prec=prec, fold_y=fold_y)
         self.L = L
         self.graph = None
         self._net = mac_network
@@ -368,7 +368,9 @@ def run_ours(args):
     use_graph = not args.no_graph
 
     # ---- resident-input arm
-    slots = [Slot(cfg, params, shape, 1234 + 1000 * rank + s, args.prec, use_graph) for s in range(NSLOTS)]
+    nstreams = max(1, args.streams)
+    fold_y = (nstreams < 4) if args.fold_y < 0 else bool(args.fold_y)     # see MACCell.__init__: latency vs throughput form
+    slots = [Slot(cfg, params, shape, 1234 + 1000 * rank + s, args.prec, use_graph, fold_y=fold_y) for s in range(NSLOTS)]
     launches_per_pass = slots[0].launches
 
     def barrier():
@@ -378,7 +380,6 @@ def run_ours(args):
 
     # `--streams S`: S independent passes (different resident batches) in flight at once, each on its own stream.
     # A pass is one serial dependency chain whose small kernels leave most SMs idle; a second chain fills them.
-    nstreams = max(1, args.streams)
     side = [torch.cuda.Stream() for _ in range(nstreams - 1)]
     main_stream = torch.cuda.current_stream()
 
@@ -427,7 +428,7 @@ def run_ours(args):
         host.append({k: torch.from_numpy(v).pin_memory() for k, v in inp.items() if k != "questionWords"})
     del slots
     torch.cuda.empty_cache()
-    pipe = HostPipeline(cfg, params, shape, prec=args.prec, slots=ND, use_graph=use_graph,
+    pipe = HostPipeline(cfg, params, shape, prec=args.prec, slots=ND, use_graph=use_graph, fold_y=fold_y,
                         cast_threads=max(1, min(12, (usable_cpus() - 1) // max(1, world))))
     h2d_bytes, d2h_bytes = pipe.h2d_bytes, pipe.d2h_bytes
     e2e_host_cast, e2e_cast_threads, pipe_cast_ms = pipe.host_kb_bf16, pipe.cast_threads, pipe.cast_ms
@@ -484,7 +485,8 @@ def run_ours(args):
                        "step": "one netLength-step unroll over one batch (%d reasoning steps)" % L,
                        "l2": "timed passes rotate over %d resident batches (%.0f MB > 126 MB L2)"
                              % (NSLOTS, NSLOTS * (B * N * d + B * S * d) * 4 / 1e6),
-                       "cuda_graph": use_graph, "projections": args.prec, "concurrent_passes": nstreams, "parallelism": "dp%d (replicas, no "
+                       "cuda_graph": use_graph, "projections": args.prec, "concurrent_passes": nstreams,
+                       "write_unit_folded_with_next_projY": fold_y, "parallelism": "dp%d (replicas, no "
                        "data-path collective in inference)" % world},
             "sample_steps_per_sec": value * B,
             "e2e": {"value": args.steps * L * world / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
@@ -734,7 +736,8 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-train", action="store_true", help="skip the short DP-training arm of the default run")
     ap.add_argument("--mode", default="infer", choices=["infer", "train"])
-    ap.add_argument("--streams", type=int, default=4, help="independent passes in flight (each on its own stream)")
+    ap.add_argument("--streams", type=int, default=6, help="independent passes in flight (each on its own stream)")
+    ap.add_argument("--fold-y", type=int, default=-1, help="write unit folded with the next step's projY: 1/0, -1 = by --streams")
     ap.add_argument("--rooflines-only", action="store_true", help="only the per-kernel measurements (for ncu)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

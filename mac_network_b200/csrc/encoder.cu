@@ -426,10 +426,10 @@ extern "C" int mac_lstm_fwd(const float* gx_fw, const float* gx_bw, const float*
   p.lengths = lengths; p.forget_bias = forget_bias; p.out_seq = out_seq; p.vecq = vecq;
   p.save_gates = save_gates; p.save_c = save_c; p.save_hprev = save_hprev;
   p.B = B; p.S = S; p.h = h; p.ndir = ndir;
-  // h == 256 (encDim 512, the reference default): the whole recurrence in one cluster launch.  Opt-in (MAC_LSTM_PERSIST=1)
-  // until it has been profiled against the per-step form; both are parity-tested.
+  // h == 256 (encDim 512, the reference default): the whole recurrence in one cluster launch (703 vs 805 us for the encoder
+  // forward at B=64, S=40, profiles/r1/lstm_bench_r1.jsonl); MAC_LSTM_PERSIST=0 selects the per-step form.  Both parity-tested.
   const char* env = getenv("MAC_LSTM_PERSIST");
-  if (h == LP_H && env && env[0] == '1') {
+  if (h == LP_H && !(env && env[0] == '0')) {
     const size_t psmem = ((size_t)LP_H * LP_HU * 4 + (size_t)2 * LP_RB * (LP_H + 4)) * sizeof(float);
     MAC_CUDA_TRY(cudaFuncSetAttribute(lstm_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
     cudaLaunchConfig_t cfg{};

@@ -140,7 +140,7 @@ class MACCell(object):
 
     def __init__(self, vecQuestions, questionWords, questionCntxWords, questionLengths, knowledgeBase,
                  memoryDropout, readDropout, writeDropout, batchSize, train, reuse=None, *,
-                 config=None, params=None, prec="fp32", seed=0, save_for_backward=False):
+                 config=None, params=None, prec="fp32", seed=0, save_for_backward=False, fold_y=None):
         self.lib = _lib.load()
         self.cfg = config if config is not None else _defaults["config"]
         self.params = params if params is not None else _defaults["params"]
@@ -188,10 +188,13 @@ class MACCell(object):
         # eval-mode hoist of the step-invariant read projections (shared cells only; env MAC_NO_READ_HOIST=1 disables)
         self._read_hoist = (self._fused_read and not c.unsharedCells and not save_for_backward
                             and os.environ.get("MAC_NO_READ_HOIST", "0") != "1")
-        # plain write unit: its GEMM also produces the next step's memory projection (env MAC_NO_FOLD_Y=1 disables)
+        # plain write unit: its GEMM also produces the next step's memory projection.  It shortens the dependency chain of
+        # ONE pass (17.0k vs fewer reasoning-steps/s with a single pass in flight); with >= 4 independent passes in flight the
+        # two smaller GEMMs pack better (25.4k vs 24.2k at 6 passes, profiles/r1/sweep_r1.jsonl), so throughput callers pass
+        # fold_y=False.  fold_y=None: on unless env MAC_NO_FOLD_Y=1.
+        want_fold = (os.environ.get("MAC_NO_FOLD_Y", "0") != "1") if fold_y is None else bool(fold_y)
         self._fold_y = (self._read_hoist and self._fused_write and not (c.writeSelfAtt or c.writeGate)
-                        and not (c.writeDropout < 1.0 and float(writeDropout) < 1.0)
-                        and os.environ.get("MAC_NO_FOLD_Y", "0") != "1")
+                        and not (c.writeDropout < 1.0 and float(writeDropout) < 1.0) and want_fold)
         self._y_for = -1
         self.kb_bf16 = None
         self.save_for_backward = bool(save_for_backward)

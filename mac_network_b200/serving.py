@@ -30,7 +30,7 @@ def usable_cpus():
 
 
 class _Slot(object):
-    def __init__(self, cfg, params, shape, prec, host_kb_bf16, use_graph):
+    def __init__(self, cfg, params, shape, prec, host_kb_bf16, use_graph, fold_y=None):
         B, S, N, d, L = shape
         dev = torch.device("cuda", torch.cuda.current_device())
         self.stream = torch.cuda.Stream()
@@ -43,7 +43,7 @@ class _Slot(object):
         x = self.x
         # questionWords is unused with controlContextual (mac_cell.py:570); the cell takes the contextual words for both
         self.cell = MACCell(x["vecQuestions"], x["questionCntxWords"], x["questionCntxWords"], x["questionLengths"],
-                            x["knowledgeBase"], 1.0, 1.0, 1.0, B, False, config=cfg, params=params, prec=prec)
+                            x["knowledgeBase"], 1.0, 1.0, 1.0, B, False, config=cfg, params=params, prec=prec, fold_y=fold_y)
         self.L = L
         self.graph = None
         with torch.cuda.stream(self.stream):
@@ -69,7 +69,7 @@ class HostPipeline(object):
     ticket.  `result(ticket)` blocks until that batch is done and returns pinned host tensors (final control / memory
     state, per-step KB and question attention maps) that stay valid until the slot is reused `slots` submits later."""
 
-    def __init__(self, cfg, params, shape, prec="bf16", slots=4, use_graph=True, cast_threads=None):
+    def __init__(self, cfg, params, shape, prec="bf16", slots=4, use_graph=True, cast_threads=None, fold_y=None):
         self.lib = _lib.load()
         self.shape = shape
         self.prec = prec
@@ -87,7 +87,9 @@ class HostPipeline(object):
             saved_ms = shape[0] * shape[2] * shape[3] * 2 / 25e9 * 1e3
             if self.cast_ms > 0.8 * saved_ms:
                 self.host_kb_bf16 = False
-        self.slots = [_Slot(cfg, params, shape, prec, self.host_kb_bf16, use_graph) for _ in range(max(1, slots))]
+        if fold_y is None:
+            fold_y = slots < 4          # several batches in flight: the unfolded write + projY GEMMs pack better (mac_cell.py)
+        self.slots = [_Slot(cfg, params, shape, prec, self.host_kb_bf16, use_graph, fold_y) for _ in range(max(1, slots))]
         self._cast_for = None
         self._next = 0
         B, S, N, d, L = shape
