@@ -415,6 +415,9 @@ def run_ours(args):
     e1.record()
     barrier()
     t_dev = e0.elapsed_time(e1) * 1e-3
+    # the sampler stops HERE: polling nvidia-smi through the host-driven end-to-end region below costs it ~15 % (19.8k vs
+    # 23.5k reasoning-steps/s on the B200 box, profiles/r1/NOTES.md) -- the queries contend with the copy / launch calls
+    clocks = sampler.stop() if rank == 0 else None
 
     # ---- end-to-end arm: host (pinned) buffers; every pass does H2D of its batch, the netLength unroll, and D2H of the
     #      final state + attention maps.  ND device slots, each on its own stream, so the copies of one pass overlap the
@@ -445,7 +448,6 @@ def run_ours(args):
     e1.record()
     barrier()
     t_e2e = e0.elapsed_time(e1) * 1e-3
-    clocks = sampler.stop() if rank == 0 else None      # sampled across both timed regions (resident-input and end-to-end)
 
     # ---- max over ranks
     if dist is not None:
