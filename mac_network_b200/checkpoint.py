@@ -5,6 +5,10 @@
   TensorFlow's binary checkpoint format needs TensorFlow; the interchange container here is a flat `.npz` with those
   names as keys, which `tf.train.load_checkpoint(...)`-side tooling can produce with a ten-line script
   (`{n: reader.get_tensor(n) for n in reader.get_variable_to_shape_map()}`).
+* `save_training_state` / `load_training_state` add what `tf.train.Saver()` with no variable list also writes
+  (`main.py:163-165`): the Adam slots under TF's slot names `<variable>/Adam` (m) and `<variable>/Adam_1` (v), and the
+  `beta1_power` / `beta2_power` accumulators (= beta^step), so a run resumes with the same optimizer trajectory
+  (`main.py:185-201`: `--restore`).
 * `attention_maps` lays the per-step maps out the way `MACnet.buildPredsList` does (`model.py:693-710`):
   `attMap[key][step][sample]`, keys `kb` (length H*W, reshaped to the image grid by `visualization.py:121`),
   `question`, `self`, `gate`, so the reference's visualisation script can consume them unchanged.
@@ -34,13 +38,60 @@ def save_checkpoint(path, params, ema_flat=None):
     return list(out)
 
 
+ADAM_M, ADAM_V = "/Adam", "/Adam_1"          # tf.train.AdamOptimizer slot names
+
+
+def save_training_state(path, trainer):
+    """Weights + EMA shadows + Adam slots + step of a `DPTrainer` (replicated state: rank 0 writes it)."""
+    p = trainer.params
+    out = collections.OrderedDict()
+    flats = {"": p.flat, EMA_SUFFIX: trainer.ema, ADAM_M: trainer.adam_m, ADAM_V: trainer.adam_v}
+    host = {suffix: t.detach().cpu().numpy() for suffix, t in flats.items()}
+    for name, (shape, _) in p.specs.items():
+        n = int(np.prod(shape)) if shape else 1
+        o = p.offsets[name]
+        for suffix, buf in host.items():
+            out[MODEL_SCOPE + name + suffix] = buf[o:o + n].reshape(shape)
+    step = int(trainer.step_id)
+    out["beta1_power"] = np.float32(trainer.hp["b1"] ** step)
+    out["beta2_power"] = np.float32(trainer.hp["b2"] ** step)
+    out["mac_b200/step"] = np.int64(step)
+    np.savez(path, **out)
+    return list(out)
+
+
+def load_training_state(path, trainer):
+    """Restore what `save_training_state` wrote into an identically configured `DPTrainer` (every rank calls it)."""
+    import torch
+    z = np.load(path)
+    p = trainer.params
+    flats = {"": p.flat, EMA_SUFFIX: trainer.ema, ADAM_M: trainer.adam_m, ADAM_V: trainer.adam_v}
+    for suffix, dst in flats.items():
+        host = np.zeros(p.numel, dtype=np.float32)
+        for name, (shape, _) in p.specs.items():
+            key = MODEL_SCOPE + name + suffix
+            if key not in z.files:
+                raise KeyError("checkpoint %s has no %s" % (path, key))
+            v = np.asarray(z[key], dtype=np.float32)
+            if tuple(v.shape) != tuple(shape):
+                raise ValueError("%s: checkpoint shape %s, model shape %s" % (key, v.shape, tuple(shape)))
+            o = p.offsets[name]
+            host[o:o + v.size] = v.reshape(-1)
+        dst.copy_(torch.from_numpy(host))
+    trainer.step_id = int(z["mac_b200/step"])
+    p.touch()                      # packed / transposed / bf16 copies of the old weights are stale
+    if getattr(trainer, "out", None) is not None:
+        trainer.out.invalidate()
+    return trainer.step_id
+
+
 def load_checkpoint(path, use_ema=False):
     """Returns {variable name without the model scope: array}, ready for `MACParams(values=...)`.
     `use_ema=True` substitutes the EMA shadows, like the reference's evaluation swap (`main.py:717-719`)."""
     z = np.load(path)
     vals = {}
     for k in z.files:
-        if not k.startswith(MODEL_SCOPE) or k.endswith(EMA_SUFFIX):
+        if not k.startswith(MODEL_SCOPE) or k.endswith((EMA_SUFFIX, ADAM_M, ADAM_V)):
             continue
         name = k[len(MODEL_SCOPE):]
         src = k + EMA_SUFFIX if (use_ema and k + EMA_SUFFIX in z.files) else k

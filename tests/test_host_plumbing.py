@@ -107,3 +107,36 @@ def test_cell_host_calls(monkeypatch, flags, prec, train):
         assert mock.calls.count("mac_read_bwd") == L
     else:
         assert mock.calls.count("mac_read_invariant") == 1 and mock.calls.count("mac_read_fwd_inv") == L
+
+
+def test_training_state_roundtrip(monkeypatch, tmp_path):
+    """Checkpoint / resume of the whole-model trainer (weights, EMA shadows, Adam slots under TF's slot names, step)."""
+    _mocklib.install(monkeypatch)
+    from mac_network_b200 import dp
+    from mac_network_b200.checkpoint import load_checkpoint, load_training_state, save_training_state
+    from mac_network_b200.config import MACConfig
+    cfg = MACConfig.args("gqa", netLength=2, memDim=32, ctrlDim=32, attDim=32)
+    kw = dict(device="cpu", classifier=(8, [16]), encoder=(9, 12), stem=(8, 2))
+    a = dp.DPTrainer(cfg, 2, seed=1, **kw)
+    g = torch.Generator().manual_seed(0)
+    for t in (a.adam_m, a.adam_v, a.ema):
+        t.copy_(torch.randn(t.shape, generator=g))
+    a.step_id = 17
+    names = save_training_state(str(tmp_path / "state.npz"), a)
+    wname = "macModel/MACnetwork/MACCell/read/linearLayermemKbProj/weights/weight"
+    assert wname in names and wname + "/Adam" in names and wname + "/Adam_1" in names
+    assert wname + "/ExponentialMovingAverage" in names and "beta1_power" in names
+    assert "macModel/encoder/birnnLayer/bidirectional_rnn/fw/basic_lstm_cell/kernel/Adam" in names
+    b = dp.DPTrainer(cfg, 2, seed=2, **kw)                      # different initial weights
+    assert not torch.equal(a.params.flat, b.params.flat)
+    assert load_training_state(str(tmp_path / "state.npz"), b) == 17
+    for x, y in ((a.params.flat, b.params.flat), (a.adam_m, b.adam_m), (a.adam_v, b.adam_v), (a.ema, b.ema)):
+        for name, (shape, _) in a.params.specs.items():          # the 64-element padding between variables is not state
+            o, n = a.params.offsets[name], max(1, int(np.prod(shape)) if shape else 1)
+            assert torch.equal(x[o:o + n], y[o:o + n]), name
+    # the weights-only reader skips the optimizer slots and can swap in the EMA shadows (main.py:717-719)
+    vals = load_checkpoint(str(tmp_path / "state.npz"), use_ema=True)
+    assert set(vals) == set(a.params.specs)
+    k = "MACnetwork/MACCell/read/linearLayermemKbProj/weights/weight"
+    o = a.params.offsets[k]
+    assert np.array_equal(vals[k].reshape(-1), a.ema[o:o + vals[k].size].numpy())
