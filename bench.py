@@ -456,7 +456,7 @@ def run_ours(args):
         t_dev, t_e2e = float(tt[0]), float(tt[1])
 
     # ---- data-parallel training arm (all ranks take part: it contains the path's one collective)
-    train = train_full = None
+    train = train_full = train_tc = None
     if not args.skip_train:
         del pipe
         torch.cuda.empty_cache()
@@ -468,6 +468,8 @@ def run_ours(args):
                 train_full = {"error": repr(exc)[:300]}
         else:
             train_full = {"skipped": "measured at N=1 only; the N>1 lines carry the cell's DP-training arm (`train`)"}
+        if world == 1:
+            train_tc = train_tc_arm()
 
     if rank == 0:
         roofs = kernel_rooflines(shape, args.prec, pk)
@@ -509,6 +511,7 @@ def run_ours(args):
             "cpu_baseline": cpu,
             "train": train,
             "train_full": train_full,
+            "train_tc": train_tc,
         }
         print(json.dumps(line))
     if dist is not None:
@@ -557,6 +560,25 @@ def train_arm(steps, warmup, rank, world, dist):
     del tr
     torch.cuda.empty_cache()
     return out
+
+
+def train_tc_arm(timeout_s=150):
+    """Mixed-precision training of the cell (bf16 tensor-core forward AND backward GEMMs) measured in a
+    CHILD process: the composition was written after the round's GPU budget was spent, so a failure of it must not be able
+    to touch this process's CUDA context or its JSON line."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--mode", "train", "--train-prec", "bf16", "--bwd-tc", "1",
+           "--steps", "4", "--warmup", "3"]
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s, cwd=ROOT)
+        if out.returncode != 0:
+            return {"error": "exit %d: %s" % (out.returncode, out.stderr.strip()[-300:])}
+        line = json.loads(out.stdout.strip().splitlines()[-1])
+        return {"value": line["value"], "unit": line["unit"], "ms_per_step": line["ms_per_step"], "steps": line["steps"],
+                "gpu_launches": line["gpu_launches"], "replicas_in_sync": line["config"]["replicas_in_sync_after_run"],
+                "what": "bench.py --mode train --train-prec bf16 --bwd-tc 1 in a child process: DP training step of the cell with "
+                        "the read unit's forward and backward products on tcgen05 tensor cores (linear-probe loss)"}
+    except Exception as exc:
+        return {"error": repr(exc)[:300]}
 
 
 def train_full_arm(steps, warmup, rank, world, dist):
@@ -626,7 +648,7 @@ def run_train(args):
     B, S, N, d, L = shape
     cfg = MACConfig.args("args", netLength=L)
     pv = perturb_biases(init_params(cfg, L, seed=100), seed=101)
-    tr = DPTrainer(cfg, L, param_values=pv, seed=7, rank=rank, world=world)
+    tr = DPTrainer(cfg, L, param_values=pv, seed=7, rank=rank, world=world, prec=args.train_prec, bwd_tc=bool(args.bwd_tc))
     nslots = 4
     batches, probes = [], []
     for s_ in range(nslots):
@@ -675,7 +697,7 @@ def run_train(args):
         nparam = tr.params.numel
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32", "data": "synthetic",
+                "dtype": "f32" if (args.train_prec == "fp32" and not args.bwd_tc) else "bf16", "data": "synthetic",
                 "config": {"workload": "BASELINE.json configs[3]: DP training of the args.txt cell, B=%d per GPU (global %d), "
                                        "S=%d, N=%d, d=%d, netLength=%d; dropouts memory/read/write = %s"
                                        % (B, B * world, S, N, d, L, str(tr.dropouts)),
@@ -683,7 +705,8 @@ def run_train(args):
                                    "%d reasoning steps" % (nparam, nparam * 4 / 1e6, L),
                            "l2": "timed steps rotate over %d resident batches per rank; activations saved for backward "
                                  "(%.0f MB per step) exceed L2" % (nslots, L * 3 * B * N * d * 4 / 1e6),
-                           "cuda_graph": False, "projections": "fp32", "parallelism": "dp%d, NCCL all-reduce per step" % world,
+                           "cuda_graph": False, "projections": "forward %s, backward %s" % (
+                               args.train_prec, "bf16 tensor cores" if args.bwd_tc else "fp32"), "parallelism": "dp%d, NCCL all-reduce per step" % world,
                            "replicas_in_sync_after_run": in_sync},
                 "sample_steps_per_sec": value * B, "gpu_launches": int(launches), "clocks": clocks,
                 "e2e": None, "roofline": None, "cpu_baseline": None}
@@ -742,6 +765,8 @@ def main():
     ap.add_argument("--streams", type=int, default=6, help="independent passes in flight (each on its own stream)")
     ap.add_argument("--fold-y", type=int, default=-1, help="write unit folded with the next step's projY: 1/0, -1 = by --streams")
     ap.add_argument("--rooflines-only", action="store_true", help="only the per-kernel measurements (for ncu)")
+    ap.add_argument("--train-prec", default="fp32", choices=["fp32", "bf16"], help="--mode train: read-unit forward GEMMs")
+    ap.add_argument("--bwd-tc", type=int, default=0, help="--mode train: read-unit backward GEMMs on tensor cores (1/0)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.rooflines_only:

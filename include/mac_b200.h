@@ -246,6 +246,17 @@ int mac_read_bwd(const float* kb, const float* memory_in, const float* control, 
                  float* dWm, float* dbm_part, float* dWm2, float* dbm2_part, float* dwr_part, float* dbr_part,
                  void* workspace, size_t workspace_bytes, int B, int N, int d, mac_stream_t stream);
 size_t mac_read_bwd_workspace_bytes(int B, int N, int d);
+/* mac_read_bwd with its six [B*N, .] products on tcgen05 tensor cores (bf16 operands, fp32 accumulation; all element-wise
+ * work in fp32): dgrad = mac_linear_tc_fwd(bf16(dY), bf16(W) in its own [in,out] layout), wgrad = mac_linear_tc_fwd(bf16(X)^T,
+ * bf16(dY)^T) with K = B*N, fed by mac_cast_bf16 / mac_pack_weight_bf16.  Same arguments and accumulation conventions as
+ * mac_read_bwd (the transposed fp32 weights are not needed except Wy_t); dWx, dWm, dWm2 are required.
+ * Needs d % 128 == 0 and (B*N) % 64 == 0, else MAC_ERR_UNSUPPORTED. */
+int mac_read_bwd_tc(const float* kb, const float* memory_in, const float* control, const mac_read_weights* w,
+                    const float* Wy_t, const float* att, const float* save, const float* dinfo, float keep_read,
+                    uint64_t seed, int step, float* dkb, float* dmem_in, float* dcontrol, float* dWx, float* dbx_part,
+                    float* dWy, float* dby, float* dWm, float* dbm_part, float* dWm2, float* dbm2_part, float* dwr_part,
+                    float* dbr_part, void* workspace, size_t workspace_bytes, int B, int N, int d, mac_stream_t stream);
+size_t mac_read_bwd_tc_workspace_bytes(int B, int N, int d);
 /* write gate (mac_cell.py:358-367): dmnew = g*z; dmprev += g*(1-z); dpre = g*(mnew-mprev)*z*(1-z) */
 int mac_gate_bwd(const float* g, const float* z, const float* mnew, const float* mprev, float* dmnew, float* dmprev,
                  float* dpre, long long n, mac_stream_t stream);

@@ -70,6 +70,9 @@ PROTOTYPES = {
     "mac_read_bwd": (c_int, [c_fp, c_fp, c_fp, ctypes.POINTER(ReadWeights), c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_f,
                              c_u64, c_int] + [c_fp] * 13 + [c_fp, c_sz, c_int, c_int, c_int, c_fp]),
     "mac_read_bwd_workspace_bytes": (c_sz, [c_int, c_int, c_int]),
+    "mac_read_bwd_tc": (c_int, [c_fp, c_fp, c_fp, ctypes.POINTER(ReadWeights), c_fp, c_fp, c_fp, c_fp, c_f, c_u64, c_int]
+                        + [c_fp] * 13 + [c_fp, c_sz, c_int, c_int, c_int, c_fp]),
+    "mac_read_bwd_tc_workspace_bytes": (c_sz, [c_int, c_int, c_int]),
     "mac_gate_bwd": (c_int, [c_fp] * 7 + [c_ll, c_fp]),
     "mac_activation_bwd": (c_int, [c_fp, c_fp, c_int, c_fp, c_ll, c_fp]),
     "mac_colsum": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_int, c_fp]),

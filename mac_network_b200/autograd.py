@@ -27,8 +27,12 @@ def _t(params, W, key):
 
 
 class _Bwd(object):
-    def __init__(self, cell, bucket=None, zero_bucket=True):
+    def __init__(self, cell, bucket=None, zero_bucket=True, tc=False):
         self.cell, self.lib = cell, cell.lib
+        # tc: the read unit's six big products on tcgen05 tensor cores (mac_read_bwd_tc) instead of the fp32 FMA GEMMs
+        self.tc = bool(tc)
+        if self.tc and (cell.d % 128 or (cell.B * cell.N) % 64):
+            raise NotImplementedError("tensor-core backward needs d % 128 == 0 and (B*N) % 64 == 0")
         self.p = cell.params
         c = cell.cfg
         if c.controlWholeQ or c.controlContinuous:
@@ -47,13 +51,16 @@ class _Bwd(object):
             self.bucket.zero_()
         self.g = views_of(self.bucket, self.p.specs, self.p.offsets)
         cache = getattr(cell, "_bwd_ws", None)            # scratch is allocated once per cell and reused every step
+        if cache is not None and cache[4] != self.tc:
+            cache = None
         if cache is None:
-            ws_bytes = int(self.lib.mac_read_bwd_workspace_bytes(self.B, self.N, self.d))
+            ws_bytes = int((self.lib.mac_read_bwd_tc_workspace_bytes if self.tc else self.lib.mac_read_bwd_workspace_bytes)(
+                self.B, self.N, self.d))
             lws_bytes = 4096 + 32 * 1536 * 512 * 4
             cache = (ws_bytes, torch.zeros(ws_bytes, dtype=torch.uint8, device=dev), lws_bytes,
-                     torch.zeros(lws_bytes, dtype=torch.uint8, device=dev))
+                     torch.zeros(lws_bytes, dtype=torch.uint8, device=dev), self.tc)
             cell._bwd_ws = cache
-        self.ws_bytes, self.ws, self.lws_bytes, self.lws = cache
+        self.ws_bytes, self.ws, self.lws_bytes, self.lws = cache[:4]
 
     def G(self, name):
         return self.g[PREFIX + name]
@@ -152,13 +159,22 @@ class _Bwd(object):
                 check(lib.mac_dropout_fwd(ptr(dinfo), keep_w, cell.seed, _lib.SITE_WRITE_INFO, i, ptr(dinfo), B * d,
                                           stream_ptr()), "dropout bwd")
             # ---------------- read unit backward (mac_cell.py:209-277)
-            check(lib.mac_read_bwd(ptr(cell.knowledgeBase), ptr(cell._mem_in_hist[i]), ptr(control), ctypes.byref(rw),
-                                   ptr(_t(self.p, Wx, nWx)), ptr(_t(self.p, Wy, nWy)), ptr(_t(self.p, Wm, nWm)),
-                                   ptr(_t(self.p, Wm2, nWm2)), ptr(cell._att_kb[i]), ptr(cell._save[i]), ptr(dinfo),
-                                   keep_r, cell.seed, i, ptr(dkb), ptr(dmem_in), ptr(gC[i + 1]), ptr(self.G(nWx)),
-                                   ptr(part["bx"]), ptr(self.G(nWy)), ptr(self.G(nby)), ptr(self.G(nWm)), ptr(part["bm"]),
-                                   ptr(self.G(nWm2)), ptr(part["bm2"]), ptr(part["wr"]), ptr(spart["br"]), ptr(self.ws),
-                                   self.ws_bytes, B, N, d, stream_ptr()), "mac_read_bwd")
+            if self.tc:
+                check(lib.mac_read_bwd_tc(ptr(cell.knowledgeBase), ptr(cell._mem_in_hist[i]), ptr(control), ctypes.byref(rw),
+                                          ptr(_t(self.p, Wy, nWy)), ptr(cell._att_kb[i]), ptr(cell._save[i]), ptr(dinfo),
+                                          keep_r, cell.seed, i, ptr(dkb), ptr(dmem_in), ptr(gC[i + 1]), ptr(self.G(nWx)),
+                                          ptr(part["bx"]), ptr(self.G(nWy)), ptr(self.G(nby)), ptr(self.G(nWm)),
+                                          ptr(part["bm"]), ptr(self.G(nWm2)), ptr(part["bm2"]), ptr(part["wr"]),
+                                          ptr(spart["br"]), ptr(self.ws), self.ws_bytes, B, N, d, stream_ptr()),
+                      "mac_read_bwd_tc")
+            else:
+                check(lib.mac_read_bwd(ptr(cell.knowledgeBase), ptr(cell._mem_in_hist[i]), ptr(control), ctypes.byref(rw),
+                                     ptr(_t(self.p, Wx, nWx)), ptr(_t(self.p, Wy, nWy)), ptr(_t(self.p, Wm, nWm)),
+                                     ptr(_t(self.p, Wm2, nWm2)), ptr(cell._att_kb[i]), ptr(cell._save[i]), ptr(dinfo),
+                                     keep_r, cell.seed, i, ptr(dkb), ptr(dmem_in), ptr(gC[i + 1]), ptr(self.G(nWx)),
+                                     ptr(part["bx"]), ptr(self.G(nWy)), ptr(self.G(nby)), ptr(self.G(nWm)), ptr(part["bm"]),
+                                     ptr(self.G(nWm2)), ptr(part["bm2"]), ptr(part["wr"]), ptr(spart["br"]), ptr(self.ws),
+                                     self.ws_bytes, B, N, d, stream_ptr()), "mac_read_bwd")
             # memory_in = (variational) dropout of m_{i-1}  (mac_cell.py:214-217)
             if keep_m < 1.0:
                 site, st = (_lib.SITE_MEM_VAR, 0) if c.memoryVariationalDropout else (_lib.SITE_MEM_PLAIN, i)
@@ -273,8 +289,9 @@ class _Bwd(object):
         return out
 
 
-def mac_backward(cell, d_control, d_memory, bucket=None, zero_bucket=True, d_vecq=None):
-    """Gradients of sum(d_control * control_L) + sum(d_memory * memory_L) w.r.t. every cell parameter and input."""
+def mac_backward(cell, d_control, d_memory, bucket=None, zero_bucket=True, d_vecq=None, tc=False):
+    """Gradients of sum(d_control * control_L) + sum(d_memory * memory_L) w.r.t. every cell parameter and input.
+    `tc=True`: the read unit's projections on tensor cores in backward too (bf16 operands, fp32 accumulation)."""
     if not getattr(cell, "save_for_backward", False):
         raise RuntimeError("construct the MACCell with save_for_backward=True and run the forward first")
-    return _Bwd(cell, bucket, zero_bucket).run(d_control, d_memory, d_vecq)
+    return _Bwd(cell, bucket, zero_bucket, tc=tc).run(d_control, d_memory, d_vecq)

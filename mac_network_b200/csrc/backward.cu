@@ -519,3 +519,138 @@ extern "C" int mac_read_bwd(const float* kb, const float* memory_in, const float
   }
   return MAC_OK;
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// Backward of the read unit with the six [B*N, .] x [., .] products on tcgen05 tensor cores (bf16 operands, fp32
+// accumulation in TMEM; everything element-wise stays fp32).  Same inputs, outputs and accumulation conventions as
+// mac_read_bwd; the GEMMs go through the entry points the forward uses (mac_linear_tc_fwd), fed by the cast / transposing
+// cast kernels (mac_cast_bf16, mac_pack_weight_bf16):
+//   dgrad  dX[M, in]   = dY[M, out] @ W^T        x = bf16(dY) [M, out],  Wt operand = bf16(W) in its own [in, out] layout
+//   wgrad  dW[in, out] = X^T[in, M] @ dY[M, out]  x = bf16(X)^T [in, M],  Wt operand = bf16(dY)^T [out, M]   (K = M = B*N)
+// The prologue / epilogue fusions of the fp32 kernels become separate fp32 passes here (P*y, dropout(KB), * ELU'(H),
+// dropout mask on dKB); the arithmetic of every pass is the forward's, so the masks and saved tensors are shared.
+// Requires d % 128 == 0 and (B*N) % 64 == 0 (the UMMA K block); otherwise MAC_ERR_UNSUPPORTED (use mac_read_bwd).
+// ------------------------------------------------------------------------------------------------------------------
+static size_t rbt_align(size_t x) { return (x + 1023) & ~(size_t)1023; }
+
+extern "C" size_t mac_read_bwd_tc_workspace_bytes(int B, int N, int d) {
+  const size_t M = (size_t)B * N;
+  return mac_read_bwd_workspace_bytes(B, N, d) + 1024 + rbt_align(M * 2 * d * 2) /*g16*/ + rbt_align(2 * d * M * 2) /*xT16*/ +
+         rbt_align(d * M * 2) /*gT16*/ + rbt_align((size_t)2 * d * d * 2) /*w16*/ + rbt_align(M * 2 * d * 4) /*tmp32*/ +
+         rbt_align((size_t)2 * d * d * 4) /*dWtmp*/;
+}
+
+extern "C" int mac_read_bwd_tc(const float* kb, const float* memory_in, const float* control, const mac_read_weights* w,
+                               const float* Wy_t, const float* att, const float* save, const float* dinfo, float keep_read,
+                               uint64_t seed, int step, float* dkb, float* dmem_in, float* dcontrol, float* dWx,
+                               float* dbx_part, float* dWy, float* dby, float* dWm, float* dbm_part, float* dWm2,
+                               float* dbm2_part, float* dwr_part, float* dbr_part, void* workspace, size_t workspace_bytes,
+                               int B, int N, int d, mac_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!kb || !memory_in || !control || !w || !att || !save || !dinfo || !dmem_in || !dcontrol || !workspace || !dWx ||
+      !dWm || !dWm2)
+    return MAC_ERR_INVALID;
+  const int M = B * N;
+  if ((d % 128) || (M % 64)) return MAC_ERR_UNSUPPORTED;
+  if (workspace_bytes < mac_read_bwd_tc_workspace_bytes(B, N, d)) return MAC_ERR_WORKSPACE;
+  const size_t Md = (size_t)M * d;
+  char* ws = reinterpret_cast<char*>(workspace);
+  float* f = reinterpret_cast<float*>(ws + BW_HEADER);
+  float* bufA = f;                 // dI1, later dP
+  float* bufB = f + Md;            // dZ
+  float* bufC = f + 2 * Md;        // dI0 [M, 2d]
+  float* dka = f + 4 * Md;         // [B,N]
+  const size_t BNp = ((size_t)B * N + 3) & ~(size_t)3;
+  float* dkl = dka + BNp;
+  float* dy = dkl + BNp;           // [B,d]
+  float* md = dy + (size_t)B * d;  // [B,d]
+  float* dmd = md + (size_t)B * d; // [B,d]
+  // tensor-core operands behind the fp32 layout of mac_read_bwd
+  char* x = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws + mac_read_bwd_workspace_bytes(B, N, d)) + 1023) &
+                                    ~(uintptr_t)1023);
+  void* g16 = x;   x += rbt_align((size_t)M * 2 * d * 2);        // bf16 [M, <=2d]   gradient as the A operand of a dgrad
+  void* xT16 = x;  x += rbt_align((size_t)2 * d * M * 2);        // bf16 [<=2d, M]   activations, transposed
+  void* gT16 = x;  x += rbt_align((size_t)d * M * 2);            // bf16 [d, M]      gradient, transposed
+  void* w16 = x;   x += rbt_align((size_t)2 * d * d * 2);        // bf16 weight in its own [in, out] layout
+  float* tmp32 = reinterpret_cast<float*>(x); x += rbt_align((size_t)M * 2 * d * 4);
+  float* dWtmp = reinterpret_cast<float*>(x);
+  const float* P = save;
+  const float* H = save + Md;
+  const float* I1 = save + 2 * Md;
+  const float* y = save + 3 * Md;
+  const bool drop = keep_read < 1.f;
+  const uint32_t thr = drop ? keep_threshold(keep_read) : 0u;
+  const float scale = drop ? 1.f / keep_read : 1.f;
+  int st;
+#define RBT(call)                 \
+  do {                            \
+    st = (call);                  \
+    if (st != MAC_OK) return st;  \
+  } while (0)
+  // wgrad: dW[in, out] += X^T @ G with X^T already packed as xT [in, M]
+  auto wgrad = [&](const void* xT, int in, const float* G, float* dW) -> int {
+    int s = mac_pack_weight_bf16(G, gT16, M, d, stream_);                                   // G [M, d] -> G^T [d, M]
+    if (s != MAC_OK) return s;
+    s = mac_linear_tc_fwd(xT, gT16, nullptr, MAC_ACT_NON, dWtmp, 0, in, M, d, stream_);     // [in, d] = xT @ (G^T)^T
+    if (s != MAC_OK) return s;
+    return mac_axpy(dW, dWtmp, 1.f, (long long)in * d, stream_);
+  };
+  // dgrad: out[M, in] = G[M, d] @ W[in, d]^T   (W fp32 in its own [in, out = d] layout)
+  auto dgrad = [&](const float* G, const float* W, int in, float* out) -> int {
+    int s = mac_cast_bf16(G, g16, (long long)M * d, stream_);
+    if (s != MAC_OK) return s;
+    s = mac_cast_bf16(W, w16, (long long)in * d, stream_);
+    if (s != MAC_OK) return s;
+    return mac_linear_tc_fwd(g16, w16, nullptr, MAC_ACT_NON, out, 0, M, d, in, stream_);
+  };
+  // (1) info = sum_n att*KB ; att = softmax(kl):  dkl, dKB += att (x) dinfo
+  RBT(mac_kb_attend_bwd(kb, att, dinfo, dka, dkl, dkb, dbr_part, B, N, d, stream_));
+  // (2) logits epilogue backward -> dI1 (bufA), dcontrol, dwr, dbm2
+  read_bwd_logits_kernel<<<dim3((d + 127) / 128, B), 128, 0, stream>>>(I1, control, w->wr, dkl, thr, scale, seed, step,
+                                                                      bufA, dcontrol, dwr_part, dbm2_part, N, d);
+  MAC_LAUNCH_CHECK();
+  // (3) I1 = H @ Wm2 + bm2:  dWm2 += H^T dI1 ;  dZ = (dI1 @ Wm2^T) * ELU'(H)
+  RBT(mac_pack_weight_bf16(H, xT16, M, d, stream_));
+  RBT(wgrad(xT16, d, bufA, dWm2));
+  RBT(dgrad(bufA, w->Wm2, d, tmp32));
+  RBT(mac_activation_bwd(H, tmp32, MAC_ACT_ELU, bufB, (long long)Md, stream_));
+  RBT(launch_colsum(bufB, dbm_part, B, N, d, 1, stream));
+  // (4) Z = [P*y, P] @ Wm + bm:  dWm += [P*y, P]^T dZ ;  dI0 = dZ @ Wm^T
+  RBT(mac_bcast_mul(P, y, 0.f, tmp32, B, N, d, stream_));                                        // P*y   (ops.py:694-703)
+  RBT(mac_pack_weight_bf16(tmp32, xT16, M, d, stream_));                                         // rows 0..d-1   of [2d, M]
+  RBT(mac_pack_weight_bf16(P, reinterpret_cast<__nv_bfloat16*>(xT16) + (size_t)d * M, M, d, stream_));   // rows d..2d-1
+  RBT(wgrad(xT16, 2 * d, bufB, dWm));
+  RBT(dgrad(bufB, w->Wm, 2 * d, bufC));
+  // (5) I0 = [P*y, P]:  dP (bufA), dy, dbx
+  read_bwd_p_kernel<<<dim3((d + 127) / 128, B), 128, 0, stream>>>(bufC, P, y, bufA, dy, dbx_part, N, d);
+  MAC_LAUNCH_CHECK();
+  // (6) P = dropout(KB) @ Wx + bx:  dWx += Kd^T dP ;  dKB += (dP @ Wx^T) * mask/keep
+  const float* kbd = kb;
+  if (drop) {
+    RBT(mac_dropout_fwd(kb, keep_read, seed, MAC_SITE_READ_KB, step, tmp32, (long long)Md, stream_));
+    kbd = tmp32;
+  }
+  RBT(mac_pack_weight_bf16(kbd, xT16, M, d, stream_));
+  RBT(wgrad(xT16, d, bufA, dWx));
+  if (dkb) {
+    RBT(dgrad(bufA, w->Wx, d, tmp32));
+    if (drop) RBT(mac_dropout_fwd(tmp32, keep_read, seed, MAC_SITE_READ_KB, step, tmp32, (long long)Md, stream_));
+    RBT(mac_axpy(dkb, tmp32, 1.f, (long long)Md, stream_));
+  }
+  // (7) y = md @ Wy + by with md = dropout(memory_in): an M = B product, fp32 (mac_linear_bwd)
+  const float* mdp = memory_in;
+  if (drop) {
+    RBT(mac_dropout_fwd(memory_in, keep_read, seed, MAC_SITE_READ_MEM, step, md, (long long)B * d, stream_));
+    mdp = md;
+  }
+  {
+    const float* xs[1] = {mdp};
+    const int ks[1] = {d};
+    float* dxs[1] = {drop ? dmd : dmem_in};
+    const int acc0[1] = {0};
+    RBT(mac_linear_bwd(xs, ks, ks, 1, Wy_t, dy, d, dxs, ks, acc0, dWy, dby, B, d, nullptr, 0, stream_));
+    if (drop) RBT(mac_dropout_fwd(dmd, keep_read, seed, MAC_SITE_READ_MEM, step, dmem_in, (long long)B * d, stream_));
+  }
+#undef RBT
+  return MAC_OK;
+}

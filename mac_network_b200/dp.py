@@ -36,15 +36,19 @@ def allreduce_sum_(bucket, group=None):
 class DPTrainer(object):
     def __init__(self, cfg, netLength, param_values=None, seed=0, rank=0, world=1, lr=1e-4, clip=8.0, ema_decay=0.999,
                  beta1=0.9, beta2=0.999, eps=1e-8, dropouts=None, device="cuda", classifier=None, output_dropout=0.85,
-                 encoder=None, stem=None, enc_dropouts=(0.85, 0.92), stem_dropout=0.82):
+                 encoder=None, stem=None, enc_dropouts=(0.85, 0.92), stem_dropout=0.82, prec="fp32", bwd_tc=False):
         """`classifier=(answerWordsNum, outClassifierDims)` adds the reference's output unit + answer loss
         (model.py:512-528, 547-576, 593-596); `encoder=(vocabulary rows, wrdEmbDim)` the question input unit
         (model.py:208-220, 279-307) and `stem=(imageInDim, stemNumLayers)` the image stem (model.py:165-204), with the
         reference's training dropouts (config.py:202-206).  All variables join the same flat buckets, so the one
-        all-reduce and the one fused optimizer pass cover the whole model (`train_step_full`)."""
+        all-reduce and the one fused optimizer pass cover the whole model (`train_step_full`).
+        `prec="bf16"` runs the read unit's forward projections on tensor cores in training too (activations saved in bf16,
+        widened for the backward); `bwd_tc=True` runs its six backward products on tensor cores (`mac_read_bwd_tc`).
+        Both are mixed precision: bf16 operands, fp32 accumulation, fp32 master weights / gradients / optimizer state."""
         from .mac_cell import MACParams, views_of
         from .params import init_params
         self.cfg, self.L, self.rank, self.world = cfg, netLength, rank, world
+        self.prec, self.bwd_tc = prec, bool(bwd_tc)
         self.lib = _lib.load()
         extra_specs = extra_values = None
         if classifier is not None:
@@ -105,7 +109,7 @@ class DPTrainer(object):
             self._cells[key] = MACCell(batch["vecQuestions"], batch["questionWords"], batch["questionCntxWords"],
                                        batch["questionLengths"], batch["knowledgeBase"], dm, dr, dw,
                                        batch["knowledgeBase"].shape[0], True, config=self.cfg, params=self.params,
-                                       save_for_backward=True)
+                                       prec=self.prec, save_for_backward=True)
         return self._cells[key]
 
     def grads(self, key, batch, t_control, t_memory, global_batch):
@@ -119,7 +123,7 @@ class DPTrainer(object):
         control, memory = mac_network(cell, self.L)
         scale = 1.0 / float(global_batch)
         g = mac_backward(cell, None if t_control is None else t_control * scale,
-                         None if t_memory is None else t_memory * scale, bucket=self.bucket)
+                         None if t_memory is None else t_memory * scale, bucket=self.bucket, tc=self.bwd_tc)
         return control, memory, g
 
     def apply(self):
@@ -149,7 +153,7 @@ class DPTrainer(object):
                                              loss_scale=1.0 / float(global_batch))
         d_mem, d_q = torch.zeros_like(memory), torch.zeros_like(memory)
         self.out.backward(gviews, d_mem, d_q)
-        mac_backward(cell, None, d_mem, bucket=self.bucket, zero_bucket=False, d_vecq=d_q)
+        mac_backward(cell, None, d_mem, bucket=self.bucket, zero_bucket=False, d_vecq=d_q, tc=self.bwd_tc)
         self.apply()
         self.out.invalidate()
         return logits, losses
@@ -189,7 +193,7 @@ class DPTrainer(object):
                                              loss_scale=1.0 / float(global_batch))
         d_mem, d_q = torch.zeros_like(memory), torch.zeros_like(memory)
         self.out.backward(gviews, d_mem, d_q)
-        g = mac_backward(cell, None, d_mem, bucket=self.bucket, zero_bucket=False, d_vecq=d_q)
+        g = mac_backward(cell, None, d_mem, bucket=self.bucket, zero_bucket=False, d_vecq=d_q, tc=self.bwd_tc)
         self.stem.backward(g["knowledgeBase"], gviews)
         if not self.cfg.controlContextual:
             raise NotImplementedError("the raw-word control inputs (controlContextual off) need wrdEmbDim == ctrlDim")

@@ -200,9 +200,11 @@ class MACCell(object):
         self.save_for_backward = bool(save_for_backward)
         recurrent_ctrl_ok = (c.controlFeedPrev and self._fused_control and not (c.controlWholeQ or c.controlContinuous
                                                                                 or c.unsharedCells))
-        if self.save_for_backward and (self.prec != PREC["fp32"] or not (self._fused_read and self._fused_write)
+        if self.save_for_backward and (not (self._fused_read and self._fused_write)
                                        or not (self._hoist or recurrent_ctrl_ok)):
-            raise NotImplementedError("backward is implemented on the fused fp32 path (DESIGN.md section 9)")
+            raise NotImplementedError("backward is implemented on the fused path (DESIGN.md section 9)")
+        if self.save_for_backward and self.prec != PREC["fp32"] and (d % 128 or self._kb_given_bf16):
+            raise NotImplementedError("training forward on tensor cores needs d % 128 == 0 and an fp32 knowledge base")
         if self.prec != PREC["fp32"] and not self._fused_read:
             raise NotImplementedError("the tensor-core projections cover the fused read unit only")
         if self._kb_given_bf16 and not (self.prec == PREC["bf16"] and self._read_hoist and float(readDropout) >= 1.0):
@@ -437,8 +439,24 @@ class MACCell(object):
                                     ctypes.byref(rw), float(self.dropouts["read"]), self.seed, i, self.prec,
                                     ptr(info), ptr(att), ptr(_save), ptr(self.ws.read), self.ws.read_bytes, B, N, d,
                                     stream_ptr()), "mac_read_fwd")
+        if _save is not None and self.prec == PREC["bf16"]:
+            self._upcast_saved(_save)
         self.attentions["kb"].append(att)
         return info
+
+    def _upcast_saved(self, save):
+        """Training forward on tensor cores: the chain leaves P, P*y, H, I1 as bf16 slabs in the read workspace (behind its
+        fp32 part, 1 KB aligned: tc_read_chain in csrc/tc_gemm.cuh); the backward kernels read `save` = [P | H | I1 | y] in
+        fp32, so widen the three it needs (a dtype-converting copy: memory plumbing; y is already there in fp32)."""
+        B, N, d = self.B, self.N, self.d
+        M = B * N
+        fp32_total = int(self.lib.mac_read_workspace_bytes(B, N, d, PREC["fp32"]))
+        base = self.ws.read.data_ptr()
+        off = ((base + fp32_total + 1023) & ~1023) - base
+        slab = (M * d * 2 + 1023) & ~1023
+        for k, src_slab in enumerate((0, 2, 3)):                       # P, H, I1  (slab 1 is P*y)
+            src = self.ws.read[off + src_slab * slab: off + src_slab * slab + M * d * 2].view(torch.bfloat16)
+            save[k * M * d:(k + 1) * M * d].copy_(src)
 
     # ------------------------------------------------------------------ write unit
     def _folded_write_weights(self, name):

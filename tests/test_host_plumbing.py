@@ -68,7 +68,7 @@ def test_full_model_trainer_host_calls(monkeypatch):
         seed = 0
     monkeypatch.setattr(tr, "cell_for", lambda key, batch: _Cell())
     monkeypatch.setattr(mac_cell, "mac_network", lambda cell, L_: (torch.zeros(B, d), torch.zeros(B, d)))
-    monkeypatch.setattr(autograd, "mac_backward", lambda cell, dc, dm, bucket=None, zero_bucket=True, d_vecq=None: {
+    monkeypatch.setattr(autograd, "mac_backward", lambda cell, dc, dm, bucket=None, zero_bucket=True, d_vecq=None, tc=False: {
         "knowledgeBase": torch.zeros(B, H * W, d), "questionCntxWords": torch.zeros(B, S, d), "vecQuestions": torch.zeros(B, d)})
     data = {"questions": torch.randint(0, V + 1, (B, S), dtype=torch.int32),
             "questionLengths": torch.randint(1, S + 1, (B,), dtype=torch.int32),
@@ -140,3 +140,29 @@ def test_training_state_roundtrip(monkeypatch, tmp_path):
     k = "MACnetwork/MACCell/read/linearLayermemKbProj/weights/weight"
     o = a.params.offsets[k]
     assert np.array_equal(vals[k].reshape(-1), a.ema[o:o + vals[k].size].numpy())
+
+
+@pytest.mark.parametrize("prec,tc", [("fp32", True), ("bf16", False), ("bf16", True)])
+def test_cell_tensor_core_training_host_calls(monkeypatch, prec, tc):
+    """Mixed-precision training forms: bf16 forward with the saved activations widened for the backward, and the backward
+    with its six big products on tensor cores (mac_read_bwd_tc)."""
+    mock = _mocklib.install(monkeypatch)
+    monkeypatch.setattr(torch.Tensor, "is_cuda", property(lambda self: True), raising=False)
+    from mac_network_b200.autograd import mac_backward
+    from mac_network_b200.config import MACConfig
+    from mac_network_b200.mac_cell import MACCell, MACParams, mac_network
+    from mac_network_b200.synthetic import make_inputs
+    B, S, N, d, L = 4, 6, 16, 128, 2                     # B*N % 64 == 0, d % 128 == 0
+    cfg = MACConfig.args("args", netLength=L, memDim=d, ctrlDim=d, attDim=d)
+    params = MACParams(cfg, L, seed=1, device="cpu")
+    x = {k: torch.from_numpy(v) for k, v in make_inputs(B, S, N, d, seed=2).items()}
+    # the mock's size queries return 64 KB; give the read workspace its real extent so the bf16 slab views exist
+    monkeypatch.setattr(mock, "mac_read_workspace_bytes",
+                        lambda b, n, dd, pr: 4096 + (2 + pr * 3) * b * n * dd * 4 + 8192, raising=False)
+    cell = MACCell(x["vecQuestions"], x["questionWords"], x["questionCntxWords"], x["questionLengths"], x["knowledgeBase"],
+                   0.85, 0.85, 1.0, B, True, config=cfg, params=params, prec=prec, save_for_backward=True)
+    mac_network(cell, L)
+    g = mac_backward(cell, torch.zeros(B, d), torch.zeros(B, d), tc=tc)
+    assert g["knowledgeBase"].shape == (B, N, d)
+    assert mock.calls.count("mac_read_bwd_tc" if tc else "mac_read_bwd") == L
+    assert mock.calls.count("mac_read_bwd" if tc else "mac_read_bwd_tc") == 0
