@@ -166,3 +166,37 @@ def test_cell_tensor_core_training_host_calls(monkeypatch, prec, tc):
     assert g["knowledgeBase"].shape == (B, N, d)
     assert mock.calls.count("mac_read_bwd_tc" if tc else "mac_read_bwd") == L
     assert mock.calls.count("mac_read_bwd" if tc else "mac_read_bwd_tc") == 0
+
+
+def test_macnet_run_batch_host_calls(monkeypatch):
+    """model.MACnet.runBatch (the reference's per-batch call, model.py:732-760): train and eval, trimming, predictions,
+    attention maps -- through the dry-run library, nothing stubbed."""
+    mock = _mocklib.install(monkeypatch)
+    monkeypatch.setattr(torch.Tensor, "is_cuda", property(lambda self: True), raising=False)
+    import importlib
+    m = importlib.import_module("mac_network_b200.model")
+    from mac_network_b200.config import MACConfig
+    B, S, V, E, d, H, W, C, A, L = 4, 9, 11, 12, 64, 3, 3, 8, 8, 2
+    cfg = MACConfig.args("gqa", netLength=L, memDim=d, ctrlDim=d, attDim=d)
+    net = m.MACnet(cfg, L, V, A, wrd_emb_dim=E, image_in_dim=C, classifier_dims=(16,), prec="fp32", device="cpu",
+                   answer_decoder=lambda i: "ans%d" % i)
+    rng = np.random.RandomState(0)
+    lengths = np.array([5, 7, 2, 6], dtype=np.int32)                     # longest question 7 < S: the batch is trimmed
+    q = rng.randint(1, V + 1, size=(B, S)).astype(np.int32)
+    q[np.arange(S)[None, :] >= lengths[:, None]] = 0
+    data = {"questions": q, "questionLengths": lengths, "answers": rng.randint(0, A, size=(B,)).astype(np.int32),
+            "instances": [{"questionId": i} for i in range(B)]}
+    images = {"images": rng.standard_normal((B, C, H, W)).astype(np.float32)}
+    res = net.runBatch(None, data, images, train=True)
+    assert set(res) == {"loss", "correctNum", "acc", "preds", "gradNorm", "readTime", "trainTime"}
+    assert "mac_lstm_bwd" in mock.calls and "mac_clip_adam_ema_step" in mock.calls and res["gradNorm"] != -1
+    assert data["questions"].shape == (B, S)                              # the caller's batch is not modified
+    mock.calls.clear()
+    res = net.runBatch(None, data, images, train=False, getAtt=True)
+    assert res["gradNorm"] == -1 and 0 <= res["correctNum"] <= B and len(res["preds"]) == B
+    assert "mac_read_invariant" in mock.calls and "mac_lstm_bwd" not in mock.calls      # inference form, no backward
+    rec = res["preds"][1]
+    assert rec["questionId"] == 1 and rec["prediction"].startswith("ans")
+    att = rec["attentions"]
+    assert set(att) == {"kb", "question", "self", "gate"} and len(att["kb"]) == L
+    assert np.asarray(att["kb"][0]).shape == (H, W) and len(att["question"][0]) == 7     # trimmed to the longest question
