@@ -565,6 +565,10 @@ class MACCell(object):
         sc = scope + "mul" + name + "/"
         orig_x, proj_x = x2d, None
         if proj is not None:
+            if proj.get("dropout", 1.0) < 1.0:          # ops.py:678-679: both operands, before their projections
+                i = self.iteration
+                x2d = self._dropout(x2d, proj["dropout"], _lib.SITE_READ_KB, i, self._new(*x2d.shape))
+                y = self._dropout(y, proj["dropout"], _lib.SITE_READ_MEM, i, self._new(*y.shape))
             xn, yn = ("proj", "proj") if proj["shared"] else ("projX", "projY")
             x2d = self._ops_linear([x2d], sc, xn)
             y = self._ops_linear([y], sc, yn)
@@ -585,11 +589,10 @@ class MACCell(object):
     def _read_general(self, knowledgeBase, memory, control, name, att, info):
         """mac_cell.py:209-277 composed from primitives (flag sets outside the fused read kernel)."""
         c, B, N, d = self.cfg, self.B, self.N, self.d
-        if self.dropouts["read"] < 1.0:
-            raise NotImplementedError("train-mode read dropout on the general path (use the fused flag family)")
+        keep_r = self.dropouts["read"]
         sc = "MACCell/read" + name + "/"
         kb2 = knowledgeBase.view(B * N, d)
-        proj = {"shared": c.readProjShared} if c.readProjInputs else None
+        proj = {"shared": c.readProjShared, "dropout": keep_r} if c.readProjInputs else None
         segs, projectedKB = self._mul_general(kb2, memory, c.memDim, N, sc, "memInter", proj, c.readMemAttType,
                                               c.readMemConcatKB, c.readMemConcatProj)
         if c.readMemProj:
@@ -599,6 +602,11 @@ class MACCell(object):
             if c.readCtrlConcatKB:
                 segs.append(projectedKB if c.readCtrlConcatProj else kb2)
             segs = [self._act(x, c.readCtrlAct) for x in segs]          # act(concat) == concat(act)
+        if keep_r < 1.0:
+            # inter2att's linear drops its (concatenated) input (mac_cell.py:266, ops.py:312): ONE mask over [B, N, total
+            # width], so the concat is materialised for the flat mask index (memory plumbing) and dropped as one tensor
+            cat = segs[0] if len(segs) == 1 else torch.cat(segs, dim=1)
+            segs = [self._dropout(cat, keep_r, _lib.SITE_READ_INTER, self.iteration, self._new(*cat.shape))]
         logits = self._rowdot(segs, sc + "inter2att/inter2logits/linearLayerlogits/")
         feats = projectedKB if c.readSmryKBProj else kb2
         dd = feats.shape[1]
@@ -707,6 +715,19 @@ class MACCell(object):
         self._set_histories(i + 1)                                                     # mac_cell.py:472-474
         return self.none, MACCellTuple(newControl, newMemory)
 
+    def _read_inter_width(self):
+        """Width of the tensor inter2att drops (mac_cell.py:209-266): the fused family ends in memDim columns."""
+        c = self.cfg
+        if self._fused_read:
+            return self.d
+        dim = c.attDim if c.readProjInputs else c.memDim
+        inter = dim + ((c.attDim if c.readMemConcatProj else c.memDim) if c.readMemConcatKB else 0)
+        if c.readMemProj:
+            inter = dim
+        if c.readCtrl and c.readCtrlConcatKB:
+            inter += c.attDim if c.readCtrlConcatProj else c.memDim
+        return inter
+
     # ------------------------------------------------------------------ test support
     def dropout_uniforms(self):
         """The uniforms the kernels draw for this forward, in the reference's call order (zero_state mask, then per
@@ -725,9 +746,10 @@ class MACCell(object):
             if not c.memoryVariationalDropout and km < 1.0:
                 out.append(draw(_lib.SITE_MEM_PLAIN, i, (B, d)))
             if kr < 1.0:
-                out.append(draw(_lib.SITE_READ_KB, i, (B, N, d)))
-                out.append(draw(_lib.SITE_READ_MEM, i, (B, d)))
-                out.append(draw(_lib.SITE_READ_INTER, i, (B, N, d)))
+                if self._fused_read or c.readProjInputs:
+                    out.append(draw(_lib.SITE_READ_KB, i, (B, N, d)))
+                    out.append(draw(_lib.SITE_READ_MEM, i, (B, d)))
+                out.append(draw(_lib.SITE_READ_INTER, i, (B, N, self._read_inter_width())))
             if c.writeDropout < 1.0 and kw < 1.0:
                 out.append(draw(_lib.SITE_WRITE_INFO, i, (B, d)))
         return out

@@ -72,6 +72,11 @@ CASES = {
                                    "--writeGateBias=-0.5"], SMALL, False),
     "p2_write_mem": (None, [f for f in ARGS if f != "--writeMemProj"] + ["--writeInputs=MEM"], SMALL, False),
     "p2_write_mul": (None, ARGS + ["--writeConcatMul", "--writeSelfAtt"], SMALL, False),
+    # training mode on the composed path: which tensors the read unit drops there, and over what width (mac_cell.py:266)
+    "p2_read_add_train": (None, ARGS + ["--readMemAttType=ADD", "--readCtrlAttType=ADD", "--mulBias=0.5",
+                                        "--readCtrlConcatKB", "--readCtrlConcatProj", "--readSmryKBProj"], SMALL, True),
+    "p2_read_plain_train": (None, ["--relu=STD", "--controlContextual", "--readCtrl", "--readCtrlConcatKB",
+                                   "--mulBias=0.25", "--initCtrl=Q"], SMALL, True),
     # BASELINE.json configs[0]/[1]: B=32, S=20, 14x14 KB, d=512, netLength=4 (float32 storage)
     "args_cpu_ref": ("@args.txt", [], dict(B=32, S=20, N=196, d=512, L=4), False),
     "gqa_mid": ("@args3.txt", ["--writeGate"], dict(B=8, S=30, N=49, d=512, L=6), False),

@@ -200,3 +200,30 @@ def test_macnet_run_batch_host_calls(monkeypatch):
     att = rec["attentions"]
     assert set(att) == {"kb", "question", "self", "gate"} and len(att["kb"]) == L
     assert np.asarray(att["kb"][0]).shape == (H, W) and len(att["question"][0]) == 7     # trimmed to the longest question
+
+
+@pytest.mark.filterwarnings("ignore:invalid value")          # the dry-run library leaves the drawn uniforms uninitialised
+@pytest.mark.parametrize("case", ["p2_read_add_train", "p2_read_plain_train"])
+def test_general_path_training_dropout_host_calls(monkeypatch, case):
+    """Composed (P2) read unit in training mode: the dropouts the reference applies there (ops.py:678-679 on both operands of
+    the projected interaction; mac_cell.py:266 on the concatenated interactions) and their draw order / widths."""
+    mock = _mocklib.install(monkeypatch)
+    monkeypatch.setattr(torch.Tensor, "is_cuda", property(lambda self: True), raising=False)
+    from mac_network_b200.mac_cell import MACCell, MACParams, mac_network
+    from tests._util import load_golden, rebuild
+    meta, arrays = load_golden(case)
+    cfg, inputs, pv = rebuild(meta, dtype=np.float32)
+    sh = meta["shape"]
+    B, N, d, L = sh["B"], sh["N"], sh["d"], sh["L"]
+    params = MACParams(cfg, L, values=pv, device="cpu")
+    x = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in inputs.items()}
+    dp = meta["dropouts"]
+    cell = MACCell(x["vecQuestions"], x["questionWords"], x["questionCntxWords"], x["questionLengths"], x["knowledgeBase"],
+                   dp["memory"], dp["read"], dp["write"], B, True, config=cfg, params=params)
+    assert not cell._fused_read
+    mac_network(cell, L)
+    draws = cell.dropout_uniforms()
+    # same number and shapes of uniform draws as the reference made on the shim for this flag set
+    assert len(draws) == meta["n_uniform"]
+    for i, u in enumerate(draws):
+        assert tuple(u.shape) == tuple(arrays["uniform_%03d" % i].shape), i

@@ -1,0 +1,22 @@
+"""Training-mode forward of the composed (P2) read unit on the GPU: the product draws its Philox masks, the oracle -- pinned
+to the reference's own training run of these flag sets by `tests/golden/p2_read_*_train.npz` -- is fed the same uniforms.
+Written after the round's GPU budget was spent: `xfail(strict=False)`, sorted last (see test_zzz_tensor_core_training.py)."""
+import numpy as np
+import pytest
+
+from tests._util import load_golden, rebuild
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(strict=False, reason="composition not yet run on hardware (round-1 GPU budget spent)")]
+
+
+@pytest.mark.parametrize("case", ["p2_read_add_train", "p2_read_plain_train"])
+def test_general_path_training_forward_matches_oracle(case):
+    from tests.test_gpu_parity import compare, run_gpu, run_oracle
+    meta, _ = load_golden(case)
+    cfg, inputs, params = rebuild(meta)
+    dp = (meta["dropouts"]["memory"], meta["dropouts"]["read"], meta["dropouts"]["write"])
+    L = meta["shape"]["L"]
+    got, cell = run_gpu(cfg, params, inputs, L, dropouts=dp, train=True, seed=987)
+    ref = run_oracle(cfg, params, inputs, L, dropouts=dp, uniforms=cell.dropout_uniforms())
+    compare(got, ref, what=case)
