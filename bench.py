@@ -456,7 +456,7 @@ def run_ours(args):
         t_dev, t_e2e = float(tt[0]), float(tt[1])
 
     # ---- data-parallel training arm (all ranks take part: it contains the path's one collective)
-    train = train_full = train_tc = None
+    train = train_full = train_tc = batched = None
     if not args.skip_train:
         del pipe
         torch.cuda.empty_cache()
@@ -470,6 +470,12 @@ def run_ours(args):
             train_full = {"skipped": "measured at N=1 only; the N>1 lines carry the cell's DP-training arm (`train`)"}
         if world == 1:
             train_tc = train_tc_arm()
+            # informational (NOT the headline configuration): six B=64 requests concatenated into one B=384 pass -- what
+            # dynamic batching across requests would buy over independent passes in flight; measured in a child process
+            batched = {"requests_x6_one_stream": child_measure(["--mode", "quick", "--batch-mult", "6", "--streams", "1",
+                                                                 "--steps", "12", "--warmup", "3"]),
+                       "requests_x6_two_streams": child_measure(["--mode", "quick", "--batch-mult", "6", "--streams", "2",
+                                                                  "--steps", "12", "--warmup", "4"])}
 
     if rank == 0:
         roofs = kernel_rooflines(shape, args.prec, pk)
@@ -512,6 +518,7 @@ def run_ours(args):
             "train": train,
             "train_full": train_full,
             "train_tc": train_tc,
+            "info_batched_requests": batched,
         }
         print(json.dumps(line))
     if dist is not None:
@@ -715,6 +722,64 @@ def run_train(args):
         dist.destroy_process_group()
 
 
+def run_quick(args):
+    """Resident-input throughput only (no e2e / rooflines / CPU / training arms): used in child processes for informational
+    side measurements, e.g. `--batch-mult 6 --streams 1` = six B=64 requests concatenated into one B=384 pass."""
+    from mac_network_b200.mac_cell import MACParams
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    B, S, N, d, L = SHAPES[WORKLOAD]
+    mult = max(1, args.batch_mult)
+    shape = (B * mult, S, N, d, L)
+    cfg = MACConfig.args("args", netLength=L)
+    params = MACParams(cfg, L, values=perturb_biases(init_params(cfg, L, seed=100), seed=101))
+    nstreams = max(1, args.streams)
+    fold_y = (nstreams < 4) if args.fold_y < 0 else bool(args.fold_y)
+    nslots = max(2, min(NSLOTS, 2 * nstreams)) if mult > 1 else NSLOTS          # keep > 126 MB of inputs in rotation
+    slots = [Slot(cfg, params, shape, 1234 + s, args.prec, not args.no_graph, fold_y=fold_y) for s in range(nslots)]
+    side = [torch.cuda.Stream() for _ in range(nstreams - 1)]
+    main_stream = torch.cuda.current_stream()
+
+    def run(n):
+        fork = torch.cuda.Event()
+        fork.record(main_stream)
+        for st in side:
+            st.wait_event(fork)
+        for k in range(n):
+            j = k % nstreams
+            if j == 0:
+                slots[k % nslots].run()
+            else:
+                with torch.cuda.stream(side[j - 1]):
+                    slots[k % nslots].run()
+        for st in side:
+            ev = torch.cuda.Event()
+            ev.record(st)
+            main_stream.wait_event(ev)
+    run(max(args.warmup, nstreams))
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run(args.steps)
+    e1.record()
+    torch.cuda.synchronize()
+    t = e0.elapsed_time(e1) * 1e-3
+    print(json.dumps({"metric": METRIC, "value": args.steps * L * mult / t, "unit": UNIT, "batch_rows_per_pass": B * mult,
+                      "requests_of_64_per_pass": mult, "concurrent_passes": nstreams, "ms_per_pass": t / args.steps * 1e3,
+                      "launches_per_pass": int(slots[0].launches), "resident_slots": nslots}))
+
+
+def child_measure(extra, timeout_s=120):
+    """Run `bench.py <extra>` in a child process and return its last JSON line (or an error record)."""
+    try:
+        out = subprocess.run([sys.executable, os.path.abspath(__file__)] + extra, capture_output=True, text=True,
+                             timeout=timeout_s, cwd=ROOT)
+        if out.returncode != 0:
+            return {"error": "exit %d: %s" % (out.returncode, out.stderr.strip()[-300:])}
+        return json.loads(out.stdout.strip().splitlines()[-1])
+    except Exception as exc:
+        return {"error": repr(exc)[:300]}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -761,7 +826,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-train", action="store_true", help="skip the short DP-training arm of the default run")
-    ap.add_argument("--mode", default="infer", choices=["infer", "train"])
+    ap.add_argument("--mode", default="infer", choices=["infer", "train", "quick"])
+    ap.add_argument("--batch-mult", type=int, default=1, help="--mode quick: requests of B=64 concatenated per pass")
     ap.add_argument("--streams", type=int, default=6, help="independent passes in flight (each on its own stream)")
     ap.add_argument("--fold-y", type=int, default=-1, help="write unit folded with the next step's projY: 1/0, -1 = by --streams")
     ap.add_argument("--rooflines-only", action="store_true", help="only the per-kernel measurements (for ncu)")
@@ -776,6 +842,8 @@ def main():
         run_reference(args)
     elif args.mode == "train":
         run_train(args)
+    elif args.mode == "quick":
+        run_quick(args)
     else:
         run_ours(args)
 
