@@ -271,6 +271,24 @@ def kernel_rooflines(shape, prec, pk):
                 "torch_copy_13MB_read_13MB_write_us": t_copy * 1e6, "torch_copy_frac_of_peak": nbytes / t_copy / 1e9 / pk["hbm"],
                 "torch_sum_26MB_read_us": t_sum * 1e6, "torch_sum_frac_of_peak": nbytes / t_sum / 1e9 / pk["hbm"]}
         del kbs
+    # ---- the same kernel with six requests' knowledge bases in ONE launch (B = 384, 78 MB bf16): informational -- separates
+    #      "latency-bound at 13 MB per launch" from "inefficient kernel" (the headline K3 entry stays the B = 64 one above)
+    try:
+        Bb = 6 * B
+        kbs6 = [torch.randn(Bb, N, d, device="cuda").to(torch.bfloat16) for _ in range(3)]          # 3 x 77 MB > L2
+        parts6 = torch.randn(Bb, N, 4, device="cuda")
+        att6, info6 = torch.empty(Bb, N, device="cuda"), torch.empty(Bb, d, device="cuda")
+        fns6 = [(lambda k_=k_: L.check(lib.mac_kb_attend_fwd(L.ptr(parts6), 4, 0.0, L.ptr(k_), 1, L.ptr(att6), L.ptr(info6), Bb,
+                                                              N, d, L.stream_ptr()))) for k_ in kbs6]
+        t6 = time_kernel(fns6, iters=24)
+        nb6 = Bb * N * d * 2 + Bb * N * 4 * 4 + Bb * N * 4 + Bb * d * 4
+        out["kb_attend_bf16_kb_x6_rows"] = {"bound": "hbm", "achieved": nb6 / t6 / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                                            "frac": nb6 / t6 / 1e9 / pk["hbm"], "traffic": None, "us": t6 * 1e6,
+                                            "algorithmic_bytes": nb6,
+                                            "note": "informational: B = %d rows per launch (six B = 64 requests), same kernel" % Bb}
+        del kbs6
+    except Exception as exc:
+        out["kb_attend_bf16_kb_x6_rows"] = {"error": repr(exc)[:200]}
     # ---- dominant projection GEMM: memKbProj, [B*N, 2d] x [2d, d] (49.6 % of the step's FLOPs)
     M, K = B * N, 2 * d
     xs = [torch.randn(M, K, device="cuda") for _ in range(3)]
