@@ -587,7 +587,7 @@ def train_arm(steps, warmup, rank, world, dist):
     return out
 
 
-def train_tc_arm(timeout_s=150):
+def train_tc_arm(timeout_s=90):
     """Mixed-precision training of the cell (bf16 tensor-core forward AND backward GEMMs) measured in a
     CHILD process: the composition was written after the round's GPU budget was spent, so a failure of it must not be able
     to touch this process's CUDA context or its JSON line."""
@@ -786,7 +786,7 @@ def run_quick(args):
                       "launches_per_pass": int(slots[0].launches), "resident_slots": nslots}))
 
 
-def child_measure(extra, timeout_s=120):
+def child_measure(extra, timeout_s=60):
     """Run `bench.py <extra>` in a child process and return its last JSON line (or an error record)."""
     try:
         out = subprocess.run([sys.executable, os.path.abspath(__file__)] + extra, capture_output=True, text=True,
