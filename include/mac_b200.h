@@ -140,6 +140,17 @@ int mac_read_fwd_inv(const float* kb, const void* kb_bf16, const void* inv, cons
                      mac_stream_t stream);
 /* y_pre (may be NULL): y = memory_in @ Wy + by [B, d] when the caller already has it, see mac_write_fwd_next_y. */
 
+/* One inference read step as ONE kernel (csrc/read_step.cuh): given inv = [P | Q] from mac_read_invariant (bf16), the bf16
+ * knowledge base, y = memory @ Wy + by [B, d] (ops.py:689) and the control state [B, d], computes
+ *   H = ELU((P*y) @ Wm[0:d] + Q);  logits = ELU((H @ Wm2 + bm2) * control) . wr + br;  att = softmax_n(logits);
+ *   info = sum_n att * KB                                     (mac_cell.py:230-275 at readDropout == 1)
+ * with P*y, H, I1, I2 and the logits kept on the SM (shared / tensor memory).  mac_read_fwd_inv dispatches to it when
+ * mac_read_step_fused_supported(B, N, d) (d == 512, N <= 256) unless the environment sets MAC_READ_FUSED=0.
+ * Returns MAC_ERR_UNSUPPORTED for other shapes. */
+int mac_read_step_fused(const void* inv, const void* kb_bf16, const float* y, const float* control,
+                        const mac_read_weights* w, float* info, float* att, int B, int N, int d, mac_stream_t stream);
+int mac_read_step_fused_supported(int B, int N, int d);
+
 /* The HBM-bound tail of the read unit on its own (ops.py:143, 149-150):
  *   att[b,:] = softmax_n( sum_p logit_parts[(b*N+n)*nparts + p] + br );  info[b,:] = sum_n att[b,n] * KB[b,n,:]
  * kb_is_bf16 != 0: `kb` points at bf16 data. */

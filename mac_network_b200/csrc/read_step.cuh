@@ -1,0 +1,514 @@
+// One reasoning step of the read unit as ONE kernel (inference form, mac_cell.py:209-277 with readDropout == 1):
+//
+//   H      = ELU((P * y_b) @ Wm[0:d, :] + Q)            (ops.py:694-703 MUL, mac_cell.py:236-238; P, Q step-invariant)
+//   I2     = ELU((H @ Wm2 + bm2) * control_b)           (ops.py:325-328, mac_cell.py:248-250, 262)
+//   logit  = I2 . wr + br                               (mac_cell.py:266, ops.py:316-317)
+//   att    = softmax_n(logit);  info = sum_n att * KB   (ops.py:143, 149-150; original KB, mac_cell.py:271-275)
+//
+// replacing scale_rows_bf16 + tc_gemm<ADDACT> + tc_gemm<LOGITS> + kb_attend (4 launches, ~64 MB of L2/HBM traffic for the
+// P*y and H round trips) by one launch in which P*y, H, I1, I2 and the logits never leave the SM.
+//
+// Tiling: a CTA owns 128 knowledge-base rows and the FULL d = 512 output width, so the fp32 accumulator fills the SM's
+// whole tensor memory (128 lanes x 512 columns) and every logit is finished inside one CTA.  Rows are aligned to samples:
+//   PAIR  (128 < N <= 256, CLEVR's 14x14 grid): a 2-CTA cluster per sample; rank r takes rows [128 r, min(N, 128 r + 128)).
+//         The softmax statistics and the two partial weighted sums are exchanged through distributed shared memory.
+//   !PAIR (N <= 128, e.g. the 7x7 GQA grid): a CTA takes spc = min(128 / N, 2) whole samples; no exchange.
+//
+// Warp roles (576 threads):
+//   warp 0       TMA producer: P tile k-blocks (A ring), Wm[0:d] and then Wm2 k-blocks in [256 x 64] halves (B ring)
+//   warp 1       TMEM allocator + tcgen05.mma issuer (UMMA 128 x 256 x 16, two N halves per k-step)
+//   warps 2..17  workers (512 threads).  GEMM 1: scale each landed P k-block by y_b IN PLACE in shared memory (the
+//                operand never exists in HBM), fence it to the async proxy and hand it to the MMA warp.  Then epilogue 1:
+//                TMEM -> registers, + Q, ELU, bf16 -> shared memory in the 128-byte-swizzled K-major layout tcgen05
+//                reads as the A operand of GEMM 2.  Then epilogue 2 (bias, control product, ELU, dot with wr) and the
+//                attention tail (softmax, weighted sum over the bf16 knowledge base).
+//
+// Shared memory (13 units of 16 KB + 14 KB of parameters / exchange): GEMM 1 uses 3 A slots (units 0-2) and 5 B slots
+// (units 3-12); H (128 KB) then overlays units 0-7 and GEMM 2 streams Wm2 through B slots 3 and 4 (units 9-12).
+#pragma once
+#include "tc_gemm.cuh"
+
+namespace mac {
+
+constexpr int RS_D = 512;                       // d (TMEM columns of the accumulator)
+constexpr int RS_KB = RS_D / TC_BK;             // 8 k-blocks of 64
+constexpr int RS_WORKER_WARPS = 16;
+constexpr int RS_WORKERS = 32 * RS_WORKER_WARPS;
+constexpr int RS_THREADS = 64 + RS_WORKERS;     // 576
+constexpr int RS_UNIT = 16384;                  // one [128 x 64] bf16 tile
+constexpr int RS_A_SLOTS = 3;
+constexpr int RS_B_SLOTS = 5;
+constexpr int RS_UNITS = RS_A_SLOTS + 2 * RS_B_SLOTS;      // 13
+constexpr int RS_MAX_SPC = 2;                   // samples per CTA on the N <= 128 path
+constexpr int RS_PAR_FLOATS = (2 + RS_MAX_SPC) * RS_D;     // bm2, wr, control rows
+constexpr int RS_RED_GROUPS = 8;                // row groups of the weighted sum
+constexpr int RS_SMEM_BYTES = RS_UNITS * RS_UNIT + 1024 /*align*/ + 256 /*barriers*/ + RS_PAR_FLOATS * 4 +
+                              4 * 128 * 4 /*logit partials*/ + 128 * 4 /*att*/ + 64 /*exchange*/ + RS_D * 4 /*peer info*/;
+
+struct ReadStepParams {
+  int B, N;
+  int spc;                          // samples per CTA (!PAIR); 1 for PAIR
+  const float* y;                   // [B, d]   memory projection (ops.py:689)
+  const float* ctrl;                // [B, d]
+  const float* bm2;                 // [d]
+  const float* wr;                  // [d]
+  float br;
+  const __nv_bfloat16* Q;           // [B*N, d]  P @ Wm[d:2d] + bm
+  const __nv_bfloat16* kb;          // [B*N, d]  bf16 knowledge base
+  float* att;                       // [B, N]
+  float* info;                      // [B, d]
+};
+
+__device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void st_cluster_f32(const float* local_addr, uint32_t cta, float v) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "st.shared::cluster.f32 [ra], %2;\n\t}"
+      ::"r"(smem_u32(local_addr)), "r"(cta), "f"(v)
+      : "memory");
+}
+__device__ __forceinline__ float bf16lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+__device__ __forceinline__ void rs_worker_bar() { asm volatile("bar.sync 1, %0;" ::"n"(RS_WORKERS) : "memory"); }
+
+template <bool PAIR>
+__global__ void __launch_bounds__(RS_THREADS, 1)
+read_step_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ CUtensorMap map_w1,
+                 const __grid_constant__ CUtensorMap map_w2, const ReadStepParams p) {
+  extern __shared__ unsigned char smem_dyn[];
+  const uint32_t base_u32 = smem_u32(smem_dyn);
+  const uint32_t pad = (1024u - (base_u32 & 1023u)) & 1023u;
+  unsigned char* tiles = smem_dyn + pad;                         // 13 units, 1024-byte aligned
+  unsigned char* a_slots = tiles;                                // units 0..2
+  unsigned char* b_slots = tiles + RS_A_SLOTS * RS_UNIT;         // units 3..12, 32 KB each
+  unsigned char* h_tile = tiles;                                 // units 0..7 (after GEMM 1)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + RS_UNITS * RS_UNIT);
+  uint64_t* a_full = bars;                         // [3] TMA -> workers
+  uint64_t* a_ready = bars + 3;                    // [3] workers -> MMA   (16 warp arrivals)
+  uint64_t* a_empty = bars + 6;                    // [3] MMA -> TMA
+  uint64_t* b_full = bars + 9;                     // [5] TMA -> MMA
+  uint64_t* b_empty = bars + 14;                   // [5] MMA -> TMA
+  uint64_t* g1_done = bars + 19;                   // MMA -> workers (accumulator of GEMM 1 complete)
+  uint64_t* h_ready = bars + 20;                   // workers -> MMA (H in shared memory, accumulator drained)
+  uint64_t* g2_done = bars + 21;                   // MMA -> workers
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 22);
+  float* par = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bars) + 256);   // bm2 | wr | ctrl rows
+  float* s_part = par + RS_PAR_FLOATS;             // [4][128] logit partial sums
+  float* s_att = s_part + 4 * 128;                 // [128] logits, then attention weights
+  float* s_xch = s_att + 128;                      // [2 ranks][max, sum] (+ padding to 64 B)
+  float* s_peer = s_xch + 16;                      // [512] partner's partial weighted sum (rank 0 only reads it)
+  float* s_red = reinterpret_cast<float*>(b_slots + 3 * 2 * RS_UNIT);   // [8][512] over B slots 3, 4 (after GEMM 2)
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int N = p.N;
+  uint32_t rank = 0;
+  int s0, nsamp, row0, valid;            // first sample, samples of this CTA, first flat KB row, valid tile rows
+  if constexpr (PAIR) {
+    rank = cluster_rank();
+    s0 = blockIdx.x >> 1;
+    nsamp = 1;
+    row0 = s0 * N + (int)rank * 128;
+    valid = min(128, N - (int)rank * 128);
+  } else {
+    s0 = blockIdx.x * p.spc;
+    nsamp = min(p.spc, p.B - s0);
+    row0 = s0 * N;
+    valid = nsamp * N;
+  }
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_p);
+    tma_prefetch_desc(&map_w1);
+    tma_prefetch_desc(&map_w2);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_ready[i], RS_WORKER_WARPS);
+      mbar_init(&a_empty[i], 1);
+    }
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
+    }
+    mbar_init(g1_done, 1);
+    mbar_init(h_ready, RS_WORKER_WARPS);
+    mbar_init(g2_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (elect_one()) {
+      // the tiles the tail of this CTA will read with plain loads: start them towards L2 now
+      {
+        const size_t bytes = (size_t)valid * RS_D * 2;
+        const char* q0 = reinterpret_cast<const char*>(p.Q + (size_t)row0 * RS_D);
+        const char* k0 = reinterpret_cast<const char*>(p.kb + (size_t)row0 * RS_D);
+        for (size_t o = 0; o < bytes; o += 16384) {
+          const uint32_t n = (uint32_t)min((size_t)16384, bytes - o);
+          l2_prefetch_bulk(q0 + o, n);
+          l2_prefetch_bulk(k0 + o, n);
+        }
+      }
+      // GEMM 1: A = P rows of this tile, B = Wm[0:d] in two [256 x 64] halves per k-block
+      for (int kb = 0; kb < RS_KB; ++kb) {
+        const int sa = kb % RS_A_SLOTS, na = kb / RS_A_SLOTS;
+        mbar_wait(&a_empty[sa], (na & 1) ^ 1);
+        mbar_expect_tx(&a_full[sa], RS_UNIT);
+        tma_load_2d(a_slots + sa * RS_UNIT, &map_p, kb * TC_BK, row0, &a_full[sa]);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int j = kb * 2 + h, sb = j % RS_B_SLOTS, nb = j / RS_B_SLOTS;
+          mbar_wait(&b_empty[sb], (nb & 1) ^ 1);
+          mbar_expect_tx(&b_full[sb], 2 * RS_UNIT);
+          tma_load_2d(b_slots + sb * 2 * RS_UNIT, &map_w1, kb * TC_BK, h * 256, &b_full[sb]);
+        }
+      }
+      // GEMM 2: B = Wm2 through slots 3 and 4 only (0..2 are under H); use index continues the per-slot count
+      for (int i = 0; i < 2 * RS_KB; ++i) {
+        const int sb = 3 + (i & 1), nb = 3 + (i >> 1);
+        mbar_wait(&b_empty[sb], (nb & 1) ^ 1);
+        mbar_expect_tx(&b_full[sb], 2 * RS_UNIT);
+        tma_load_2d(b_slots + sb * 2 * RS_UNIT, &map_w2, (i >> 1) * TC_BK, (i & 1) * 256, &b_full[sb]);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    constexpr uint32_t idesc = make_idesc_bf16(128, 256);
+    for (int kb = 0; kb < RS_KB; ++kb) {
+      const int sa = kb % RS_A_SLOTS, na = kb / RS_A_SLOTS;
+      mbar_wait(&a_ready[sa], na & 1);                         // scaled by the workers, visible to the async proxy
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int j = kb * 2 + h, sb = j % RS_B_SLOTS, nb = j / RS_B_SLOTS;
+        mbar_wait(&b_full[sb], nb & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t adesc = make_sw128_kmajor_desc(smem_u32(a_slots + sa * RS_UNIT));
+          const uint64_t bdesc = make_sw128_kmajor_desc(smem_u32(b_slots + sb * 2 * RS_UNIT));
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k)
+            umma_bf16(tmem_base + h * 256, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+          umma_commit(&b_empty[sb]);
+          if (h == 1) {
+            umma_commit(&a_empty[sa]);
+            if (kb == RS_KB - 1) umma_commit(g1_done);
+          }
+        }
+        __syncwarp();
+      }
+    }
+    mbar_wait(h_ready, 0);                                     // H written, GEMM-1 accumulator drained
+    tc_fence_after();
+    for (int i = 0; i < 2 * RS_KB; ++i) {
+      const int kb = i >> 1, h = i & 1;
+      const int sb = 3 + h, nb = 3 + kb;
+      mbar_wait(&b_full[sb], nb & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t adesc = make_sw128_kmajor_desc(smem_u32(h_tile + kb * RS_UNIT));
+        const uint64_t bdesc = make_sw128_kmajor_desc(smem_u32(b_slots + sb * 2 * RS_UNIT));
+#pragma unroll
+        for (int k = 0; k < TC_BK / 16; ++k)
+          umma_bf16(tmem_base + h * 256, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+        umma_commit(&b_empty[sb]);
+        if (i == 2 * RS_KB - 1) umma_commit(g2_done);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================================================== workers
+    const int wt = threadIdx.x - 64;                 // 0..511
+    const int q = warp & 3;                          // TMEM lane quarter this warp may touch
+    const int cg = (warp - 2) >> 2;                  // column group: columns [128 cg, 128 cg + 128)
+    const int row = q * 32 + lane;                   // tile row == TMEM lane of this thread in the epilogues
+    // ---- parameters of epilogue 2 into shared memory (overlaps the first TMA round trips)
+    for (int i = wt; i < RS_D; i += RS_WORKERS) {
+      par[i] = __ldg(p.bm2 + i);
+      par[RS_D + i] = __ldg(p.wr + i);
+    }
+    for (int i = wt; i < nsamp * RS_D; i += RS_WORKERS) par[2 * RS_D + i] = __ldg(p.ctrl + (size_t)s0 * RS_D + i);
+    // ---- Q addend of this thread's row, first half of its 128 columns (8 x 16 B); the rest is fetched while consuming
+    const bool row_ok = row < valid;
+    const __nv_bfloat16* qrow = p.Q + (size_t)(row0 + (row_ok ? row : 0)) * RS_D + cg * 128;
+    uint4 qv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) qv[i] = ldg_nc_v4(qrow + 8 * i);
+
+    // ---- GEMM 1 operand path: P k-block -> (P * y_b) in place.  Thread handles 16-byte chunks c = wt and wt + 512 of
+    //      the 1024 in a [128 x 64] tile: row c >> 3, physical chunk c & 7 == logical chunk (c & 7) ^ (row & 7)
+    //      (the 128-byte swizzle TMA wrote and tcgen05 expects).
+    {
+      const int r_a = wt >> 3, r_b = r_a + 64;
+      const int pc = wt & 7;
+      const int lc_a = pc ^ (r_a & 7), lc_b = pc ^ (r_b & 7);
+      const bool ok_a = r_a < valid, ok_b = r_b < valid;
+      const int b_a = s0 + (PAIR ? 0 : (ok_a ? r_a / N : 0));
+      const int b_b = s0 + (PAIR ? 0 : (ok_b ? r_b / N : 0));
+      const float* y_a = p.y + (size_t)b_a * RS_D + lc_a * 8;
+      const float* y_b = p.y + (size_t)b_b * RS_D + lc_b * 8;
+      auto scale16 = [](uint4 v, const float4 f0, const float4 f1) {
+        uint4 o;
+        o.x = pack_bf16(bf16lo(v.x) * f0.x, bf16hi(v.x) * f0.y);
+        o.y = pack_bf16(bf16lo(v.y) * f0.z, bf16hi(v.y) * f0.w);
+        o.z = pack_bf16(bf16lo(v.z) * f1.x, bf16hi(v.z) * f1.y);
+        o.w = pack_bf16(bf16lo(v.w) * f1.z, bf16hi(v.w) * f1.w);
+        return o;
+      };
+      for (int kb = 0; kb < RS_KB; ++kb) {
+        const int sa = kb % RS_A_SLOTS, na = kb / RS_A_SLOTS;
+        // this k-block's y values (L1-resident after the first touch) before the wait on the tile
+        const float4 ya0 = __ldg(reinterpret_cast<const float4*>(y_a + kb * TC_BK));
+        const float4 ya1 = __ldg(reinterpret_cast<const float4*>(y_a + kb * TC_BK + 4));
+        const float4 yb0 = __ldg(reinterpret_cast<const float4*>(y_b + kb * TC_BK));
+        const float4 yb1 = __ldg(reinterpret_cast<const float4*>(y_b + kb * TC_BK + 4));
+        mbar_wait(&a_full[sa], na & 1);
+        uint4* t = reinterpret_cast<uint4*>(a_slots + sa * RS_UNIT);
+        if (ok_a) t[wt] = scale16(t[wt], ya0, ya1);
+        if (ok_b) t[wt + 512] = scale16(t[wt + 512], yb0, yb1);
+        fence_proxy_async();                       // generic-proxy writes -> visible to tcgen05's async-proxy reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_ready[sa]);
+      }
+    }
+
+    // ---- epilogue 1: H = ELU(acc + Q) -> bf16, K-major 128-byte-swizzled tiles over units 0..7
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + cg * 128;
+    mbar_wait(g1_done, 0);
+    tc_fence_after();
+#pragma unroll
+    for (int ch = 0; ch < 8; ++ch) {
+      uint32_t r[16];
+      tmem_ld16(taddr + 16 * ch, r);
+      tmem_ld_wait();
+      const uint4 qa = qv[(2 * ch) & 7], qb = qv[(2 * ch + 1) & 7];
+      if (ch < 4) {                                // refill the two slots just consumed with columns + 64
+        qv[(2 * ch) & 7] = ldg_nc_v4(qrow + 64 + 16 * ch);
+        qv[(2 * ch + 1) & 7] = ldg_nc_v4(qrow + 64 + 16 * ch + 8);
+      }
+      const uint32_t qw[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+      uint32_t w[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        w[j] = pack_bf16(elu_fast(__uint_as_float(r[2 * j]) + bf16lo(qw[j])),
+                         elu_fast(__uint_as_float(r[2 * j + 1]) + bf16hi(qw[j])));
+      const int c0 = cg * 128 + 16 * ch;           // H column of w[0]
+      const int kb2 = c0 >> 6, lc = (c0 & 63) >> 3;
+      unsigned char* hrow = h_tile + kb2 * RS_UNIT + row * 128;
+      *reinterpret_cast<uint4*>(hrow + ((lc ^ (row & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+      *reinterpret_cast<uint4*>(hrow + (((lc + 1) ^ (row & 7)) << 4)) = make_uint4(w[4], w[5], w[6], w[7]);
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(h_ready);
+
+    // ---- epilogue 2: logit partial of this thread's row over its 128 columns
+    rs_worker_bar();                               // parameters staged by all workers are visible
+    const int ls = PAIR ? 0 : (row_ok ? row / N : 0);
+    const float* crow = par + (2 + ls) * RS_D;
+    mbar_wait(g2_done, 0);
+    tc_fence_after();
+    float part = 0.f;
+#pragma unroll 2
+    for (int ch = 0; ch < 8; ++ch) {
+      uint32_t r[16];
+      tmem_ld16(taddr + 16 * ch, r);
+      tmem_ld_wait();
+      const int c0 = cg * 128 + 16 * ch;
+      const float4* b4 = reinterpret_cast<const float4*>(par + c0);
+      const float4* w4 = reinterpret_cast<const float4*>(par + RS_D + c0);
+      const float4* c4 = reinterpret_cast<const float4*>(crow + c0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 bb = b4[j], ww = w4[j], cc = c4[j];
+        part = fmaf(elu_fast((__uint_as_float(r[4 * j]) + bb.x) * cc.x), ww.x, part);
+        part = fmaf(elu_fast((__uint_as_float(r[4 * j + 1]) + bb.y) * cc.y), ww.y, part);
+        part = fmaf(elu_fast((__uint_as_float(r[4 * j + 2]) + bb.z) * cc.z), ww.z, part);
+        part = fmaf(elu_fast((__uint_as_float(r[4 * j + 3]) + bb.w) * cc.w), ww.w, part);
+      }
+    }
+    tc_fence_before();
+    s_part[cg * 128 + row] = part;
+    rs_worker_bar();
+    if (wt < 128) s_att[wt] = s_part[wt] + s_part[128 + wt] + s_part[256 + wt] + s_part[384 + wt] + p.br;
+    rs_worker_bar();
+
+    // ---- softmax statistics: worker warp w < nsamp owns local sample w (rows [w N, w N + nrows))
+    const int wi = warp - 2;
+    const int nrows = PAIR ? valid : N;
+    float e_lane[4] = {0.f, 0.f, 0.f, 0.f};
+    float mx = -INFINITY, sum = 0.f;
+    if (wi < nsamp) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int n = lane + 32 * i;
+        if (n < nrows) mx = fmaxf(mx, s_att[wi * N + n]);
+      }
+      mx = warp_max(mx);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int n = lane + 32 * i;
+        if (n < nrows) {
+          e_lane[i] = __expf(s_att[wi * N + n] - mx);
+          sum += e_lane[i];
+        }
+      }
+      sum = warp_sum(sum);
+      if constexpr (PAIR) {
+        if (lane == 0) {
+          s_xch[2 * rank] = mx;
+          s_xch[2 * rank + 1] = sum;
+          st_cluster_f32(&s_xch[2 * rank], rank ^ 1u, mx);
+          st_cluster_f32(&s_xch[2 * rank + 1], rank ^ 1u, sum);
+        }
+      }
+    }
+    if constexpr (PAIR) cluster_barrier();         // #1 (all 576 threads of both CTAs; warps 0/1 join below)
+    if (wi < nsamp) {
+      float scale;
+      if constexpr (PAIR) {
+        const float m0 = s_xch[0], z0 = s_xch[1], m1 = s_xch[2], z1 = s_xch[3];
+        const float M = fmaxf(m0, m1);
+        const float Z = z0 * __expf(m0 - M) + z1 * __expf(m1 - M);
+        scale = __expf(mx - M) / Z;
+      } else {
+        scale = 1.f / sum;
+      }
+      const int b = s0 + wi;
+      const int n_off = PAIR ? (int)rank * 128 : 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int n = lane + 32 * i;
+        if (n < nrows) {
+          const float a = e_lane[i] * scale;
+          s_att[wi * N + n] = a;
+          p.att[(size_t)b * N + n_off + n] = a;
+        }
+      }
+    }
+    rs_worker_bar();
+
+    // ---- info = sum_n att[n] * KB[n, :]: thread = (row group rg of 8, 8-column chunk cq of 64), 16-byte loads
+    const int rg = wt >> 6, cq = wt & 63;
+    for (int s = 0; s < nsamp; ++s) {
+      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      const __nv_bfloat16* kbase = p.kb + (size_t)(row0 + s * N) * RS_D + cq * 8;
+      const float* a_s = s_att + s * N;
+#pragma unroll 4
+      for (int n = rg; n < nrows; n += RS_RED_GROUPS) {
+        const uint4 v = ldg_nc_v4(kbase + (size_t)n * RS_D);
+        const float a = a_s[n];
+        acc[0] = fmaf(a, bf16lo(v.x), acc[0]); acc[1] = fmaf(a, bf16hi(v.x), acc[1]);
+        acc[2] = fmaf(a, bf16lo(v.y), acc[2]); acc[3] = fmaf(a, bf16hi(v.y), acc[3]);
+        acc[4] = fmaf(a, bf16lo(v.z), acc[4]); acc[5] = fmaf(a, bf16hi(v.z), acc[5]);
+        acc[6] = fmaf(a, bf16lo(v.w), acc[6]); acc[7] = fmaf(a, bf16hi(v.w), acc[7]);
+      }
+      if (s > 0) rs_worker_bar();                  // previous sample's reduction has been read
+      float4* dst = reinterpret_cast<float4*>(s_red + rg * RS_D + cq * 8);
+      dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+      rs_worker_bar();
+      float t = 0.f;
+#pragma unroll
+      for (int g = 0; g < RS_RED_GROUPS; ++g) t += s_red[g * RS_D + wt];
+      if constexpr (PAIR) {
+        if (rank == 1) st_cluster_f32(&s_peer[wt], 0u, t);        // partner's half of the rows -> leader's smem
+        cluster_barrier();                         // #2
+        if (rank == 0) p.info[(size_t)s0 * RS_D + wt] = t + s_peer[wt];
+      } else {
+        p.info[(size_t)(s0 + s) * RS_D + wt] = t;
+      }
+    }
+  }
+  if constexpr (PAIR) {
+    if (warp < 2) {                                // the producer / MMA warps take part in the two cluster barriers
+      __syncwarp();
+      cluster_barrier();
+      cluster_barrier();
+    }
+  }
+
+  // ---- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// can the fused kernel take this shape?
+inline bool read_step_supported(int B, int N, int d) { return d == RS_D && N >= 1 && N <= 256 && B >= 1; }
+
+// inv = [P | Q] (tc_read_invariant); y, control [B, d] fp32; att [B, N], info [B, d]
+inline int read_step_launch(const void* inv, const void* kb_bf16, const float* y, const float* control,
+                            const mac_read_weights* w, float* att, float* info, int B, int N, int d, cudaStream_t stream) {
+  if (!read_step_supported(B, N, d)) return MAC_ERR_UNSUPPORTED;
+  if (!inv || !kb_bf16 || !y || !control || !w->Wm_bf16 || !w->Wm2_bf16 || !att || !info) return MAC_ERR_INVALID;
+  const int M = B * N;
+  const size_t slab = (((size_t)M * d * 2 + 1023) & ~(size_t)1023);
+  const char* ibase = tc_align1k(const_cast<void*>(inv));
+  CUtensorMap mp, mw1, mw2;
+  int st = make_tmap_2d(&mp, ibase, 1, (uint64_t)M, (uint64_t)d, (uint64_t)d * 2, 128, TC_BK, 1);
+  if (st != MAC_OK) return st;
+  st = make_tmap_2d(&mw1, w->Wm_bf16, 1, (uint64_t)d, (uint64_t)d, (uint64_t)2 * d * 2, 256, TC_BK, 1);   // Wm[0:d] of [d, 2d]
+  if (st != MAC_OK) return st;
+  st = make_tmap_2d(&mw2, w->Wm2_bf16, 1, (uint64_t)d, (uint64_t)d, (uint64_t)d * 2, 256, TC_BK, 1);
+  if (st != MAC_OK) return st;
+  ReadStepParams p{};
+  p.B = B; p.N = N; p.y = y; p.ctrl = control; p.bm2 = w->bm2; p.wr = w->wr; p.br = w->br;
+  p.Q = reinterpret_cast<const __nv_bfloat16*>(ibase + slab);
+  p.kb = reinterpret_cast<const __nv_bfloat16*>(kb_bf16);
+  p.att = att; p.info = info;
+  static bool attr_set[2] = {false, false};
+  if (N > 128) {
+    auto kern = read_step_kernel<true>;
+    if (!attr_set[0]) {
+      MAC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_SMEM_BYTES));
+      attr_set[0] = true;
+    }
+    p.spc = 1;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * B, 1, 1);
+    cfg.blockDim = dim3(RS_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = RS_SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    MAC_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, mp, mw1, mw2, p));
+  } else {
+    auto kern = read_step_kernel<false>;
+    if (!attr_set[1]) {
+      MAC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_SMEM_BYTES));
+      attr_set[1] = true;
+    }
+    p.spc = min(128 / N, RS_MAX_SPC);
+    const int grid = (B + p.spc - 1) / p.spc;
+    kern<<<grid, RS_THREADS, RS_SMEM_BYTES, stream>>>(mp, mw1, mw2, p);
+  }
+  MAC_LAUNCH_CHECK();
+  return MAC_OK;
+}
+
+}  // namespace mac

@@ -3,6 +3,7 @@
 #include "sgemm.cuh"
 #include "skinny.cuh"
 #include "tc_gemm.cuh"
+#include "read_step.cuh"
 
 using namespace mac;
 
@@ -171,6 +172,23 @@ static int read_fwd_impl(const float* kb, const void* kb_bf16, const void* inv, 
                          uint64_t seed, int step, int prec, float* info, float* att, float* save, void* workspace,
                          size_t workspace_bytes, int B, int N, int d, mac_stream_t stream_);
 
+// MAC_READ_FUSED=0 keeps the four-launch form of the inference read step (scale, two GEMMs, attention) for comparison
+static bool read_step_enabled() {
+  static const bool on = !(getenv("MAC_READ_FUSED") && atoi(getenv("MAC_READ_FUSED")) == 0);
+  return on;
+}
+
+extern "C" int mac_read_step_fused(const void* inv, const void* kb_bf16, const float* y, const float* control,
+                                   const mac_read_weights* w, float* info, float* att, int B, int N, int d,
+                                   mac_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!inv || !kb_bf16 || !y || !control || !w || !info || !att || B <= 0 || N <= 0 || d <= 0) return MAC_ERR_INVALID;
+  if (!mac_aligned16(inv) || !mac_aligned16(kb_bf16) || !mac_aligned16(y) || !mac_aligned16(control)) return MAC_ERR_ALIGN;
+  if (!mac_b200_device_ok()) return MAC_ERR_ARCH;
+  return read_step_launch(inv, kb_bf16, y, control, w, att, info, B, N, d, stream);
+}
+extern "C" int mac_read_step_fused_supported(int B, int N, int d) { return read_step_supported(B, N, d) ? 1 : 0; }
+
 extern "C" int mac_read_fwd(const float* kb, const void* kb_bf16, const float* memory_in, const float* control,
                             const mac_read_weights* w, float keep_read, uint64_t seed, int step, int prec, float* info,
                             float* att, float* save, void* workspace, size_t workspace_bytes, int B, int N, int d,
@@ -237,6 +255,10 @@ static int read_fwd_impl(const float* kb, const void* kb_bf16, const void* inv, 
     if (st != MAC_OK) return st;
   }
   int nparts = 0;
+  if (inv && prec == MAC_PREC_BF16 && kb_bf16 && read_step_supported(B, N, d) && read_step_enabled()) {
+    // the whole step (P*y, both projections, logits, softmax, weighted sum) as ONE kernel: read_step.cuh
+    return read_step_launch(inv, kb_bf16, y, control, w, att, info, B, N, d, stream);
+  }
   if (inv && prec == MAC_PREC_BF16) {
     int st = tc_read_chain_inv(inv, y, control, w, parts, &nparts, ws + fp32_total, workspace_bytes - fp32_total, B, N,
                                d, stream);
