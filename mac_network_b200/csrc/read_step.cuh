@@ -57,6 +57,7 @@ struct ReadStepParams {
   const __nv_bfloat16* kb;          // [B*N, d]  bf16 knowledge base
   float* att;                       // [B, N]
   float* info;                      // [B, d]
+  long long* dbg;                   // profiling only (mac_dbg_read_step_timestamps): [gridDim.x][8] SM-clock stamps, or NULL
 };
 
 __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
@@ -77,6 +78,9 @@ __device__ __forceinline__ void st_cluster_f32(const float* local_addr, uint32_t
 }
 __device__ __forceinline__ float bf16lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+__device__ __forceinline__ void rs_stamp(const ReadStepParams& p, int slot) {
+  if (p.dbg) p.dbg[(size_t)blockIdx.x * 8 + slot] = clock64();
+}
 __device__ __forceinline__ void rs_worker_bar() { asm volatile("bar.sync 1, %0;" ::"n"(RS_WORKERS) : "memory"); }
 
 template <bool PAIR>
@@ -97,9 +101,9 @@ read_step_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_constan
   uint64_t* b_full = bars + 9;                     // [5] TMA -> MMA
   uint64_t* b_empty = bars + 14;                   // [5] MMA -> TMA
   uint64_t* g1_done = bars + 19;                   // MMA -> workers (accumulator of GEMM 1 complete)
-  uint64_t* h_ready = bars + 20;                   // workers -> MMA (H in shared memory, accumulator drained)
-  uint64_t* g2_done = bars + 21;                   // MMA -> workers
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 22);
+  uint64_t* hk_ready = bars + 20;                  // [8] workers -> MMA (H k-block in shared memory, its accumulator columns drained)
+  uint64_t* g2_done = bars + 28;                   // [2] MMA -> workers (N half of GEMM 2 complete)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 30);
   float* par = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bars) + 256);   // bm2 | wr | ctrl rows
   float* s_part = par + RS_PAR_FLOATS;             // [4][128] logit partial sums
   float* s_att = s_part + 4 * 128;                 // [128] logits, then attention weights
@@ -140,8 +144,10 @@ read_step_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_constan
       mbar_init(&b_empty[i], 1);
     }
     mbar_init(g1_done, 1);
-    mbar_init(h_ready, RS_WORKER_WARPS);
-    mbar_init(g2_done, 1);
+#pragma unroll
+    for (int i = 0; i < RS_KB; ++i) mbar_init(&hk_ready[i], RS_WORKER_WARPS);
+    mbar_init(&g2_done[0], 1);
+    mbar_init(&g2_done[1], 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr, 512);
@@ -179,11 +185,12 @@ read_step_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_constan
         }
       }
       // GEMM 2: B = Wm2 through slots 3 and 4 only (0..2 are under H); use index continues the per-slot count
+      //         order: all k-blocks of output half 0, then half 1 (epilogue 2 of half 0 overlaps the MMAs of half 1)
       for (int i = 0; i < 2 * RS_KB; ++i) {
         const int sb = 3 + (i & 1), nb = 3 + (i >> 1);
         mbar_wait(&b_empty[sb], (nb & 1) ^ 1);
         mbar_expect_tx(&b_full[sb], 2 * RS_UNIT);
-        tma_load_2d(b_slots + sb * 2 * RS_UNIT, &map_w2, (i >> 1) * TC_BK, (i & 1) * 256, &b_full[sb]);
+        tma_load_2d(b_slots + sb * 2 * RS_UNIT, &map_w2, (i & 7) * TC_BK, (i >> 3) * 256, &b_full[sb]);
       }
     }
     __syncwarp();
@@ -213,11 +220,22 @@ read_step_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_constan
         __syncwarp();
       }
     }
-    mbar_wait(h_ready, 0);                                     // H written, GEMM-1 accumulator drained
-    tc_fence_after();
+    // GEMM 2, output half h = columns [256 h, 256 h + 256): k-block kb needs H k-block kb (hk_ready[kb]); the first MMA of
+    // half 0 overwrites accumulator columns 0..255 = the GEMM-1 columns of H k-blocks 0..3, so it waits for those four;
+    // half 1 (columns 256..511) starts after all eight.  Epilogue 1 of k-blocks 4..7 thus overlaps half 0's first MMAs.
     for (int i = 0; i < 2 * RS_KB; ++i) {
-      const int kb = i >> 1, h = i & 1;
-      const int sb = 3 + h, nb = 3 + kb;
+      const int h = i >> 3, kb = i & 7;
+      const int sb = 3 + (i & 1), nb = 3 + (i >> 1);
+      if (h == 0) {
+        if (kb == 0) {
+          mbar_wait(&hk_ready[0], 0);
+          mbar_wait(&hk_ready[1], 0);
+          mbar_wait(&hk_ready[2], 0);
+          mbar_wait(&hk_ready[3], 0);
+        } else if (kb >= 4) {
+          mbar_wait(&hk_ready[kb], 0);
+        }
+      }
       mbar_wait(&b_full[sb], nb & 1);
       tc_fence_after();
       if (elect_one()) {
@@ -227,7 +245,7 @@ read_step_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_constan
         for (int k = 0; k < TC_BK / 16; ++k)
           umma_bf16(tmem_base + h * 256, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
         umma_commit(&b_empty[sb]);
-        if (i == 2 * RS_KB - 1) umma_commit(g2_done);
+        if (kb == RS_KB - 1) umma_commit(&g2_done[h]);
       }
       __syncwarp();
     }
@@ -235,20 +253,24 @@ read_step_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_constan
     // ===================================================== workers
     const int wt = threadIdx.x - 64;                 // 0..511
     const int q = warp & 3;                          // TMEM lane quarter this warp may touch
-    const int cg = (warp - 2) >> 2;                  // column group: columns [128 cg, 128 cg + 128)
+    const int cg = (warp - 2) >> 2;                  // column group: 16 columns of every 64-column k-block
     const int row = q * 32 + lane;                   // tile row == TMEM lane of this thread in the epilogues
+    if (wt == 0) rs_stamp(p, 0);
     // ---- parameters of epilogue 2 into shared memory (overlaps the first TMA round trips)
     for (int i = wt; i < RS_D; i += RS_WORKERS) {
       par[i] = __ldg(p.bm2 + i);
       par[RS_D + i] = __ldg(p.wr + i);
     }
     for (int i = wt; i < nsamp * RS_D; i += RS_WORKERS) par[2 * RS_D + i] = __ldg(p.ctrl + (size_t)s0 * RS_D + i);
-    // ---- Q addend of this thread's row, first half of its 128 columns (8 x 16 B); the rest is fetched while consuming
+    // ---- Q addend of this thread's row: its 16 columns of k-blocks 0..3 now (8 x 16 B), k-blocks 4..7 while consuming
     const bool row_ok = row < valid;
-    const __nv_bfloat16* qrow = p.Q + (size_t)(row0 + (row_ok ? row : 0)) * RS_D + cg * 128;
+    const __nv_bfloat16* qrow = p.Q + (size_t)(row0 + (row_ok ? row : 0)) * RS_D + cg * 16;
     uint4 qv[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) qv[i] = ldg_nc_v4(qrow + 8 * i);
+    for (int i = 0; i < 4; ++i) {
+      qv[2 * i] = ldg_nc_v4(qrow + 64 * i);
+      qv[2 * i + 1] = ldg_nc_v4(qrow + 64 * i + 8);
+    }
 
     // ---- GEMM 1 operand path: P k-block -> (P * y_b) in place.  Thread handles 16-byte chunks c = wt and wt + 512 of
     //      the 1024 in a [128 x 64] tile: row c >> 3, physical chunk c & 7 == logical chunk (c & 7) ^ (row & 7)
@@ -287,19 +309,22 @@ read_step_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_constan
       }
     }
 
-    // ---- epilogue 1: H = ELU(acc + Q) -> bf16, K-major 128-byte-swizzled tiles over units 0..7
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + cg * 128;
+    // ---- epilogue 1: H = ELU(acc + Q) -> bf16, K-major 128-byte-swizzled tiles over units 0..7.  One H k-block (64
+    //      columns) at a time across all 16 warps, so that GEMM 2 can start on the k-blocks that are done.
+    const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+    if (wt == 0) rs_stamp(p, 1);                   // last P k-block scaled
     mbar_wait(g1_done, 0);
     tc_fence_after();
+    if (wt == 0) rs_stamp(p, 2);                   // GEMM 1 complete
 #pragma unroll
-    for (int ch = 0; ch < 8; ++ch) {
+    for (int kb2 = 0; kb2 < RS_KB; ++kb2) {
       uint32_t r[16];
-      tmem_ld16(taddr + 16 * ch, r);
+      tmem_ld16(tlane + kb2 * 64 + cg * 16, r);
       tmem_ld_wait();
-      const uint4 qa = qv[(2 * ch) & 7], qb = qv[(2 * ch + 1) & 7];
-      if (ch < 4) {                                // refill the two slots just consumed with columns + 64
-        qv[(2 * ch) & 7] = ldg_nc_v4(qrow + 64 + 16 * ch);
-        qv[(2 * ch + 1) & 7] = ldg_nc_v4(qrow + 64 + 16 * ch + 8);
+      const uint4 qa = qv[(2 * kb2) & 7], qb = qv[(2 * kb2 + 1) & 7];
+      if (kb2 < 4) {                               // refill the two slots just consumed with k-block kb2 + 4
+        qv[(2 * kb2) & 7] = ldg_nc_v4(qrow + 64 * (kb2 + 4));
+        qv[(2 * kb2 + 1) & 7] = ldg_nc_v4(qrow + 64 * (kb2 + 4) + 8);
       }
       const uint32_t qw[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
       uint32_t w[8];
@@ -307,40 +332,44 @@ read_step_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_constan
       for (int j = 0; j < 8; ++j)
         w[j] = pack_bf16(elu_fast(__uint_as_float(r[2 * j]) + bf16lo(qw[j])),
                          elu_fast(__uint_as_float(r[2 * j + 1]) + bf16hi(qw[j])));
-      const int c0 = cg * 128 + 16 * ch;           // H column of w[0]
-      const int kb2 = c0 >> 6, lc = (c0 & 63) >> 3;
+      const int lc = cg * 2;                       // 16-byte chunk of w[0..3] inside the k-block's 128-byte row
       unsigned char* hrow = h_tile + kb2 * RS_UNIT + row * 128;
       *reinterpret_cast<uint4*>(hrow + ((lc ^ (row & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
       *reinterpret_cast<uint4*>(hrow + (((lc + 1) ^ (row & 7)) << 4)) = make_uint4(w[4], w[5], w[6], w[7]);
+      fence_proxy_async();                         // H k-block visible to tcgen05's async-proxy reads
+      tc_fence_before();                           // ... and this warp's reads of the accumulator columns are done
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&hk_ready[kb2]);
     }
-    fence_proxy_async();
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(h_ready);
+    if (wt == 0) rs_stamp(p, 3);                   // H written
 
-    // ---- epilogue 2: logit partial of this thread's row over its 128 columns
+    // ---- epilogue 2: logit partial of this thread's row; output half h as soon as its MMAs are done
     rs_worker_bar();                               // parameters staged by all workers are visible
     const int ls = PAIR ? 0 : (row_ok ? row / N : 0);
     const float* crow = par + (2 + ls) * RS_D;
-    mbar_wait(g2_done, 0);
-    tc_fence_after();
     float part = 0.f;
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {
+      mbar_wait(&g2_done[h], 0);
+      tc_fence_after();
+      if (wt == 0 && h == 1) rs_stamp(p, 4);       // GEMM 2 complete
 #pragma unroll 2
-    for (int ch = 0; ch < 8; ++ch) {
-      uint32_t r[16];
-      tmem_ld16(taddr + 16 * ch, r);
-      tmem_ld_wait();
-      const int c0 = cg * 128 + 16 * ch;
-      const float4* b4 = reinterpret_cast<const float4*>(par + c0);
-      const float4* w4 = reinterpret_cast<const float4*>(par + RS_D + c0);
-      const float4* c4 = reinterpret_cast<const float4*>(crow + c0);
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t r[16];
+        const int c0 = h * 256 + cg * 64 + 16 * ch;
+        tmem_ld16(tlane + c0, r);
+        tmem_ld_wait();
+        const float4* b4 = reinterpret_cast<const float4*>(par + c0);
+        const float4* w4 = reinterpret_cast<const float4*>(par + RS_D + c0);
+        const float4* c4 = reinterpret_cast<const float4*>(crow + c0);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float4 bb = b4[j], ww = w4[j], cc = c4[j];
-        part = fmaf(elu_fast((__uint_as_float(r[4 * j]) + bb.x) * cc.x), ww.x, part);
-        part = fmaf(elu_fast((__uint_as_float(r[4 * j + 1]) + bb.y) * cc.y), ww.y, part);
-        part = fmaf(elu_fast((__uint_as_float(r[4 * j + 2]) + bb.z) * cc.z), ww.z, part);
-        part = fmaf(elu_fast((__uint_as_float(r[4 * j + 3]) + bb.w) * cc.w), ww.w, part);
+        for (int j = 0; j < 4; ++j) {
+          const float4 bb = b4[j], ww = w4[j], cc = c4[j];
+          part = fmaf(elu_fast((__uint_as_float(r[4 * j]) + bb.x) * cc.x), ww.x, part);
+          part = fmaf(elu_fast((__uint_as_float(r[4 * j + 1]) + bb.y) * cc.y), ww.y, part);
+          part = fmaf(elu_fast((__uint_as_float(r[4 * j + 2]) + bb.z) * cc.z), ww.z, part);
+          part = fmaf(elu_fast((__uint_as_float(r[4 * j + 3]) + bb.w) * cc.w), ww.w, part);
+        }
       }
     }
     tc_fence_before();
@@ -348,10 +377,26 @@ read_step_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_constan
     rs_worker_bar();
     if (wt < 128) s_att[wt] = s_part[wt] + s_part[128 + wt] + s_part[256 + wt] + s_part[384 + wt] + p.br;
     rs_worker_bar();
+    if (wt == 0) rs_stamp(p, 5);                   // logits
+
+    // ---- knowledge-base rows of the weighted sum: thread = (row group rg of 8, 8-column chunk cq of 64); nrows <= 128 ->
+    //      at most 16 rows per thread.  The 16-byte loads do not depend on the attention weights: all of them are issued
+    //      here, before the softmax (and the pair's cluster barrier), and consumed after it.
+    const int nrows = PAIR ? valid : N;
+    const int rg = wt >> 6, cq = wt & 63;
+    uint4 v[16];
+    auto load_kb_rows = [&](int s) {
+      const __nv_bfloat16* kbase = p.kb + (size_t)(row0 + s * N) * RS_D + cq * 8;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int n = rg + RS_RED_GROUPS * i;
+        v[i] = n < nrows ? ldg_nc_v4(kbase + (size_t)n * RS_D) : make_uint4(0u, 0u, 0u, 0u);
+      }
+    };
+    load_kb_rows(0);
 
     // ---- softmax statistics: worker warp w < nsamp owns local sample w (rows [w N, w N + nrows))
     const int wi = warp - 2;
-    const int nrows = PAIR ? valid : N;
     float e_lane[4] = {0.f, 0.f, 0.f, 0.f};
     float mx = -INFINITY, sum = 0.f;
     if (wi < nsamp) {
@@ -404,20 +449,20 @@ read_step_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_constan
     }
     rs_worker_bar();
 
-    // ---- info = sum_n att[n] * KB[n, :]: thread = (row group rg of 8, 8-column chunk cq of 64), 16-byte loads
-    const int rg = wt >> 6, cq = wt & 63;
+    if (wt == 0) rs_stamp(p, 6);                   // attention weights
+    // ---- info = sum_n att[n] * KB[n, :]
     for (int s = 0; s < nsamp; ++s) {
       float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      const __nv_bfloat16* kbase = p.kb + (size_t)(row0 + s * N) * RS_D + cq * 8;
       const float* a_s = s_att + s * N;
-#pragma unroll 4
-      for (int n = rg; n < nrows; n += RS_RED_GROUPS) {
-        const uint4 v = ldg_nc_v4(kbase + (size_t)n * RS_D);
-        const float a = a_s[n];
-        acc[0] = fmaf(a, bf16lo(v.x), acc[0]); acc[1] = fmaf(a, bf16hi(v.x), acc[1]);
-        acc[2] = fmaf(a, bf16lo(v.y), acc[2]); acc[3] = fmaf(a, bf16hi(v.y), acc[3]);
-        acc[4] = fmaf(a, bf16lo(v.z), acc[4]); acc[5] = fmaf(a, bf16hi(v.z), acc[5]);
-        acc[6] = fmaf(a, bf16lo(v.w), acc[6]); acc[7] = fmaf(a, bf16hi(v.w), acc[7]);
+      if (s > 0) load_kb_rows(s);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int n = rg + RS_RED_GROUPS * i;
+        const float a = n < nrows ? a_s[n] : 0.f;
+        acc[0] = fmaf(a, bf16lo(v[i].x), acc[0]); acc[1] = fmaf(a, bf16hi(v[i].x), acc[1]);
+        acc[2] = fmaf(a, bf16lo(v[i].y), acc[2]); acc[3] = fmaf(a, bf16hi(v[i].y), acc[3]);
+        acc[4] = fmaf(a, bf16lo(v[i].z), acc[4]); acc[5] = fmaf(a, bf16hi(v[i].z), acc[5]);
+        acc[6] = fmaf(a, bf16lo(v[i].w), acc[6]); acc[7] = fmaf(a, bf16hi(v[i].w), acc[7]);
       }
       if (s > 0) rs_worker_bar();                  // previous sample's reduction has been read
       float4* dst = reinterpret_cast<float4*>(s_red + rg * RS_D + cq * 8);
@@ -435,6 +480,7 @@ read_step_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_constan
         p.info[(size_t)(s0 + s) * RS_D + wt] = t;
       }
     }
+    if (wt == 0) rs_stamp(p, 7);
   }
   if constexpr (PAIR) {
     if (warp < 2) {                                // the producer / MMA warps take part in the two cluster barriers
@@ -452,6 +498,9 @@ read_step_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_constan
     tmem_dealloc(tmem_base, 512);
   }
 }
+
+// profiling hook (not part of the ABI header): device buffer [grid][8] that subsequent launches fill with clock64 stamps
+inline long long*& read_step_dbg_ptr() { static long long* p = nullptr; return p; }
 
 // can the fused kernel take this shape?
 inline bool read_step_supported(int B, int N, int d) { return d == RS_D && N >= 1 && N <= 256 && B >= 1; }
@@ -475,7 +524,7 @@ inline int read_step_launch(const void* inv, const void* kb_bf16, const float* y
   p.B = B; p.N = N; p.y = y; p.ctrl = control; p.bm2 = w->bm2; p.wr = w->wr; p.br = w->br;
   p.Q = reinterpret_cast<const __nv_bfloat16*>(ibase + slab);
   p.kb = reinterpret_cast<const __nv_bfloat16*>(kb_bf16);
-  p.att = att; p.info = info;
+  p.att = att; p.info = info; p.dbg = read_step_dbg_ptr();
   static bool attr_set[2] = {false, false};
   if (N > 128) {
     auto kern = read_step_kernel<true>;

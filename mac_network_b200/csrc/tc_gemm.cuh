@@ -154,7 +154,17 @@ struct TcCfg {
 
 // fast ELU for the tensor-core path: x > 0 ? x : exp(x) - 1 with the SFU exponential (abs error ~1e-7 near 0,
 // far below the bf16 rounding of the stored activations)
-__device__ __forceinline__ float elu_fast(float x) { return x > 0.f ? x : __expf(x) - 1.f; }
+// (ex2.approx.ftz directly: without -ftz, __expf expands to a ~10-instruction denormal-safe sequence per element, which
+// made the 128 x 512 epilogues of the fused read step issue-bound)
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float elu_fast(float x) {
+  const float e = ex2_ftz(x * 1.4426950408889634f) - 1.f;
+  return x > 0.f ? x : e;
+}
 template <int ACT>
 __device__ __forceinline__ float act_ct(float x) {
   if constexpr (ACT == MAC_ACT_TANH) return tanhf(x);

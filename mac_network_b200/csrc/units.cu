@@ -187,6 +187,7 @@ extern "C" int mac_read_step_fused(const void* inv, const void* kb_bf16, const f
   if (!mac_b200_device_ok()) return MAC_ERR_ARCH;
   return read_step_launch(inv, kb_bf16, y, control, w, att, info, B, N, d, stream);
 }
+extern "C" void mac_dbg_read_step_timestamps(long long* dev_buf) { read_step_dbg_ptr() = dev_buf; }
 extern "C" int mac_read_step_fused_supported(int B, int N, int d) { return read_step_supported(B, N, d) ? 1 : 0; }
 
 extern "C" int mac_read_fwd(const float* kb, const void* kb_bf16, const float* memory_in, const float* control,

@@ -102,15 +102,46 @@ class DPTrainer(object):
         self.base_seed = seed
         self._cells = {}
 
+    MAX_CACHED_CELLS = 4      # a save-for-backward cell holds L x (3 B N d + B d) floats (~1.2 GB at B=64, N=196, d=512, L=16)
+
     def cell_for(self, key, batch):
+        """The training cell of shape-key `key`, fed with `batch`.
+
+        The reference cell captures its input tensors at construction (mac_cell.py:59-79), and so does `MACCell`; the
+        trainer therefore owns PERSISTENT input buffers per key and copies the caller's batch into them on every call, so
+        a cached cell can never run on the tensors of an earlier batch.  A batch that already lives in these
+        buffers (`full_forward_backward` writes into them directly) is not copied again.  At most MAX_CACHED_CELLS keys
+        are kept (least recently used first out): callers with many distinct shapes -- e.g. one per trimmed question
+        length -- should bucket / pad instead (attention masks the padding)."""
         from .mac_cell import MACCell
-        if key not in self._cells:
+        names = ("vecQuestions", "questionWords", "questionCntxWords", "questionLengths", "knowledgeBase")
+        ent = self._cells.pop(key, None)
+        if ent is None:
+            bufs = {}
+            for n in names:
+                src = batch[n]
+                bufs[n] = src.to(torch.int32).clone().contiguous() if n == "questionLengths" else src.clone().contiguous()
             dm, dr, dw = self.dropouts
-            self._cells[key] = MACCell(batch["vecQuestions"], batch["questionWords"], batch["questionCntxWords"],
-                                       batch["questionLengths"], batch["knowledgeBase"], dm, dr, dw,
-                                       batch["knowledgeBase"].shape[0], True, config=self.cfg, params=self.params,
-                                       prec=self.prec, save_for_backward=True)
-        return self._cells[key]
+            cell = MACCell(bufs["vecQuestions"], bufs["questionWords"], bufs["questionCntxWords"], bufs["questionLengths"],
+                           bufs["knowledgeBase"], dm, dr, dw, bufs["knowledgeBase"].shape[0], True, config=self.cfg,
+                           params=self.params, prec=self.prec, save_for_backward=True)
+            ent = (cell, bufs)
+            while len(self._cells) >= self.MAX_CACHED_CELLS:
+                old_key = next(iter(self._cells))
+                del self._cells[old_key]
+                if hasattr(self, "_full_bufs"):
+                    self._full_bufs.pop(old_key, None)
+        else:
+            cell, bufs = ent
+            for n in names:
+                src = batch[n]
+                if src.data_ptr() != bufs[n].data_ptr():
+                    if tuple(src.shape) != tuple(bufs[n].shape):
+                        raise ValueError("batch tensor %s has shape %s but key %r was built for %s"
+                                         % (n, tuple(src.shape), key, tuple(bufs[n].shape)))
+                    bufs[n].copy_(src)
+        self._cells[key] = ent                 # (re-)insert as most recently used
+        return ent[0]
 
     def grads(self, key, batch, t_control, t_memory, global_batch):
         """Forward + backward of the local shard into the flat bucket (not yet reduced)."""
@@ -149,7 +180,7 @@ class DPTrainer(object):
         control, memory = mac_network(cell, self.L)
         self.bucket.zero_()
         gviews = self._views_of(self.bucket, self.params.specs, self.params.offsets)
-        logits, losses, _ = self.out.forward(memory, batch["vecQuestions"], answers, step=self.step_id,
+        logits, losses, _ = self.out.forward(memory, getattr(cell, "vecQuestions", batch["vecQuestions"]), answers, step=self.step_id,
                                              loss_scale=1.0 / float(global_batch))
         d_mem, d_q = torch.zeros_like(memory), torch.zeros_like(memory)
         self.out.backward(gviews, d_mem, d_q)
@@ -173,23 +204,17 @@ class DPTrainer(object):
         words, cntx, vecq = self.enc.forward(data["questions"], data["questionLengths"], step=self.step_id,
                                              save_for_backward=True)
         kb = self.stem.forward(data["images"], keep=self.stem_dropout, step=self.step_id, save_for_backward=True)
-        # the cell captures its inputs at construction (mac_cell.py:59-79): persistent buffers, refreshed per step
-        bufs = self._full_bufs.get(key)
-        if bufs is None:
-            bufs = {"vecQuestions": torch.empty_like(vecq), "questionWords": torch.empty_like(words),
-                    "questionCntxWords": torch.empty_like(cntx), "knowledgeBase": torch.empty_like(kb),
-                    "questionLengths": torch.empty_like(data["questionLengths"], dtype=torch.int32)}
-            self._full_bufs[key] = bufs
-        for name, src in (("vecQuestions", vecq), ("questionWords", words), ("questionCntxWords", cntx),
-                          ("knowledgeBase", kb), ("questionLengths", data["questionLengths"])):
-            bufs[name].copy_(src)
+        # the cell captures its inputs at construction (mac_cell.py:59-79): cell_for owns persistent buffers per key and
+        # copies this step's encoder / stem outputs into them
+        bufs = {"vecQuestions": vecq, "questionWords": words, "questionCntxWords": cntx, "knowledgeBase": kb,
+                "questionLengths": data["questionLengths"]}
         cell = self.cell_for(key, bufs)
         cell._rw.clear()
         cell.seed = seed
         control, memory = mac_network(cell, self.L)
         self.bucket.zero_()
         gviews = self._views_of(self.bucket, self.params.specs, self.params.offsets)
-        logits, losses, _ = self.out.forward(memory, bufs["vecQuestions"], data["answers"], step=self.step_id,
+        logits, losses, _ = self.out.forward(memory, getattr(cell, "vecQuestions", vecq), data["answers"], step=self.step_id,
                                              loss_scale=1.0 / float(global_batch))
         d_mem, d_q = torch.zeros_like(memory), torch.zeros_like(memory)
         self.out.backward(gviews, d_mem, d_q)

@@ -203,6 +203,10 @@ class MACCell(object):
         if self.save_for_backward and (not (self._fused_read and self._fused_write)
                                        or not (self._hoist or recurrent_ctrl_ok)):
             raise NotImplementedError("backward is implemented on the fused path (DESIGN.md section 9)")
+        if self.save_for_backward and (c.controlInWordsProj or c.controlOutWordsProj):
+            # the hand-written backward does not propagate through the shared wordsProj layer (mac_cell.py:578-581): its
+            # weight / bias gradients would silently stay zero and dL/dwords would be wrong
+            raise NotImplementedError("backward through controlInWordsProj / controlOutWordsProj is not implemented")
         if self.save_for_backward and self.prec != PREC["fp32"] and (d % 128 or self._kb_given_bf16):
             raise NotImplementedError("training forward on tensor cores needs d % 128 == 0 and an fp32 knowledge base")
         if self.prec != PREC["fp32"] and not self._fused_read:

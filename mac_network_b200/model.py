@@ -107,7 +107,7 @@ class MACnet(object):
         gradNorm = -1
         if train:
             logits, losses = t.train_step_full((B, S), dev, global_batch=B * t.world)
-            self.macCell = t._cells[(B, S)]
+            self.macCell = t._cells[(B, S)][0]
             gradNorm = float(t.norm[0].item())
             self._out.invalidate()
             self._stem._packed.clear()
