@@ -499,6 +499,411 @@ read_step_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_constan
   }
 }
 
+// =====================================================================================================================
+// cta_group::2 form of the PAIR case: the two CTAs of a sample's cluster issue ONE tcgen05.mma per k-step (M = 256: rank r
+// contributes its 128 rows, N = 256 per output half), so each CTA stages only HALF of every weight tile -- 512 KB instead
+// of 1 MB of L2 -> SM traffic per CTA and step (the chip-wide L2 read rate, ~6300 B/clk, is what bounds the 1-CTA form:
+// 128 CTAs x 1.4 MB per step), and each SM's shared memory feeds 8 KB instead of 12 KB per MMA (SS-mode operand limit).
+//   * A tiles (own 128 rows of P) land on the CTA's OWN a_full barrier, are scaled by its own workers, and every worker
+//     warp of BOTH CTAs arrives on the LEADER's a_ready (32 arrivals, release/acquire at cluster scope).
+//   * B half tiles ([128 x 64] of the [256 x 64] block: rows 256 h + 128 rank) complete on the LEADER's b_full
+//     (cp.async.bulk.tensor ... .cta_group::2); the leader's tcgen05.commit multicasts to both CTAs' empty barriers.
+//   * H stays local (each CTA's 128 rows); hk_ready on the leader counts both CTAs' warps.
+// Shared memory: GEMM 1 = 4 stages x (A | B half 0 | B half 1) over units 0..11; H over units 0..7; GEMM 2 streams Wm2
+// through 5 single-unit slots (units 8..12), started once GEMM 1 is complete.
+// =====================================================================================================================
+constexpr int RS2_STAGES = 4;
+constexpr int RS2_B2_SLOTS = 5;
+constexpr int RS2_SMEM_BYTES = RS_UNITS * RS_UNIT + 1024 /*align*/ + 512 /*barriers*/ + RS_PAR_FLOATS * 4 + 4 * 128 * 4 +
+                               128 * 4 + 64 + RS_D * 4;
+
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(smem_u32(bar)), "r"(cta)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+
+__global__ void __launch_bounds__(RS_THREADS, 1)
+read_step2_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ CUtensorMap map_w1,
+                  const __grid_constant__ CUtensorMap map_w2, const ReadStepParams p) {
+  extern __shared__ unsigned char smem_dyn[];
+  const uint32_t base_u32 = smem_u32(smem_dyn);
+  const uint32_t pad = (1024u - (base_u32 & 1023u)) & 1023u;
+  unsigned char* tiles = smem_dyn + pad;
+  unsigned char* h_tile = tiles;                                 // units 0..7 (after GEMM 1)
+  unsigned char* b2_slots = tiles + 8 * RS_UNIT;                 // units 8..12
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + RS_UNITS * RS_UNIT);
+  uint64_t* a_full = bars;                         // [4] own:    TMA A -> own workers
+  uint64_t* a_ready = bars + 4;                    // [4] leader: workers of both CTAs -> MMA (32 arrivals)
+  uint64_t* b_full = bars + 8;                     // [4] leader: B halves of both CTAs -> MMA
+  uint64_t* s_empty = bars + 12;                   // [4] own:    MMA (multicast commit) -> TMA
+  uint64_t* b2_full = bars + 16;                   // [5] leader
+  uint64_t* b2_empty = bars + 21;                  // [5] own
+  uint64_t* g1_done = bars + 26;                   // own (multicast commit)
+  uint64_t* hk_ready = bars + 27;                  // [8] leader (32 arrivals)
+  uint64_t* g2_done = bars + 35;                   // [2] own (multicast commit)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 37);
+  float* par = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bars) + 512);
+  float* s_part = par + RS_PAR_FLOATS;
+  float* s_att = s_part + 4 * 128;
+  float* s_xch = s_att + 128;
+  float* s_peer = s_xch + 16;
+  float* s_red = reinterpret_cast<float*>(tiles + 9 * RS_UNIT);          // [8][512] over units 9..12 (after GEMM 2)
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int N = p.N;
+  const uint32_t rank = cluster_rank();
+  const int s0 = blockIdx.x >> 1;
+  const int row0 = s0 * N + (int)rank * 128;
+  const int valid = min(128, N - (int)rank * 128);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_p);
+    tma_prefetch_desc(&map_w1);
+    tma_prefetch_desc(&map_w2);
+#pragma unroll
+    for (int i = 0; i < RS2_STAGES; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_ready[i], 2 * RS_WORKER_WARPS);
+      mbar_init(&b_full[i], 1);
+      mbar_init(&s_empty[i], 1);
+    }
+#pragma unroll
+    for (int i = 0; i < RS2_B2_SLOTS; ++i) {
+      mbar_init(&b2_full[i], 1);
+      mbar_init(&b2_empty[i], 1);
+    }
+    mbar_init(g1_done, 1);
+#pragma unroll
+    for (int i = 0; i < RS_KB; ++i) mbar_init(&hk_ready[i], 2 * RS_WORKER_WARPS);
+    mbar_init(&g2_done[0], 1);
+    mbar_init(&g2_done[1], 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc2(tmem_ptr, 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_barrier();                               // #0: both CTAs' barriers and tensor memory exist
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer (both CTAs)
+    if (elect_one()) {
+      {
+        const size_t bytes = (size_t)valid * RS_D * 2;
+        const char* q0 = reinterpret_cast<const char*>(p.Q + (size_t)row0 * RS_D);
+        const char* k0 = reinterpret_cast<const char*>(p.kb + (size_t)row0 * RS_D);
+        for (size_t o = 0; o < bytes; o += 16384) {
+          const uint32_t n = (uint32_t)min((size_t)16384, bytes - o);
+          l2_prefetch_bulk(q0 + o, n);
+          l2_prefetch_bulk(k0 + o, n);
+        }
+      }
+      for (int kb = 0; kb < RS_KB; ++kb) {
+        const int s = kb % RS2_STAGES, n = kb / RS2_STAGES;
+        unsigned char* st = tiles + s * 3 * RS_UNIT;
+        mbar_wait(&s_empty[s], (n & 1) ^ 1);
+        mbar_expect_tx(&a_full[s], RS_UNIT);
+        tma_load_2d(st, &map_p, kb * TC_BK, row0, &a_full[s]);
+        if (rank == 0) mbar_expect_tx(&b_full[s], 4 * RS_UNIT);        // two halves from each of the two CTAs
+        tma2_load_2d(st + RS_UNIT, &map_w1, kb * TC_BK, (int)rank * 128, &b_full[s]);
+        tma2_load_2d(st + 2 * RS_UNIT, &map_w1, kb * TC_BK, 256 + (int)rank * 128, &b_full[s]);
+      }
+      mbar_wait(g1_done, 0);                       // the GEMM-2 ring overlays stages 2 and 3
+      for (int i = 0; i < 2 * RS_KB; ++i) {
+        const int h = i >> 3, kb = i & 7;
+        const int sl = i % RS2_B2_SLOTS, n = i / RS2_B2_SLOTS;
+        mbar_wait(&b2_empty[sl], (n & 1) ^ 1);
+        if (rank == 0) mbar_expect_tx(&b2_full[sl], 2 * RS_UNIT);
+        tma2_load_2d(b2_slots + sl * RS_UNIT, &map_w2, kb * TC_BK, h * 256 + (int)rank * 128, &b2_full[sl]);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer (leader CTA only)
+    if (rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(256, 256);
+      for (int kb = 0; kb < RS_KB; ++kb) {
+        const int s = kb % RS2_STAGES, n = kb / RS2_STAGES;
+        mbar_wait_cluster(&a_ready[s], n & 1);
+        mbar_wait(&b_full[s], n & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t st = smem_u32(tiles + s * 3 * RS_UNIT);
+          const uint64_t adesc = make_sw128_kmajor_desc(st);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const uint64_t bdesc = make_sw128_kmajor_desc(st + (1 + h) * RS_UNIT);
+#pragma unroll
+            for (int k = 0; k < TC_BK / 16; ++k)
+              umma2_bf16(tmem_base + h * 256, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+          }
+          umma2_commit_mc(&s_empty[s], 0x3);
+          if (kb == RS_KB - 1) umma2_commit_mc(g1_done, 0x3);
+        }
+        __syncwarp();
+      }
+      for (int i = 0; i < 2 * RS_KB; ++i) {
+        const int h = i >> 3, kb = i & 7;
+        const int sl = i % RS2_B2_SLOTS, n = i / RS2_B2_SLOTS;
+        if (h == 0) {
+          if (kb == 0) {
+            mbar_wait_cluster(&hk_ready[0], 0);
+            mbar_wait_cluster(&hk_ready[1], 0);
+            mbar_wait_cluster(&hk_ready[2], 0);
+            mbar_wait_cluster(&hk_ready[3], 0);
+          } else if (kb >= 4) {
+            mbar_wait_cluster(&hk_ready[kb], 0);
+          }
+        }
+        mbar_wait(&b2_full[sl], n & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t adesc = make_sw128_kmajor_desc(smem_u32(h_tile + kb * RS_UNIT));
+          const uint64_t bdesc = make_sw128_kmajor_desc(smem_u32(b2_slots + sl * RS_UNIT));
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k)
+            umma2_bf16(tmem_base + h * 256, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+          umma2_commit_mc(&b2_empty[sl], 0x3);
+          if (kb == RS_KB - 1) umma2_commit_mc(&g2_done[h], 0x3);
+        }
+        __syncwarp();
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================================================== workers (both CTAs; own 128 rows)
+    const int wt = threadIdx.x - 64;
+    const int q = warp & 3;
+    const int cg = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    if (wt == 0) rs_stamp(p, 0);
+    for (int i = wt; i < RS_D; i += RS_WORKERS) {
+      par[i] = __ldg(p.bm2 + i);
+      par[RS_D + i] = __ldg(p.wr + i);
+      par[2 * RS_D + i] = __ldg(p.ctrl + (size_t)s0 * RS_D + i);
+    }
+    const bool row_ok = row < valid;
+    const __nv_bfloat16* qrow = p.Q + (size_t)(row0 + (row_ok ? row : 0)) * RS_D + cg * 16;
+    uint4 qv[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      qv[2 * i] = ldg_nc_v4(qrow + 64 * i);
+      qv[2 * i + 1] = ldg_nc_v4(qrow + 64 * i + 8);
+    }
+    // ---- GEMM 1 operand path: own P k-block -> P * y_b in place (see read_step_kernel)
+    {
+      const int r_a = wt >> 3, r_b = r_a + 64;
+      const int pc = wt & 7;
+      const int lc_a = pc ^ (r_a & 7), lc_b = pc ^ (r_b & 7);
+      const bool ok_a = r_a < valid, ok_b = r_b < valid;
+      const float* y_a = p.y + (size_t)s0 * RS_D + lc_a * 8;
+      const float* y_b = p.y + (size_t)s0 * RS_D + lc_b * 8;
+      auto scale16 = [](uint4 v, const float4 f0, const float4 f1) {
+        uint4 o;
+        o.x = pack_bf16(bf16lo(v.x) * f0.x, bf16hi(v.x) * f0.y);
+        o.y = pack_bf16(bf16lo(v.y) * f0.z, bf16hi(v.y) * f0.w);
+        o.z = pack_bf16(bf16lo(v.z) * f1.x, bf16hi(v.z) * f1.y);
+        o.w = pack_bf16(bf16lo(v.w) * f1.z, bf16hi(v.w) * f1.w);
+        return o;
+      };
+      for (int kb = 0; kb < RS_KB; ++kb) {
+        const int s = kb % RS2_STAGES, n = kb / RS2_STAGES;
+        const float4 ya0 = __ldg(reinterpret_cast<const float4*>(y_a + kb * TC_BK));
+        const float4 ya1 = __ldg(reinterpret_cast<const float4*>(y_a + kb * TC_BK + 4));
+        const float4 yb0 = __ldg(reinterpret_cast<const float4*>(y_b + kb * TC_BK));
+        const float4 yb1 = __ldg(reinterpret_cast<const float4*>(y_b + kb * TC_BK + 4));
+        mbar_wait(&a_full[s], n & 1);
+        uint4* t = reinterpret_cast<uint4*>(tiles + s * 3 * RS_UNIT);
+        if (ok_a) t[wt] = scale16(t[wt], ya0, ya1);
+        if (ok_b) t[wt + 512] = scale16(t[wt + 512], yb0, yb1);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(&a_ready[s], 0u);
+      }
+    }
+
+    // ---- epilogue 1
+    const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+    if (wt == 0) rs_stamp(p, 1);
+    mbar_wait(g1_done, 0);
+    tc_fence_after();
+    if (wt == 0) rs_stamp(p, 2);
+#pragma unroll
+    for (int kb2 = 0; kb2 < RS_KB; ++kb2) {
+      uint32_t r[16];
+      tmem_ld16(tlane + kb2 * 64 + cg * 16, r);
+      tmem_ld_wait();
+      const uint4 qa = qv[(2 * kb2) & 7], qb = qv[(2 * kb2 + 1) & 7];
+      if (kb2 < 4) {
+        qv[(2 * kb2) & 7] = ldg_nc_v4(qrow + 64 * (kb2 + 4));
+        qv[(2 * kb2 + 1) & 7] = ldg_nc_v4(qrow + 64 * (kb2 + 4) + 8);
+      }
+      const uint32_t qw[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+      uint32_t w[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        w[j] = pack_bf16(elu_fast(__uint_as_float(r[2 * j]) + bf16lo(qw[j])),
+                         elu_fast(__uint_as_float(r[2 * j + 1]) + bf16hi(qw[j])));
+      const int lc = cg * 2;
+      unsigned char* hrow = h_tile + kb2 * RS_UNIT + row * 128;
+      *reinterpret_cast<uint4*>(hrow + ((lc ^ (row & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+      *reinterpret_cast<uint4*>(hrow + (((lc + 1) ^ (row & 7)) << 4)) = make_uint4(w[4], w[5], w[6], w[7]);
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(&hk_ready[kb2], 0u);
+    }
+    if (wt == 0) rs_stamp(p, 3);
+
+    // ---- epilogue 2
+    rs_worker_bar();
+    const float* crow = par + 2 * RS_D;
+    float part = 0.f;
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {
+      mbar_wait(&g2_done[h], 0);
+      tc_fence_after();
+      if (wt == 0 && h == 1) rs_stamp(p, 4);
+#pragma unroll 2
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t r[16];
+        const int c0 = h * 256 + cg * 64 + 16 * ch;
+        tmem_ld16(tlane + c0, r);
+        tmem_ld_wait();
+        const float4* b4 = reinterpret_cast<const float4*>(par + c0);
+        const float4* w4 = reinterpret_cast<const float4*>(par + RS_D + c0);
+        const float4* c4 = reinterpret_cast<const float4*>(crow + c0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 bb = b4[j], ww = w4[j], cc = c4[j];
+          part = fmaf(elu_fast((__uint_as_float(r[4 * j]) + bb.x) * cc.x), ww.x, part);
+          part = fmaf(elu_fast((__uint_as_float(r[4 * j + 1]) + bb.y) * cc.y), ww.y, part);
+          part = fmaf(elu_fast((__uint_as_float(r[4 * j + 2]) + bb.z) * cc.z), ww.z, part);
+          part = fmaf(elu_fast((__uint_as_float(r[4 * j + 3]) + bb.w) * cc.w), ww.w, part);
+        }
+      }
+    }
+    tc_fence_before();
+    s_part[cg * 128 + row] = part;
+    rs_worker_bar();
+    if (wt < 128) s_att[wt] = s_part[wt] + s_part[128 + wt] + s_part[256 + wt] + s_part[384 + wt] + p.br;
+    rs_worker_bar();
+    if (wt == 0) rs_stamp(p, 5);
+
+    // ---- knowledge-base rows of the weighted sum (issued before the softmax, consumed after it)
+    const int nrows = valid;
+    const int rg = wt >> 6, cq = wt & 63;
+    uint4 v[16];
+    {
+      const __nv_bfloat16* kbase = p.kb + (size_t)row0 * RS_D + cq * 8;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int n = rg + RS_RED_GROUPS * i;
+        v[i] = n < nrows ? ldg_nc_v4(kbase + (size_t)n * RS_D) : make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+    // ---- softmax over the sample's N rows: local statistics, exchange with the partner, final weights
+    const int wi = warp - 2;
+    float e_lane[4] = {0.f, 0.f, 0.f, 0.f};
+    float mx = -INFINITY, sum = 0.f;
+    if (wi == 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int n = lane + 32 * i;
+        if (n < nrows) mx = fmaxf(mx, s_att[n]);
+      }
+      mx = warp_max(mx);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int n = lane + 32 * i;
+        if (n < nrows) {
+          e_lane[i] = __expf(s_att[n] - mx);
+          sum += e_lane[i];
+        }
+      }
+      sum = warp_sum(sum);
+      if (lane == 0) {
+        s_xch[2 * rank] = mx;
+        s_xch[2 * rank + 1] = sum;
+        st_cluster_f32(&s_xch[2 * rank], rank ^ 1u, mx);
+        st_cluster_f32(&s_xch[2 * rank + 1], rank ^ 1u, sum);
+      }
+    }
+    cluster_barrier();                             // #1
+    if (wi == 0) {
+      const float m0 = s_xch[0], z0 = s_xch[1], m1 = s_xch[2], z1 = s_xch[3];
+      const float M = fmaxf(m0, m1);
+      const float Z = z0 * __expf(m0 - M) + z1 * __expf(m1 - M);
+      const float scale = __expf(mx - M) / Z;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int n = lane + 32 * i;
+        if (n < nrows) {
+          const float a = e_lane[i] * scale;
+          s_att[n] = a;
+          p.att[(size_t)s0 * N + (int)rank * 128 + n] = a;
+        }
+      }
+    }
+    rs_worker_bar();
+    if (wt == 0) rs_stamp(p, 6);
+    {
+      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int n = rg + RS_RED_GROUPS * i;
+        const float a = n < nrows ? s_att[n] : 0.f;
+        acc[0] = fmaf(a, bf16lo(v[i].x), acc[0]); acc[1] = fmaf(a, bf16hi(v[i].x), acc[1]);
+        acc[2] = fmaf(a, bf16lo(v[i].y), acc[2]); acc[3] = fmaf(a, bf16hi(v[i].y), acc[3]);
+        acc[4] = fmaf(a, bf16lo(v[i].z), acc[4]); acc[5] = fmaf(a, bf16hi(v[i].z), acc[5]);
+        acc[6] = fmaf(a, bf16lo(v[i].w), acc[6]); acc[7] = fmaf(a, bf16hi(v[i].w), acc[7]);
+      }
+      float4* dst = reinterpret_cast<float4*>(s_red + rg * RS_D + cq * 8);
+      dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+      rs_worker_bar();
+      float t = 0.f;
+#pragma unroll
+      for (int g = 0; g < RS_RED_GROUPS; ++g) t += s_red[g * RS_D + wt];
+      if (rank == 1) st_cluster_f32(&s_peer[wt], 0u, t);
+      cluster_barrier();                           // #2
+      if (rank == 0) p.info[(size_t)s0 * RS_D + wt] = t + s_peer[wt];
+    }
+    if (wt == 0) rs_stamp(p, 7);
+  }
+  if (warp < 2) {                                  // the producer / MMA warps take part in cluster barriers #1 and #2
+    __syncwarp();
+    cluster_barrier();
+    cluster_barrier();
+  }
+
+  // ---- teardown: neither CTA frees its tensor memory while the pair may still use it
+  tc_fence_before();
+  __syncthreads();
+  cluster_barrier();                               // #3
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, 512);
+  }
+}
+
 // profiling hook (not part of the ABI header): device buffer [grid][8] that subsequent launches fill with clock64 stamps
 inline long long*& read_step_dbg_ptr() { static long long* p = nullptr; return p; }
 
@@ -525,8 +930,35 @@ inline int read_step_launch(const void* inv, const void* kb_bf16, const float* y
   p.Q = reinterpret_cast<const __nv_bfloat16*>(ibase + slab);
   p.kb = reinterpret_cast<const __nv_bfloat16*>(kb_bf16);
   p.att = att; p.info = info; p.dbg = read_step_dbg_ptr();
-  static bool attr_set[2] = {false, false};
-  if (N > 128) {
+  static bool attr_set[3] = {false, false, false};
+  static const bool pair_mma = !(getenv("MAC_READ_PAIR_MMA") && atoi(getenv("MAC_READ_PAIR_MMA")) == 0);
+  if (N > 128 && pair_mma) {
+    // weight boxes are [128 x 64] halves here: separate tensor maps
+    CUtensorMap hw1, hw2;
+    st = make_tmap_2d(&hw1, w->Wm_bf16, 1, (uint64_t)d, (uint64_t)d, (uint64_t)2 * d * 2, 128, TC_BK, 1);
+    if (st != MAC_OK) return st;
+    st = make_tmap_2d(&hw2, w->Wm2_bf16, 1, (uint64_t)d, (uint64_t)d, (uint64_t)d * 2, 128, TC_BK, 1);
+    if (st != MAC_OK) return st;
+    auto kern = read_step2_kernel;
+    if (!attr_set[2]) {
+      MAC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, RS2_SMEM_BYTES));
+      attr_set[2] = true;
+    }
+    p.spc = 1;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * B, 1, 1);
+    cfg.blockDim = dim3(RS_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = RS2_SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    MAC_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, mp, hw1, hw2, p));
+  } else if (N > 128) {
     auto kern = read_step_kernel<true>;
     if (!attr_set[0]) {
       MAC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_SMEM_BYTES));

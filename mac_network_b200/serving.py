@@ -29,6 +29,46 @@ def usable_cpus():
     return max(1, n)
 
 
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        if "-" in part:
+            a, b = part.split("-")
+            cpus.update(range(int(a), int(b) + 1))
+        else:
+            cpus.add(int(part))
+    return cpus
+
+
+def bind_to_gpu_numa(device_index):
+    """Pin this process (and the threads / pinned host buffers it creates afterwards: first touch) to the NUMA node the
+    GPU's PCIe root hangs off.  One process per GPU on a 2-socket host otherwise leaves half of the ranks staging their
+    batches through the remote socket (SCALE_r01: end-to-end efficiency 0.38 at 8 GPUs with GPUs 4-7 on node 1).
+    Returns a description dict; never raises (a container without /sys access simply stays unbound)."""
+    info = {"bound": False}
+    try:
+        prop = torch.cuda.get_device_properties(device_index)
+        bus = "%04x:%02x:%02x.0" % (getattr(prop, "pci_domain_id", 0), prop.pci_bus_id, prop.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as f:
+            node = int(f.read().strip())
+        info.update(pci=bus, numa_node=node)
+        if node < 0:
+            return info
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            node_cpus = _parse_cpulist(f.read())
+        mine = set(os.sched_getaffinity(0))
+        target = sorted(node_cpus & mine)
+        if not target:
+            return info
+        os.sched_setaffinity(0, target)
+        info.update(bound=True, cpus=len(target))
+    except Exception as exc:           # noqa: BLE001 -- advisory only
+        info["error"] = repr(exc)[:120]
+    return info
+
+
 class _Slot(object):
     def __init__(self, cfg, params, shape, prec, host_kb_bf16, use_graph, fold_y=None):
         B, S, N, d, L = shape

@@ -1,6 +1,6 @@
 """`model.MACnet.runBatch` (the reference's per-batch call, model.py:732-760) on the GPU.  A composition of classes that each
 have their own hardware-validated parity tests (encoder, stem, cell, output unit, trainer); the composition itself was written
-after the round's GPU budget was spent, hence `xfail(strict=False)` and a file name that sorts last (see
+after round 1's GPU budget was spent (then `xfail(strict=False)`; XPASSed on the B200, gating since round 2; see
 tests/test_zzz_tensor_core_training.py)."""
 import numpy as np
 import pytest
@@ -8,8 +8,7 @@ import pytest
 from tests._util import max_rel
 from tests.test_full_model import _oracle_loss
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="composition not yet run on hardware (round-1 GPU budget spent)")]
+pytestmark = pytest.mark.gpu       # round 2: gating (all of these XPASSed on the B200 at the end of round 1)
 
 
 def _batch(B, S, V, C, H, W, A, seed):

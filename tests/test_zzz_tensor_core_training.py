@@ -2,8 +2,7 @@
 budget of the round was spent: every CUDA entry point they use is validated elsewhere in this suite (mac_linear_tc_fwd,
 mac_pack_weight_bf16, mac_cast_bf16, the fp32 element-wise kernels of the backward), but their COMPOSITION
 (`mac_read_bwd_tc`, the bf16 training forward with widened saved activations) has not yet run on a B200.  The tests are
-therefore `xfail(strict=False)`: the first hardware run reports XPASS / XFAIL without gating the suite, and this file sorts
-last so that nothing runs after it in the same process.  Tolerances are mixed-precision ones (bf16 operands, fp32
+were `xfail(strict=False)` in round 1; all of them XPASSed on the driver's B200 (GPUTEST_r01), so since round 2 they GATE.  Tolerances are mixed-precision ones (bf16 operands, fp32
 accumulation), stated per test."""
 import numpy as np
 import pytest
@@ -14,8 +13,7 @@ from mac_network_b200.params import init_params, perturb_biases
 from mac_network_b200.synthetic import make_inputs
 from tests._util import max_rel
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="composition not yet run on hardware (round-1 GPU budget spent)")]
+pytestmark = pytest.mark.gpu       # round 2: gating (all of these XPASSed on the B200 at the end of round 1)
 
 
 @pytest.mark.parametrize("prec,tc,tol", [("fp32", True, 3e-2), ("bf16", False, 3e-2), ("bf16", True, 5e-2)])
