@@ -228,6 +228,22 @@ int mac_pack_weight_bf16(const float* W, void* Wt_bf16, int K, int n_out, mac_st
 int mac_linear_tc_fwd(const void* x_bf16, const void* wt_bf16, const float* b, int act, void* y, int y_is_bf16,
                       int M, int K, int n_out, mac_stream_t stream);
 
+/* The cell's M <= 128 projections on tensor cores (csrc/skinny_tc.cuh) -- ops.linear at mac_cell.py:442-448 (qInput,
+ * qInput{i}), 322 (ctrlProj), 352 (newMemory), 363 (gate) and ops.py:689 (projY), the calls whose M is the batch:
+ *   y[M, n_out] = epilogue( concat_k(x_0 .. x_{nseg-1})[M, K] @ W + b + bias_const ),  M <= 128, fp32 in / fp32 out.
+ * mac_pack_weight_bf16_split: fp32 W[K, n_out] -> bf16 hi and lo halves, both [n_out, K] (K-major), W ~= hi + lo.
+ * With wt_lo != NULL the product is three tcgen05 passes (x_hi W_hi + x_lo W_hi + x_hi W_lo, the activations split in the
+ * kernel) accumulated in fp32 in tensor memory: fp32-class accuracy (~1e-5) on the tensor pipe, so the recurrent state
+ * does not pass through bf16.  wt_lo == NULL: one plain bf16 pass.
+ * Epilogue: act in MAC_ACT_*; y2 != NULL sends columns >= n_split to y2[m, n - n_split] (the folded write unit, see
+ * mac_write_fwd_next_y); gate_new != NULL selects the write gate z = sigmoid(t), y = gate_new*z + gate_old*(1-z), z stored
+ * to gate_z when given (mac_cell.py:358-367).  Needs k_segs[i] % 64 == 0, n_out % 32 == 0, else MAC_ERR_UNSUPPORTED. */
+int mac_pack_weight_bf16_split(const float* W, void* hi_bf16, void* lo_bf16, int K, int n_out, mac_stream_t stream);
+int mac_linear_tc_small_fwd(const float* const* x_segs, const int* k_segs, const int* ldx, int nseg,
+                            const void* wt_hi, const void* wt_lo, const float* b, float bias_const, int act,
+                            float* y, int ldy, float* y2, int n_split, const float* gate_new, const float* gate_old,
+                            float* gate_z, int M, int n_out, mac_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Backward (fp32 path).  The reference differentiates the graph with TF autodiff (model.py:626-636); each forward
  * entry point above has a counterpart here (math: SURVEY.md Appendix E).  "+=" outputs accumulate (zero them once per

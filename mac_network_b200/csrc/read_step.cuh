@@ -57,7 +57,9 @@ struct ReadStepParams {
   const __nv_bfloat16* kb;          // [B*N, d]  bf16 knowledge base
   float* att;                       // [B, N]
   float* info;                      // [B, d]
-  long long* dbg;                   // profiling only (mac_dbg_read_step_timestamps): [gridDim.x][8] SM-clock stamps, or NULL
+  int dbg_flags;                    // profiling only (mac_dbg_read_step_flags; results are WRONG when set): 1 skip the P*y
+                                    // smem pass, 2 skip the GEMM-1/2 MMAs, 4 skip the Wm loads of GEMM 1 (pair kernel)
+  long long* dbg;                   // profiling only (mac_dbg_read_step_timestamps): [gridDim.x][64] SM-clock stamps, or NULL
 };
 
 __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
@@ -79,7 +81,7 @@ __device__ __forceinline__ void st_cluster_f32(const float* local_addr, uint32_t
 __device__ __forceinline__ float bf16lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
 __device__ __forceinline__ void rs_stamp(const ReadStepParams& p, int slot) {
-  if (p.dbg) p.dbg[(size_t)blockIdx.x * 8 + slot] = clock64();
+  if (p.dbg) p.dbg[(size_t)blockIdx.x * 64 + slot] = clock64();
 }
 __device__ __forceinline__ void rs_worker_bar() { asm volatile("bar.sync 1, %0;" ::"n"(RS_WORKERS) : "memory"); }
 
@@ -510,33 +512,30 @@ read_step_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_constan
 //     (cp.async.bulk.tensor ... .cta_group::2); the leader's tcgen05.commit multicasts to both CTAs' empty barriers.
 //   * H stays local (each CTA's 128 rows); hk_ready on the leader counts both CTAs' warps.
 // Shared memory: GEMM 1 = 4 stages x (A | B half 0 | B half 1) over units 0..11; H over units 0..7; GEMM 2 streams Wm2
-// through 5 single-unit slots (units 8..12), started once GEMM 1 is complete.
+// through 5 single-unit slots (units 8..12).  Unit 12 is outside the GEMM-1 ring, so the FIRST Wm2 tile is requested at
+// kernel start: a tensor map's first use costs a ~4.5k-clock descriptor fetch (measured: GEMM 2's first MMA was issued
+// 5.9k clocks after GEMM 1 completed), which this hides; the other slots are filled once GEMM 1 is complete.
+// Tail: ONE cluster barrier -- rank 1 ships its local softmax statistics, its un-normalised exp values and its
+// un-normalised partial weighted sum to rank 0, which combines and writes att / info for the whole sample.
 // =====================================================================================================================
 constexpr int RS2_STAGES = 4;
 constexpr int RS2_B2_SLOTS = 5;
 constexpr int RS2_SMEM_BYTES = RS_UNITS * RS_UNIT + 1024 /*align*/ + 512 /*barriers*/ + RS_PAR_FLOATS * 4 + 4 * 128 * 4 +
-                               128 * 4 + 64 + RS_D * 4;
+                               128 * 4 + 64 + RS_D * 4 + 128 * 4 /*partner's exp values*/;
 
+// arrive on the barrier at the same offset in CTA `cta` of the cluster.  Default semantics (release at CTA scope), as
+// CUTLASS's ClusterBarrier::arrive(cta_id): the data the barrier guards is this CTA's OWN shared memory, published to the
+// async proxy by fence.proxy.async before the arrive and read by the pair's tcgen05.mma -- an explicit .release.cluster
+// costs a cluster-scope fence (L1 invalidate) per arrive and made the 2-CTA form slower than the 1-CTA one (52k vs 44k clk).
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
       ::"r"(smem_u32(bar)), "r"(cta)
       : "memory");
 }
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-  } while (!ok);
-}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); }
 
 __global__ void __launch_bounds__(RS_THREADS, 1)
 read_step2_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ CUtensorMap map_w1,
@@ -562,7 +561,8 @@ read_step2_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_consta
   float* s_part = par + RS_PAR_FLOATS;
   float* s_att = s_part + 4 * 128;
   float* s_xch = s_att + 128;
-  float* s_peer = s_xch + 16;
+  float* s_peer = s_xch + 16;                      // [512] rank 1's un-normalised partial weighted sum (read by rank 0)
+  float* s_peer_e = s_peer + RS_D;                 // [128] rank 1's un-normalised exp values (read by rank 0)
   float* s_red = reinterpret_cast<float*>(tiles + 9 * RS_UNIT);          // [8][512] over units 9..12 (after GEMM 2)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -605,7 +605,33 @@ read_step2_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_consta
   if (warp == 0) {
     // ===================================================== TMA producer (both CTAs)
     if (elect_one()) {
+      auto issue_stage = [&](int kb) {
+        const int s = kb % RS2_STAGES, n = kb / RS2_STAGES;
+        unsigned char* st = tiles + s * 3 * RS_UNIT;
+        mbar_wait(&s_empty[s], (n & 1) ^ 1);
+        rs_stamp(p, 16 + kb);                      // stage free: loads of k-block kb issued
+        mbar_expect_tx(&a_full[s], RS_UNIT);
+        tma_load_2d(st, &map_p, kb * TC_BK, row0, &a_full[s]);
+        if (p.dbg_flags & 4) {
+          if (rank == 0) mbar_arrive(&b_full[s]);
+        } else {
+          if (rank == 0) mbar_expect_tx(&b_full[s], 4 * RS_UNIT);      // two halves from each of the two CTAs
+          tma2_load_2d(st + RS_UNIT, &map_w1, kb * TC_BK, (int)rank * 128, &b_full[s]);
+          tma2_load_2d(st + 2 * RS_UNIT, &map_w1, kb * TC_BK, 256 + (int)rank * 128, &b_full[s]);
+        }
+      };
+      // GEMM-2 tile i = (half h = i / 8, k-block i % 8) goes to slot (i + 4) % 5, i.e. tile 0 to unit 12
+      auto issue_w2 = [&](int i) {
+        const int h = i >> 3, kb = i & 7;
+        const int sl = (i + 4) % RS2_B2_SLOTS, n = i / RS2_B2_SLOTS;
+        mbar_wait(&b2_empty[sl], (n & 1) ^ 1);
+        if (rank == 0) mbar_expect_tx(&b2_full[sl], 2 * RS_UNIT);
+        tma2_load_2d(b2_slots + sl * RS_UNIT, &map_w2, kb * TC_BK, h * 256 + (int)rank * 128, &b2_full[sl]);
+      };
+      for (int kb = 0; kb < RS2_STAGES; ++kb) issue_stage(kb);          // the whole ring first: nothing else delays it
+      issue_w2(0);                                                       // unit 12; also warms the Wm2 descriptor
       {
+        // the tiles the tail of this CTA will read with plain loads: start them towards L2
         const size_t bytes = (size_t)valid * RS_D * 2;
         const char* q0 = reinterpret_cast<const char*>(p.Q + (size_t)row0 * RS_D);
         const char* k0 = reinterpret_cast<const char*>(p.kb + (size_t)row0 * RS_D);
@@ -615,24 +641,10 @@ read_step2_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_consta
           l2_prefetch_bulk(k0 + o, n);
         }
       }
-      for (int kb = 0; kb < RS_KB; ++kb) {
-        const int s = kb % RS2_STAGES, n = kb / RS2_STAGES;
-        unsigned char* st = tiles + s * 3 * RS_UNIT;
-        mbar_wait(&s_empty[s], (n & 1) ^ 1);
-        mbar_expect_tx(&a_full[s], RS_UNIT);
-        tma_load_2d(st, &map_p, kb * TC_BK, row0, &a_full[s]);
-        if (rank == 0) mbar_expect_tx(&b_full[s], 4 * RS_UNIT);        // two halves from each of the two CTAs
-        tma2_load_2d(st + RS_UNIT, &map_w1, kb * TC_BK, (int)rank * 128, &b_full[s]);
-        tma2_load_2d(st + 2 * RS_UNIT, &map_w1, kb * TC_BK, 256 + (int)rank * 128, &b_full[s]);
-      }
-      mbar_wait(g1_done, 0);                       // the GEMM-2 ring overlays stages 2 and 3
-      for (int i = 0; i < 2 * RS_KB; ++i) {
-        const int h = i >> 3, kb = i & 7;
-        const int sl = i % RS2_B2_SLOTS, n = i / RS2_B2_SLOTS;
-        mbar_wait(&b2_empty[sl], (n & 1) ^ 1);
-        if (rank == 0) mbar_expect_tx(&b2_full[sl], 2 * RS_UNIT);
-        tma2_load_2d(b2_slots + sl * RS_UNIT, &map_w2, kb * TC_BK, h * 256 + (int)rank * 128, &b2_full[sl]);
-      }
+      for (int kb = RS2_STAGES; kb < RS_KB; ++kb) issue_stage(kb);
+      mbar_wait(g1_done, 0);                       // the rest of the GEMM-2 ring overlays stages 2 and 3
+      rs_stamp(p, 56);
+      for (int i = 1; i < 2 * RS_KB; ++i) issue_w2(i);
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -642,8 +654,10 @@ read_step2_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_consta
       for (int kb = 0; kb < RS_KB; ++kb) {
         const int s = kb % RS2_STAGES, n = kb / RS2_STAGES;
         mbar_wait_cluster(&a_ready[s], n & 1);
+        if (lane == 0) rs_stamp(p, 48 + kb);       // both CTAs' P k-block scaled
         mbar_wait(&b_full[s], n & 1);
         tc_fence_after();
+        if (lane == 0) rs_stamp(p, 8 + kb);        // MMAs of k-block kb issued
         if (elect_one()) {
           const uint32_t st = smem_u32(tiles + s * 3 * RS_UNIT);
           const uint64_t adesc = make_sw128_kmajor_desc(st);
@@ -652,7 +666,7 @@ read_step2_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_consta
             const uint64_t bdesc = make_sw128_kmajor_desc(st + (1 + h) * RS_UNIT);
 #pragma unroll
             for (int k = 0; k < TC_BK / 16; ++k)
-              umma2_bf16(tmem_base + h * 256, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+              if (!(p.dbg_flags & 2)) umma2_bf16(tmem_base + h * 256, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
           }
           umma2_commit_mc(&s_empty[s], 0x3);
           if (kb == RS_KB - 1) umma2_commit_mc(g1_done, 0x3);
@@ -661,25 +675,21 @@ read_step2_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_consta
       }
       for (int i = 0; i < 2 * RS_KB; ++i) {
         const int h = i >> 3, kb = i & 7;
-        const int sl = i % RS2_B2_SLOTS, n = i / RS2_B2_SLOTS;
-        if (h == 0) {
-          if (kb == 0) {
-            mbar_wait_cluster(&hk_ready[0], 0);
-            mbar_wait_cluster(&hk_ready[1], 0);
-            mbar_wait_cluster(&hk_ready[2], 0);
-            mbar_wait_cluster(&hk_ready[3], 0);
-          } else if (kb >= 4) {
-            mbar_wait_cluster(&hk_ready[kb], 0);
-          }
+        const int sl = (i + 4) % RS2_B2_SLOTS, n = i / RS2_B2_SLOTS;
+        if (h == 0) {                              // H hand-over groups {0..3}, {4, 5}, {6, 7}
+          if (kb == 0) mbar_wait_cluster(&hk_ready[0], 0);
+          else if (kb == 4) mbar_wait_cluster(&hk_ready[1], 0);
+          else if (kb == 6) mbar_wait_cluster(&hk_ready[2], 0);
         }
         mbar_wait(&b2_full[sl], n & 1);
         tc_fence_after();
+        if (lane == 0) rs_stamp(p, 32 + i);        // GEMM-2 MMAs of (half, k-block) i issued
         if (elect_one()) {
           const uint64_t adesc = make_sw128_kmajor_desc(smem_u32(h_tile + kb * RS_UNIT));
           const uint64_t bdesc = make_sw128_kmajor_desc(smem_u32(b2_slots + sl * RS_UNIT));
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k)
-            umma2_bf16(tmem_base + h * 256, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+            if (!(p.dbg_flags & 2)) umma2_bf16(tmem_base + h * 256, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
           umma2_commit_mc(&b2_empty[sl], 0x3);
           if (kb == RS_KB - 1) umma2_commit_mc(&g2_done[h], 0x3);
         }
@@ -730,10 +740,13 @@ read_step2_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_consta
         const float4 yb0 = __ldg(reinterpret_cast<const float4*>(y_b + kb * TC_BK));
         const float4 yb1 = __ldg(reinterpret_cast<const float4*>(y_b + kb * TC_BK + 4));
         mbar_wait(&a_full[s], n & 1);
+        if (wt == 0) rs_stamp(p, 24 + kb);         // own P k-block landed
         uint4* t = reinterpret_cast<uint4*>(tiles + s * 3 * RS_UNIT);
-        if (ok_a) t[wt] = scale16(t[wt], ya0, ya1);
-        if (ok_b) t[wt + 512] = scale16(t[wt + 512], yb0, yb1);
-        fence_proxy_async();
+        if (!(p.dbg_flags & 1)) {
+          if (ok_a) t[wt] = scale16(t[wt], ya0, ya1);
+          if (ok_b) t[wt + 512] = scale16(t[wt + 512], yb0, yb1);
+          fence_proxy_async();
+        }
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(&a_ready[s], 0u);
       }
@@ -745,30 +758,41 @@ read_step2_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_consta
     mbar_wait(g1_done, 0);
     tc_fence_after();
     if (wt == 0) rs_stamp(p, 2);
+    // H k-blocks are handed to the MMA warp in three groups -- {0..3} (GEMM 2 cannot start earlier: its first MMA overwrites
+    // the accumulator columns of exactly these), {4, 5}, {6, 7} -- so each warp pays 3 proxy fences + arrives, not 8; the
+    // tensor-memory load of k-block i+1 is issued before k-block i is processed.
+    {
+      uint32_t rn[16];
+      tmem_ld16(tlane + cg * 16, rn);
 #pragma unroll
-    for (int kb2 = 0; kb2 < RS_KB; ++kb2) {
-      uint32_t r[16];
-      tmem_ld16(tlane + kb2 * 64 + cg * 16, r);
-      tmem_ld_wait();
-      const uint4 qa = qv[(2 * kb2) & 7], qb = qv[(2 * kb2 + 1) & 7];
-      if (kb2 < 4) {
-        qv[(2 * kb2) & 7] = ldg_nc_v4(qrow + 64 * (kb2 + 4));
-        qv[(2 * kb2 + 1) & 7] = ldg_nc_v4(qrow + 64 * (kb2 + 4) + 8);
+      for (int kb2 = 0; kb2 < RS_KB; ++kb2) {
+        uint32_t r[16];
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) r[j] = rn[j];
+        if (kb2 + 1 < RS_KB) tmem_ld16(tlane + (kb2 + 1) * 64 + cg * 16, rn);
+        const uint4 qa = qv[(2 * kb2) & 7], qb = qv[(2 * kb2 + 1) & 7];
+        if (kb2 < 4) {
+          qv[(2 * kb2) & 7] = ldg_nc_v4(qrow + 64 * (kb2 + 4));
+          qv[(2 * kb2 + 1) & 7] = ldg_nc_v4(qrow + 64 * (kb2 + 4) + 8);
+        }
+        const uint32_t qw[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+        uint32_t w[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          w[j] = pack_bf16(elu_fast(__uint_as_float(r[2 * j]) + bf16lo(qw[j])),
+                           elu_fast(__uint_as_float(r[2 * j + 1]) + bf16hi(qw[j])));
+        const int lc = cg * 2;
+        unsigned char* hrow = h_tile + kb2 * RS_UNIT + row * 128;
+        *reinterpret_cast<uint4*>(hrow + ((lc ^ (row & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4*>(hrow + (((lc + 1) ^ (row & 7)) << 4)) = make_uint4(w[4], w[5], w[6], w[7]);
+        if (kb2 == 3 || kb2 == 5 || kb2 == 7) {
+          fence_proxy_async();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(&hk_ready[kb2 == 3 ? 0 : (kb2 == 5 ? 1 : 2)], 0u);
+        }
       }
-      const uint32_t qw[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
-      uint32_t w[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        w[j] = pack_bf16(elu_fast(__uint_as_float(r[2 * j]) + bf16lo(qw[j])),
-                         elu_fast(__uint_as_float(r[2 * j + 1]) + bf16hi(qw[j])));
-      const int lc = cg * 2;
-      unsigned char* hrow = h_tile + kb2 * RS_UNIT + row * 128;
-      *reinterpret_cast<uint4*>(hrow + ((lc ^ (row & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
-      *reinterpret_cast<uint4*>(hrow + (((lc + 1) ^ (row & 7)) << 4)) = make_uint4(w[4], w[5], w[6], w[7]);
-      fence_proxy_async();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(&hk_ready[kb2], 0u);
     }
     if (wt == 0) rs_stamp(p, 3);
 
@@ -781,12 +805,16 @@ read_step2_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_consta
       mbar_wait(&g2_done[h], 0);
       tc_fence_after();
       if (wt == 0 && h == 1) rs_stamp(p, 4);
-#pragma unroll 2
+      uint32_t rn[16];
+      tmem_ld16(tlane + h * 256 + cg * 64, rn);
+#pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
         uint32_t r[16];
         const int c0 = h * 256 + cg * 64 + 16 * ch;
-        tmem_ld16(tlane + c0, r);
         tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) r[j] = rn[j];
+        if (ch + 1 < 4) tmem_ld16(tlane + c0 + 16, rn);
         const float4* b4 = reinterpret_cast<const float4*>(par + c0);
         const float4* w4 = reinterpret_cast<const float4*>(par + RS_D + c0);
         const float4* c4 = reinterpret_cast<const float4*>(crow + c0);
@@ -819,11 +847,14 @@ read_step2_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_consta
         v[i] = n < nrows ? ldg_nc_v4(kbase + (size_t)n * RS_D) : make_uint4(0u, 0u, 0u, 0u);
       }
     }
-    // ---- softmax over the sample's N rows: local statistics, exchange with the partner, final weights
+    // ---- softmax over the sample's N rows, split over the pair: each CTA forms its LOCAL maximum m_r, exp values
+    //      e[n] = exp(l[n] - m_r), their sum z_r and the un-normalised partial I_r = sum_n e[n] KB[n, :]; rank 1 ships
+    //      (m_1, z_1, e_1[], I_1[]) into rank 0's shared memory, ONE cluster barrier, and rank 0 writes
+    //      att[n] = e_r[n] c_r / Z,  info = (c_0 I_0 + c_1 I_1) / Z   with c_r = exp(m_r - max(m_0, m_1)), Z = c_0 z_0 + c_1 z_1.
     const int wi = warp - 2;
-    float e_lane[4] = {0.f, 0.f, 0.f, 0.f};
-    float mx = -INFINITY, sum = 0.f;
     if (wi == 0) {
+      float e_lane[4] = {0.f, 0.f, 0.f, 0.f};
+      float mx = -INFINITY, sum = 0.f;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int n = lane + 32 * i;
@@ -839,31 +870,19 @@ read_step2_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_consta
         }
       }
       sum = warp_sum(sum);
-      if (lane == 0) {
-        s_xch[2 * rank] = mx;
-        s_xch[2 * rank + 1] = sum;
-        st_cluster_f32(&s_xch[2 * rank], rank ^ 1u, mx);
-        st_cluster_f32(&s_xch[2 * rank + 1], rank ^ 1u, sum);
-      }
-    }
-    cluster_barrier();                             // #1
-    if (wi == 0) {
-      const float m0 = s_xch[0], z0 = s_xch[1], m1 = s_xch[2], z1 = s_xch[3];
-      const float M = fmaxf(m0, m1);
-      const float Z = z0 * __expf(m0 - M) + z1 * __expf(m1 - M);
-      const float scale = __expf(mx - M) / Z;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int n = lane + 32 * i;
-        if (n < nrows) {
-          const float a = e_lane[i] * scale;
-          s_att[n] = a;
-          p.att[(size_t)s0 * N + (int)rank * 128 + n] = a;
-        }
+        if (n < nrows) s_att[n] = e_lane[i];
+      }
+      if (lane == 0) {
+        s_xch[2 * rank] = mx;
+        s_xch[2 * rank + 1] = sum;
       }
     }
     rs_worker_bar();
     if (wt == 0) rs_stamp(p, 6);
+    float t = 0.f;
     {
       float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -879,18 +898,34 @@ read_step2_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_consta
       dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
       dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
       rs_worker_bar();
-      float t = 0.f;
 #pragma unroll
       for (int g = 0; g < RS_RED_GROUPS; ++g) t += s_red[g * RS_D + wt];
-      if (rank == 1) st_cluster_f32(&s_peer[wt], 0u, t);
-      cluster_barrier();                           // #2
-      if (rank == 0) p.info[(size_t)s0 * RS_D + wt] = t + s_peer[wt];
+    }
+    if (rank == 1) {
+      st_cluster_f32(&s_peer[wt], 0u, t);
+      if (wt < nrows) st_cluster_f32(&s_peer_e[wt], 0u, s_att[wt]);
+      if (wt == 0) {
+        st_cluster_f32(&s_xch[2], 0u, s_xch[2]);
+        st_cluster_f32(&s_xch[3], 0u, s_xch[3]);
+      }
+    }
+    cluster_barrier();                             // #1 (the only one of the tail)
+    if (rank == 0) {
+      const float m0 = s_xch[0], z0 = s_xch[1], m1 = s_xch[2], z1 = s_xch[3];
+      const float M = fmaxf(m0, m1);
+      const float c0 = __expf(m0 - M), c1 = __expf(m1 - M);
+      const float rZ = 1.f / (c0 * z0 + c1 * z1);
+      p.info[(size_t)s0 * RS_D + wt] = (c0 * t + c1 * s_peer[wt]) * rZ;
+      if (wt < 128) {
+        if (wt < nrows) p.att[(size_t)s0 * N + wt] = s_att[wt] * c0 * rZ;
+      } else if (wt - 128 < N - 128) {
+        p.att[(size_t)s0 * N + wt] = s_peer_e[wt - 128] * c1 * rZ;
+      }
     }
     if (wt == 0) rs_stamp(p, 7);
   }
-  if (warp < 2) {                                  // the producer / MMA warps take part in cluster barriers #1 and #2
+  if (warp < 2) {                                  // the producer / MMA warps take part in the tail's cluster barrier
     __syncwarp();
-    cluster_barrier();
     cluster_barrier();
   }
 
@@ -906,6 +941,7 @@ read_step2_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_consta
 
 // profiling hook (not part of the ABI header): device buffer [grid][8] that subsequent launches fill with clock64 stamps
 inline long long*& read_step_dbg_ptr() { static long long* p = nullptr; return p; }
+inline int& read_step_dbg_flags() { static int f = 0; return f; }
 
 // can the fused kernel take this shape?
 inline bool read_step_supported(int B, int N, int d) { return d == RS_D && N >= 1 && N <= 256 && B >= 1; }
@@ -929,7 +965,7 @@ inline int read_step_launch(const void* inv, const void* kb_bf16, const float* y
   p.B = B; p.N = N; p.y = y; p.ctrl = control; p.bm2 = w->bm2; p.wr = w->wr; p.br = w->br;
   p.Q = reinterpret_cast<const __nv_bfloat16*>(ibase + slab);
   p.kb = reinterpret_cast<const __nv_bfloat16*>(kb_bf16);
-  p.att = att; p.info = info; p.dbg = read_step_dbg_ptr();
+  p.att = att; p.info = info; p.dbg = read_step_dbg_ptr(); p.dbg_flags = read_step_dbg_flags();
   static bool attr_set[3] = {false, false, false};
   static const bool pair_mma = !(getenv("MAC_READ_PAIR_MMA") && atoi(getenv("MAC_READ_PAIR_MMA")) == 0);
   if (N > 128 && pair_mma) {

@@ -4,6 +4,7 @@
 #include "skinny.cuh"
 #include "tc_gemm.cuh"
 #include "read_step.cuh"
+#include "skinny_tc.cuh"
 
 using namespace mac;
 
@@ -188,6 +189,7 @@ extern "C" int mac_read_step_fused(const void* inv, const void* kb_bf16, const f
   return read_step_launch(inv, kb_bf16, y, control, w, att, info, B, N, d, stream);
 }
 extern "C" void mac_dbg_read_step_timestamps(long long* dev_buf) { read_step_dbg_ptr() = dev_buf; }
+extern "C" void mac_dbg_read_step_flags(int flags) { read_step_dbg_flags() = flags; }
 extern "C" int mac_read_step_fused_supported(int B, int N, int d) { return read_step_supported(B, N, d) ? 1 : 0; }
 
 extern "C" int mac_read_fwd(const float* kb, const void* kb_bf16, const float* memory_in, const float* control,
@@ -472,6 +474,38 @@ extern "C" int mac_linear_tc_fwd(const void* x_bf16, const void* wt_bf16, const 
     p.epi = TC_EPI_F32; p.outf = reinterpret_cast<float*>(y);
   }
   return tc_gemm_launch(x_bf16, K, nullptr, 0, wt_bf16, p, stream);
+}
+
+extern "C" int mac_pack_weight_bf16_split(const float* W, void* hi_bf16, void* lo_bf16, int K, int N, mac_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!W || !hi_bf16 || !lo_bf16 || K <= 0 || N <= 0) return MAC_ERR_INVALID;
+  dim3 grid((N + 31) / 32, (K + 31) / 32), block(32, 8);
+  pack_weight_bf16_split_kernel<<<grid, block, 0, stream>>>(W, reinterpret_cast<__nv_bfloat16*>(hi_bf16),
+                                                            reinterpret_cast<__nv_bfloat16*>(lo_bf16), K, N);
+  MAC_LAUNCH_CHECK();
+  return MAC_OK;
+}
+
+extern "C" int mac_linear_tc_small_fwd(const float* const* x_segs, const int* k_segs, const int* ldx, int nseg,
+                                       const void* wt_hi, const void* wt_lo, const float* b, float bias_const, int act,
+                                       float* y, int ldy, float* y2, int n_split, const float* gate_new,
+                                       const float* gate_old, float* gate_z, int M, int n_out, mac_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!x_segs || !k_segs || !ldx || nseg < 1 || nseg > 4 || !wt_hi || !y || M <= 0 || n_out <= 0) return MAC_ERR_INVALID;
+  if ((gate_new != nullptr) != (gate_old != nullptr)) return MAC_ERR_INVALID;
+  if (!mac_b200_device_ok()) return MAC_ERR_ARCH;
+  SkinnyTcParams p{};
+  p.nseg = nseg;
+  for (int i = 0; i < nseg; ++i) {
+    p.a[i] = x_segs[i];
+    p.ak[i] = k_segs[i];
+    p.lda[i] = ldx[i];
+    p.K += k_segs[i];
+  }
+  p.M = M; p.N = n_out; p.bias = b; p.bias_const = bias_const; p.act = act;
+  p.Y = y; p.ldy = ldy; p.Y2 = y2; p.n_split = n_split;
+  p.gnew = gate_new; p.gold = gate_old; p.gate_z = gate_z;
+  return skinny_tc_launch(p, wt_hi, wt_lo, stream);
 }
 
 // ------------------------------------------------------------------------------------------------ general (unfused) path

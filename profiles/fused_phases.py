@@ -18,7 +18,9 @@ def main():
     raw = ctypes.CDLL(L.LIB_PATH)
     torch.cuda.set_device(0)
     d = 512
-    for (B, N) in ((64, 196), (64, 49)):
+    flags = int(os.environ.get("RS_DBG_FLAGS", "0"))
+    raw.mac_dbg_read_step_flags(flags)
+    for (B, N) in ((64, 196),) if flags else ((64, 196), (64, 49)):
         t, rw = make_weights(lib, d, 7)
         g = torch.Generator(device="cuda").manual_seed(3)
         kb = torch.nn.functional.elu(torch.randn(B, N, d, device="cuda", generator=g)).to(torch.bfloat16).contiguous()
@@ -29,7 +31,7 @@ def main():
         L.check(lib.mac_read_invariant(None, L.ptr(kb), ctypes.byref(rw), 1, L.ptr(inv), nb, B, N, d, L.stream_ptr()))
         info, att = torch.empty(B, d, device="cuda"), torch.empty(B, N, device="cuda")
         grid = 2 * B if N > 128 else (B + min(128 // N, 2) - 1) // min(128 // N, 2)
-        dbg = torch.zeros(grid, 8, dtype=torch.int64, device="cuda")
+        dbg = torch.zeros(grid, 64, dtype=torch.int64, device="cuda")
         flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
         def run():
@@ -44,13 +46,21 @@ def main():
             run()
             torch.cuda.synchronize()
             raw.mac_dbg_read_step_timestamps(None)
-            s = dbg.cpu().numpy().astype(np.float64)
+            full = dbg.cpu().numpy().astype(np.float64)
+            s = full[:, :8]
             dl = np.diff(s, axis=1)
             names = ["scale(GEMM1 feed)", "GEMM1 tail", "epilogue1", "GEMM2", "epilogue2", "softmax", "weighted sum"]
-            out = {"B": B, "N": N, "cold_L2": cold, "grid": grid,
+            out = {"B": B, "N": N, "cold_L2": cold, "grid": grid, "dbg_flags": flags,
                    "total_clk_median": float(np.median(s[:, 7] - s[:, 0])), "total_clk_max": float(np.max(s[:, 7] - s[:, 0])),
                    "phases_median_clk": {n: float(np.median(dl[:, i])) for i, n in enumerate(names)},
                    "phases_max_clk": {n: float(np.max(dl[:, i])) for i, n in enumerate(names)}}
+            if N > 128 and full[:, 8:].any():
+                lead = full[0::2]                      # leader CTAs (rank 0 of each pair)
+                rel = lambda a, b: [float(np.median(lead[:, a + i] - lead[:, 0])) if lead[:, a + i].any() else None for i in range(b)]
+                out["pair_pipeline_clk_from_start_leader_median"] = {
+                    "tma_issue_kb": rel(16, 8), "a_landed_kb": rel(24, 8), "a_scaled_both_kb": rel(48, 8),
+                    "mma_issue_kb": rel(8, 8), "g1_done_seen_by_tma": rel(56, 1), "gemm2_mma_issue_i": rel(32, 16),
+                    "stamps": [float(np.median(lead[:, i] - lead[:, 0])) for i in range(8)]}
             print(json.dumps(out), flush=True)
 
 
