@@ -187,14 +187,15 @@ def cpu_reference(cfg, shape, params_np, budget_s=15.0, max_forwards=8):
 class Slot(object):
     """One resident batch + its cell + the captured CUDA graph of the netLength unroll."""
 
-    def __init__(self, cfg, params, shape, seed, prec, use_graph, host_inputs=None, fold_y=None):
+    def __init__(self, cfg, params, shape, seed, prec, use_graph, host_inputs=None, fold_y=None, small_tc=None):
         from mac_network_b200.mac_cell import MACCell, mac_network
         B, S, N, d, L = shape
         inp = host_inputs if host_inputs is not None else make_inputs(B, S, N, d, seed=seed)
         self.x = {k: torch.from_numpy(v).cuda() for k, v in inp.items()}
         x = self.x
         self.cell = MACCell(x["vecQuestions"], x["questionWords"], x["questionCntxWords"], x["questionLengths"],
-                            x["knowledgeBase"], 1.0, 1.0, 1.0, B, False, config=cfg, params=params, prec=prec, fold_y=fold_y)
+                            x["knowledgeBase"], 1.0, 1.0, 1.0, B, False, config=cfg, params=params, prec=prec, fold_y=fold_y,
+                            small_tc=small_tc)
         self.L = L
         self.graph = None
         self._net = mac_network
@@ -496,7 +497,9 @@ def run_ours(args):
     # ---- resident-input arm
     nstreams = max(1, args.streams)
     fold_y = (nstreams < 4) if args.fold_y < 0 else bool(args.fold_y)     # see MACCell.__init__: latency vs throughput form
-    slots = [Slot(cfg, params, shape, 1234 + 1000 * rank + s, args.prec, use_graph, fold_y=fold_y) for s in range(NSLOTS)]
+    small_tc = nstreams >= 2        # several passes in flight: tensor-core form of the batch-sized projections (MACCell.__init__)
+    slots = [Slot(cfg, params, shape, 1234 + 1000 * rank + s, args.prec, use_graph, fold_y=fold_y, small_tc=small_tc)
+             for s in range(NSLOTS)]
     launches_per_pass = slots[0].launches
 
     def barrier():
@@ -618,7 +621,9 @@ def run_ours(args):
                        "l2": "timed passes rotate over %d resident batches (%.0f MB > 126 MB L2)"
                              % (NSLOTS, NSLOTS * (B * N * d + B * S * d) * 4 / 1e6),
                        "cuda_graph": use_graph, "projections": args.prec, "concurrent_passes": nstreams,
-                       "write_unit_folded_with_next_projY": fold_y, "parallelism": "dp%d (replicas, no "
+                       "write_unit_folded_with_next_projY": bool(fold_y or small_tc),
+                       "batch_sized_projections": "tcgen05, 3-pass split bf16 (fp32-class accuracy)" if small_tc else "fp32 cluster kernel",
+                       "read_step": "one fused launch per reasoning step (csrc/read_step.cuh)", "parallelism": "dp%d (replicas, no "
                        "data-path collective in inference)" % world},
             "sample_steps_per_sec": value * B,
             "timed_blocks": {"resident": {"blocks": len(dev_blocks), "total_s": float(np.sum(dev_blocks)),
@@ -864,7 +869,8 @@ def run_quick(args):
     nstreams = max(1, args.streams)
     fold_y = (nstreams < 4) if args.fold_y < 0 else bool(args.fold_y)
     nslots = max(2, min(NSLOTS, 2 * nstreams)) if mult > 1 else NSLOTS          # keep > 126 MB of inputs in rotation
-    slots = [Slot(cfg, params, shape, 1234 + s, args.prec, not args.no_graph, fold_y=fold_y) for s in range(nslots)]
+    slots = [Slot(cfg, params, shape, 1234 + s, args.prec, not args.no_graph, fold_y=fold_y, small_tc=(nstreams >= 2))
+             for s in range(nslots)]
     side = [torch.cuda.Stream() for _ in range(nstreams - 1)]
     main_stream = torch.cuda.current_stream()
 

@@ -151,6 +151,20 @@ int mac_read_step_fused(const void* inv, const void* kb_bf16, const float* y, co
                         const mac_read_weights* w, float* info, float* att, int B, int N, int d, mac_stream_t stream);
 int mac_read_step_fused_supported(int B, int N, int d);
 
+/* One whole inference reasoning step as ONE kernel (plain write unit: writeInputs=BOTH, writeMemProj, no self-attention,
+ * no gate; control chain hoisted; dropouts = 1).  mac_read_step_fused with the recurrent glue moved into its prologue:
+ *   memory = info_prev ? [mem_prev, info_prev] @ Ww + bw : mem_prev      (write unit of the PREVIOUS step, mac_cell.py:339-352)
+ *   y      = memory @ Wy + by                                            (ops.py:689)
+ *   info, att = read step (as mac_read_step_fused) with this y and `control`
+ * `memory` is written to mem_out when info_prev != NULL.  The two products are per-sample matrix-vector products against bf16
+ * [out, in] copies of the weights (mac_pack_weight_bf16; fp32 activations and accumulation), computed while the kernel's
+ * first TMA requests wait for their tensor-map descriptors.  The caller runs mac_write_fwd once after the last step for the
+ * final memory.  mac_step_fused_supported: d == 512 and 128 < N <= 256 (a CTA pair per sample). */
+int mac_step_fused(const void* inv, const void* kb_bf16, const float* mem_prev, const float* info_prev, const float* control,
+                   const mac_read_weights* w, const void* Ww_t_bf16, const float* bw, const void* Wy_t_bf16, float* mem_out,
+                   float* info, float* att, int B, int N, int d, mac_stream_t stream);
+int mac_step_fused_supported(int B, int N, int d);
+
 /* The HBM-bound tail of the read unit on its own (ops.py:143, 149-150):
  *   att[b,:] = softmax_n( sum_p logit_parts[(b*N+n)*nparts + p] + br );  info[b,:] = sum_n att[b,n] * KB[b,n,:]
  * kb_is_bf16 != 0: `kb` points at bf16 data. */

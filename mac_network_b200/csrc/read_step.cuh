@@ -57,6 +57,15 @@ struct ReadStepParams {
   const __nv_bfloat16* kb;          // [B*N, d]  bf16 knowledge base
   float* att;                       // [B, N]
   float* info;                      // [B, d]
+  // whole-step form (pair kernel only; Wy_t != NULL): the memory projection -- and, from the second step on, the previous
+  // step's write unit -- are computed in the kernel's prologue (see read_step2_kernel); `y` is then unused
+  const float* mem_prev;            // [B, d]   memory the previous step read with (or the initial memory when info_prev == NULL)
+  const float* info_prev;           // [B, d]   previous step's retrieved information, or NULL (first step: memory = mem_prev)
+  const __nv_bfloat16* Ww_t;        // [d, 2d]  write/linearLayernewMemory weight, bf16 [out, in]
+  const float* bw;                  // [d]
+  const __nv_bfloat16* Wy_t;        // [d, d]   read/.../linearLayerprojY weight, bf16 [out, in]
+  const float* by;                  // [d]
+  float* mem_out;                   // [B, d]   memory of THIS step (written when info_prev != NULL)
   int dbg_flags;                    // profiling only (mac_dbg_read_step_flags; results are WRONG when set): 1 skip the P*y
                                     // smem pass, 2 skip the GEMM-1/2 MMAs, 4 skip the Wm loads of GEMM 1 (pair kernel)
   long long* dbg;                   // profiling only (mac_dbg_read_step_timestamps): [gridDim.x][64] SM-clock stamps, or NULL
@@ -515,6 +524,11 @@ read_step_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_constan
 // through 5 single-unit slots (units 8..12).  Unit 12 is outside the GEMM-1 ring, so the FIRST Wm2 tile is requested at
 // kernel start: a tensor map's first use costs a ~4.5k-clock descriptor fetch (measured: GEMM 2's first MMA was issued
 // 5.9k clocks after GEMM 1 completed), which this hides; the other slots are filled once GEMM 1 is complete.
+// Whole-step form (p.Wy_t != NULL): while the first TMA requests wait ~6k clocks for their tensor-map descriptors, the
+// workers compute, per sample, the previous step's write unit m = [m_prev, info_prev] @ Ww + bw (mac_cell.py:339-352,
+// plain form) and this step's memory projection y = m @ Wy + by (ops.py:689) as two matrix-vector products against bf16
+// weights (fp32 activations and accumulation), each CTA half of the outputs, exchanged through distributed shared
+// memory.  A reasoning step is then ONE launch: no separate write / projY kernels, and y never exists in HBM.
 // Tail: ONE cluster barrier -- rank 1 ships its local softmax statistics, its un-normalised exp values and its
 // un-normalised partial weighted sum to rank 0, which combines and writes att / info for the whole sample.
 // =====================================================================================================================
@@ -557,6 +571,8 @@ read_step2_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_consta
   uint64_t* hk_ready = bars + 27;                  // [8] leader (32 arrivals)
   uint64_t* g2_done = bars + 35;                   // [2] own (multicast commit)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 37);
+  uint64_t* xm_ready = bars + 40;                  // own: both CTAs' halves of the new memory are in s_m (32 warp arrivals)
+  uint64_t* xy_ready = bars + 41;                  // own: both halves of y are in s_y
   float* par = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bars) + 512);
   float* s_part = par + RS_PAR_FLOATS;
   float* s_att = s_part + 4 * 128;
@@ -564,6 +580,8 @@ read_step2_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_consta
   float* s_peer = s_xch + 16;                      // [512] rank 1's un-normalised partial weighted sum (read by rank 0)
   float* s_peer_e = s_peer + RS_D;                 // [128] rank 1's un-normalised exp values (read by rank 0)
   float* s_red = reinterpret_cast<float*>(tiles + 9 * RS_UNIT);          // [8][512] over units 9..12 (after GEMM 2)
+  float* s_m = s_peer;                             // [512] prologue only: this step's memory (s_peer is used by the tail)
+  float* s_y = s_part;                             // [512] prologue + GEMM 1: y (s_part is used from epilogue 2 on)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int N = p.N;
@@ -593,6 +611,8 @@ read_step2_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_consta
     for (int i = 0; i < RS_KB; ++i) mbar_init(&hk_ready[i], 2 * RS_WORKER_WARPS);
     mbar_init(&g2_done[0], 1);
     mbar_init(&g2_done[1], 1);
+    mbar_init(xm_ready, 2 * RS_WORKER_WARPS);
+    mbar_init(xy_ready, 2 * RS_WORKER_WARPS);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc2(tmem_ptr, 512);
@@ -630,17 +650,6 @@ read_step2_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_consta
       };
       for (int kb = 0; kb < RS2_STAGES; ++kb) issue_stage(kb);          // the whole ring first: nothing else delays it
       issue_w2(0);                                                       // unit 12; also warms the Wm2 descriptor
-      {
-        // the tiles the tail of this CTA will read with plain loads: start them towards L2
-        const size_t bytes = (size_t)valid * RS_D * 2;
-        const char* q0 = reinterpret_cast<const char*>(p.Q + (size_t)row0 * RS_D);
-        const char* k0 = reinterpret_cast<const char*>(p.kb + (size_t)row0 * RS_D);
-        for (size_t o = 0; o < bytes; o += 16384) {
-          const uint32_t n = (uint32_t)min((size_t)16384, bytes - o);
-          l2_prefetch_bulk(q0 + o, n);
-          l2_prefetch_bulk(k0 + o, n);
-        }
-      }
       for (int kb = RS2_STAGES; kb < RS_KB; ++kb) issue_stage(kb);
       mbar_wait(g1_done, 0);                       // the rest of the GEMM-2 ring overlays stages 2 and 3
       rs_stamp(p, 56);
@@ -710,6 +719,117 @@ read_step2_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_consta
       par[2 * RS_D + i] = __ldg(p.ctrl + (size_t)s0 * RS_D + i);
     }
     const bool row_ok = row < valid;
+    const int wi = warp - 2;
+    // ---- whole-step prologue: write unit of the previous step + memory projection of this one (see the header comment)
+    if (p.Wy_t) {
+      const int nbase = (int)rank * 256 + wi * 16;                 // this warp's 16 output columns
+      // dot of a bf16 weight row segment with fp32 x held in registers: NV = uint4 loads per lane (8 elements each)
+      auto dot8 = [](const uint4 w, const float* x) {
+        float a = bf16lo(w.x) * x[0];
+        a = fmaf(bf16hi(w.x), x[1], a);
+        a = fmaf(bf16lo(w.y), x[2], a); a = fmaf(bf16hi(w.y), x[3], a);
+        a = fmaf(bf16lo(w.z), x[4], a); a = fmaf(bf16hi(w.z), x[5], a);
+        a = fmaf(bf16lo(w.w), x[6], a); a = fmaf(bf16hi(w.w), x[7], a);
+        return a;
+      };
+      if (p.info_prev) {
+        // m[n] = sum_k [m_prev, info_prev][k] * Ww[k, n] + bw[n]; lane l holds x[32 l, 32 l + 32) (lanes 0..15: m_prev)
+        float x[32];
+        {
+          const float* src = (lane < 16 ? p.mem_prev : p.info_prev) + (size_t)s0 * RS_D + (lane & 15) * 32;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 f = __ldg(reinterpret_cast<const float4*>(src) + i);
+            x[4 * i] = f.x; x[4 * i + 1] = f.y; x[4 * i + 2] = f.z; x[4 * i + 3] = f.w;
+          }
+        }
+        float mine = 0.f;
+#pragma unroll 1
+        for (int j = 0; j < 16; j += 2) {
+          const __nv_bfloat16* r0 = p.Ww_t + (size_t)(nbase + j) * (2 * RS_D) + lane * 32;
+          const __nv_bfloat16* r1 = r0 + 2 * RS_D;
+          uint4 w0[4], w1[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { w0[i] = ldg_nc_v4(r0 + 8 * i); w1[i] = ldg_nc_v4(r1 + 8 * i); }
+          float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { a0 += dot8(w0[i], x + 8 * i); a1 += dot8(w1[i], x + 8 * i); }
+          a0 = warp_sum(a0);
+          a1 = warp_sum(a1);
+          if (lane == j) mine = a0;
+          if (lane == j + 1) mine = a1;
+        }
+        if (lane < 16) {
+          const float v_ = mine + __ldg(p.bw + nbase + lane);
+          s_m[nbase + lane] = v_;
+          st_cluster_f32(&s_m[nbase + lane], rank ^ 1u, v_);
+          p.mem_out[(size_t)s0 * RS_D + nbase + lane] = v_;
+        }
+      } else {
+        s_m[wt] = __ldg(p.mem_prev + (size_t)s0 * RS_D + wt);       // first step: the memory is given; both CTAs load all of it
+      }
+      if (p.info_prev) {
+        __syncwarp();
+        if (lane == 0) {
+          asm volatile("mbarrier.arrive.release.cluster.shared::cta.b64 _, [%0];" ::"r"(smem_u32(xm_ready)) : "memory");
+          asm volatile(
+              "{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
+              "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(xm_ready)), "r"(rank ^ 1u) : "memory");
+        }
+        uint32_t ok;
+        do {
+          asm volatile(
+              "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+              "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(xm_ready)), "r"(0u) : "memory");
+        } while (!ok);
+      } else {
+        rs_worker_bar();
+      }
+      {
+        // y[n] = sum_k m[k] * Wy[k, n] + by[n]; lane l holds m[16 l, 16 l + 16)
+        float x[16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 f = *reinterpret_cast<const float4*>(s_m + lane * 16 + 4 * i);
+          x[4 * i] = f.x; x[4 * i + 1] = f.y; x[4 * i + 2] = f.z; x[4 * i + 3] = f.w;
+        }
+        float mine = 0.f;
+#pragma unroll 1
+        for (int j = 0; j < 16; j += 4) {
+          uint4 w_[4][2];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const __nv_bfloat16* r = p.Wy_t + (size_t)(nbase + j + u) * RS_D + lane * 16;
+            w_[u][0] = ldg_nc_v4(r);
+            w_[u][1] = ldg_nc_v4(r + 8);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float a = warp_sum(dot8(w_[u][0], x) + dot8(w_[u][1], x + 8));
+            if (lane == j + u) mine = a;
+          }
+        }
+        if (lane < 16) {
+          const float v_ = mine + __ldg(p.by + nbase + lane);
+          s_y[nbase + lane] = v_;
+          st_cluster_f32(&s_y[nbase + lane], rank ^ 1u, v_);
+        }
+        __syncwarp();
+        if (lane == 0) {
+          asm volatile("mbarrier.arrive.release.cluster.shared::cta.b64 _, [%0];" ::"r"(smem_u32(xy_ready)) : "memory");
+          asm volatile(
+              "{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
+              "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(xy_ready)), "r"(rank ^ 1u) : "memory");
+        }
+        uint32_t ok;
+        do {
+          asm volatile(
+              "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+              "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(xy_ready)), "r"(0u) : "memory");
+        } while (!ok);
+      }
+      if (wt == 0) rs_stamp(p, 57);                // y ready
+    }
     const __nv_bfloat16* qrow = p.Q + (size_t)(row0 + (row_ok ? row : 0)) * RS_D + cg * 16;
     uint4 qv[8];
 #pragma unroll
@@ -723,8 +843,8 @@ read_step2_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_consta
       const int pc = wt & 7;
       const int lc_a = pc ^ (r_a & 7), lc_b = pc ^ (r_b & 7);
       const bool ok_a = r_a < valid, ok_b = r_b < valid;
-      const float* y_a = p.y + (size_t)s0 * RS_D + lc_a * 8;
-      const float* y_b = p.y + (size_t)s0 * RS_D + lc_b * 8;
+      const float* y_a = (p.Wy_t ? s_y : p.y + (size_t)s0 * RS_D) + lc_a * 8;
+      const float* y_b = (p.Wy_t ? s_y : p.y + (size_t)s0 * RS_D) + lc_b * 8;
       auto scale16 = [](uint4 v, const float4 f0, const float4 f1) {
         uint4 o;
         o.x = pack_bf16(bf16lo(v.x) * f0.x, bf16hi(v.x) * f0.y);
@@ -735,10 +855,10 @@ read_step2_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_consta
       };
       for (int kb = 0; kb < RS_KB; ++kb) {
         const int s = kb % RS2_STAGES, n = kb / RS2_STAGES;
-        const float4 ya0 = __ldg(reinterpret_cast<const float4*>(y_a + kb * TC_BK));
-        const float4 ya1 = __ldg(reinterpret_cast<const float4*>(y_a + kb * TC_BK + 4));
-        const float4 yb0 = __ldg(reinterpret_cast<const float4*>(y_b + kb * TC_BK));
-        const float4 yb1 = __ldg(reinterpret_cast<const float4*>(y_b + kb * TC_BK + 4));
+        const float4 ya0 = *reinterpret_cast<const float4*>(y_a + kb * TC_BK);
+        const float4 ya1 = *reinterpret_cast<const float4*>(y_a + kb * TC_BK + 4);
+        const float4 yb0 = *reinterpret_cast<const float4*>(y_b + kb * TC_BK);
+        const float4 yb1 = *reinterpret_cast<const float4*>(y_b + kb * TC_BK + 4);
         mbar_wait(&a_full[s], n & 1);
         if (wt == 0) rs_stamp(p, 24 + kb);         // own P k-block landed
         uint4* t = reinterpret_cast<uint4*>(tiles + s * 3 * RS_UNIT);
@@ -749,6 +869,15 @@ read_step2_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_consta
         }
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(&a_ready[s], 0u);
+        // The tiles this CTA reads later with plain loads are started towards L2 from here, NOT at kernel start: with the
+        // inputs of 6+ passes in flight nothing is L2-resident, and at kernel start these requests competed with the first
+        // P tiles for HBM (GEMM-1 feed 25k clocks cold vs 13.6k warm).  Q (epilogue 1) after k-block 1, KB (tail) after 5.
+        if ((kb == 1 || kb == 5) && wt < 8) {
+          const size_t bytes = (size_t)valid * RS_D * 2;
+          const char* base = reinterpret_cast<const char*>((kb == 1 ? p.Q : p.kb) + (size_t)row0 * RS_D);
+          const size_t o = (size_t)wt * 16384;
+          if (o < bytes) l2_prefetch_bulk(base + o, (uint32_t)min((size_t)16384, bytes - o));
+        }
       }
     }
 
@@ -851,7 +980,6 @@ read_step2_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_consta
     //      e[n] = exp(l[n] - m_r), their sum z_r and the un-normalised partial I_r = sum_n e[n] KB[n, :]; rank 1 ships
     //      (m_1, z_1, e_1[], I_1[]) into rank 0's shared memory, ONE cluster barrier, and rank 0 writes
     //      att[n] = e_r[n] c_r / Z,  info = (c_0 I_0 + c_1 I_1) / Z   with c_r = exp(m_r - max(m_0, m_1)), Z = c_0 z_0 + c_1 z_1.
-    const int wi = warp - 2;
     if (wi == 0) {
       float e_lane[4] = {0.f, 0.f, 0.f, 0.f};
       float mx = -INFINITY, sum = 0.f;
@@ -947,10 +1075,33 @@ inline int& read_step_dbg_flags() { static int f = 0; return f; }
 inline bool read_step_supported(int B, int N, int d) { return d == RS_D && N >= 1 && N <= 256 && B >= 1; }
 
 // inv = [P | Q] (tc_read_invariant); y, control [B, d] fp32; att [B, N], info [B, d]
+// whole-step form: the write unit of the previous step and this step's memory projection in the kernel's prologue
+struct WholeStepArgs {
+  const float* mem_prev;
+  const float* info_prev;           // NULL on the first step
+  const void* Ww_t_bf16;            // [d, 2d] bf16 (mac_pack_weight_bf16 of write/newMemory)
+  const float* bw;
+  const void* Wy_t_bf16;            // [d, d] bf16 (mac_pack_weight_bf16 of projY)
+  float* mem_out;
+};
+inline bool whole_step_supported(int B, int N, int d) {
+  static const bool pair_mma = !(getenv("MAC_READ_PAIR_MMA") && atoi(getenv("MAC_READ_PAIR_MMA")) == 0);
+  return read_step_supported(B, N, d) && N > 128 && pair_mma;
+}
+
 inline int read_step_launch(const void* inv, const void* kb_bf16, const float* y, const float* control,
-                            const mac_read_weights* w, float* att, float* info, int B, int N, int d, cudaStream_t stream) {
+                            const mac_read_weights* w, float* att, float* info, int B, int N, int d, cudaStream_t stream,
+                            const WholeStepArgs* ws = nullptr) {
   if (!read_step_supported(B, N, d)) return MAC_ERR_UNSUPPORTED;
-  if (!inv || !kb_bf16 || !y || !control || !w->Wm_bf16 || !w->Wm2_bf16 || !att || !info) return MAC_ERR_INVALID;
+  if (!inv || !kb_bf16 || (!y && !ws) || !control || !w->Wm_bf16 || !w->Wm2_bf16 || !att || !info) return MAC_ERR_INVALID;
+  if (ws) {
+    if (!whole_step_supported(B, N, d)) return MAC_ERR_UNSUPPORTED;
+    if (!ws->mem_prev || !ws->Wy_t_bf16 || !w->by) return MAC_ERR_INVALID;
+    if (ws->info_prev && (!ws->Ww_t_bf16 || !ws->bw || !ws->mem_out)) return MAC_ERR_INVALID;
+    if (!mac_aligned16(ws->mem_prev) || !mac_aligned16(ws->Wy_t_bf16) || (ws->info_prev && !mac_aligned16(ws->info_prev)) ||
+        (ws->Ww_t_bf16 && !mac_aligned16(ws->Ww_t_bf16)))
+      return MAC_ERR_ALIGN;
+  }
   const int M = B * N;
   const size_t slab = (((size_t)M * d * 2 + 1023) & ~(size_t)1023);
   const char* ibase = tc_align1k(const_cast<void*>(inv));
@@ -966,6 +1117,11 @@ inline int read_step_launch(const void* inv, const void* kb_bf16, const float* y
   p.Q = reinterpret_cast<const __nv_bfloat16*>(ibase + slab);
   p.kb = reinterpret_cast<const __nv_bfloat16*>(kb_bf16);
   p.att = att; p.info = info; p.dbg = read_step_dbg_ptr(); p.dbg_flags = read_step_dbg_flags();
+  if (ws) {
+    p.mem_prev = ws->mem_prev; p.info_prev = ws->info_prev; p.bw = ws->bw; p.by = w->by; p.mem_out = ws->mem_out;
+    p.Ww_t = reinterpret_cast<const __nv_bfloat16*>(ws->Ww_t_bf16);
+    p.Wy_t = reinterpret_cast<const __nv_bfloat16*>(ws->Wy_t_bf16);
+  }
   static bool attr_set[3] = {false, false, false};
   static const bool pair_mma = !(getenv("MAC_READ_PAIR_MMA") && atoi(getenv("MAC_READ_PAIR_MMA")) == 0);
   if (N > 128 && pair_mma) {

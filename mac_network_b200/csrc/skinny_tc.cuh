@@ -14,17 +14,22 @@
 // One CTA per BN output columns (BN = 32 / 64 -> 16..96 CTAs pull the weights from L2 in parallel).  Warp roles:
 //   warp 0      TMA producer: weight k-blocks [BN x 64] (hi and lo) through a 4-stage ring
 //   warp 1      TMEM allocator + MMA issuer
-//   warps 2..5  workers: load the fp32 activation k-block [M x 64] with 16-byte loads, split it into bf16 hi / lo and
-//               write both tiles in the 128-byte-swizzled K-major layout tcgen05 reads (3-stage ring); then the epilogue
-//               (bias, activation / write gate, column split of the folded write unit), thread == output row.
+//   warps 2..9  workers: load the fp32 activation k-block [M x 64] with 16-byte loads -- the loads of k-block i+2 are in
+//               flight while k-block i is split into bf16 hi / lo and written in the 128-byte-swizzled K-major layout
+//               tcgen05 reads (4-stage ring) -- then warps 2..5 run the epilogue (bias, activation / write gate, column
+//               split of the folded write unit), thread == output row.
+// (First version: 4 worker warps, loads issued per k-block: 18.7 us at K = 512 -- one L2 round trip per k-block on the
+// critical path; the fp32 cluster kernel took 9.5 us.)
 #pragma once
 #include "tc_gemm.cuh"
 
 namespace mac {
 
-constexpr int ST_A_STAGES = 3;
-constexpr int ST_B_STAGES = 4;
-constexpr int ST_THREADS = 64 + 128;
+constexpr int ST_A_STAGES = 4;
+constexpr int ST_B_STAGES = 6;
+constexpr int ST_WORKERS = 256;
+constexpr int ST_THREADS = 64 + ST_WORKERS;
+constexpr int ST_F4 = 128 * 16 / ST_WORKERS;  // float4 groups per worker thread and k-block at M = 128
 constexpr int ST_A_TILE = 128 * 128;          // [128 rows x 64 bf16]
 
 struct SkinnyTcParams {
@@ -68,12 +73,12 @@ skinny_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
   unsigned char* a_tiles = smem_dyn + pad;                       // [stage][hi | lo]
   unsigned char* b_tiles = a_tiles + C::A_BYTES;                 // [stage][hi | lo]
   uint64_t* bars = reinterpret_cast<uint64_t*>(b_tiles + C::B_BYTES);
-  uint64_t* a_ready = bars;                        // [3] workers -> MMA (4 warp arrivals)
-  uint64_t* a_empty = bars + 3;                    // [3] MMA -> workers
-  uint64_t* b_full = bars + 6;                     // [4] TMA -> MMA
-  uint64_t* b_empty = bars + 10;                   // [4] MMA -> TMA
-  uint64_t* done = bars + 14;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 15);
+  uint64_t* a_ready = bars;                        // [4] workers -> MMA (8 warp arrivals)
+  uint64_t* a_empty = bars + 4;                    // [4] MMA -> workers
+  uint64_t* b_full = bars + 8;                     // [6] TMA -> MMA
+  uint64_t* b_empty = bars + 14;                   // [6] MMA -> TMA
+  uint64_t* done = bars + 20;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 21);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BN;
@@ -85,7 +90,7 @@ skinny_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
     if (p.split) tma_prefetch_desc(&map_lo);
 #pragma unroll
     for (int i = 0; i < ST_A_STAGES; ++i) {
-      mbar_init(&a_ready[i], 4);
+      mbar_init(&a_ready[i], ST_WORKERS / 32);
       mbar_init(&a_empty[i], 1);
     }
 #pragma unroll
@@ -142,31 +147,35 @@ skinny_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
     }
   } else {
     // ===================================================== workers: activation split, then the epilogue
-    const int wt = threadIdx.x - 64;                 // 0..127
+    const int wt = threadIdx.x - 64;                 // 0..255
     const int nf4 = p.M * 16;                        // float4 groups of one [M x 64] k-block
-    int seg = 0, seg_off = 0;                        // segment that holds the current k-block
-    for (int kb = 0; kb < kblocks; ++kb) {
-      const int k0 = kb * TC_BK;
-      while (seg + 1 < p.nseg && k0 >= seg_off + p.ak[seg]) { seg_off += p.ak[seg]; ++seg; }
-      const float* src = p.a[seg] + (k0 - seg_off);
-      const int ld = p.lda[seg];
-      const int sa = kb % ST_A_STAGES, na = kb / ST_A_STAGES;
-      // the global loads of this k-block first (they do not depend on the stage being free)
-      float4 v[16];
+    // k-block -> (segment pointer at that k, leading dimension)
+    auto kb_src = [&](int kb, int& ld) -> const float* {
+      int k0 = kb * TC_BK, sg = 0;
+      while (sg + 1 < p.nseg && k0 >= p.ak[sg]) { k0 -= p.ak[sg]; ++sg; }
+      ld = p.lda[sg];
+      return p.a[sg] + k0;
+    };
+    auto load_kb = [&](int kb, float4 (&v)[ST_F4]) {
+      int ld;
+      const float* src = kb_src(kb, ld);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int e = wt + 128 * i;
+      for (int i = 0; i < ST_F4; ++i) {
+        const int e = wt + ST_WORKERS * i;
         if (e < nf4) {
           const uint4 u = ldg_nc_v4(src + (size_t)(e >> 4) * ld + (e & 15) * 4);
           v[i] = make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
         }
       }
+    };
+    auto store_kb = [&](int kb, const float4 (&v)[ST_F4]) {
+      const int sa = kb % ST_A_STAGES, na = kb / ST_A_STAGES;
       mbar_wait(&a_empty[sa], (na & 1) ^ 1);
       unsigned char* t_hi = a_tiles + sa * 2 * ST_A_TILE;
       unsigned char* t_lo = t_hi + ST_A_TILE;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int e = wt + 128 * i;
+      for (int i = 0; i < ST_F4; ++i) {
+        const int e = wt + ST_WORKERS * i;
         if (e < nf4) {
           const int row = e >> 4, f4 = e & 15;
           const uint32_t off = row * 128 + (((f4 >> 1) ^ (row & 7)) << 4) + (f4 & 1) * 8;
@@ -182,7 +191,24 @@ skinny_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&a_ready[sa]);
+    };
+    // three register buffers rotate: k-blocks i+1 and i+2 are in flight while k-block i is converted
+    float4 v0[ST_F4], v1[ST_F4], v2[ST_F4];
+    load_kb(0, v0);
+    if (kblocks > 1) load_kb(1, v1);
+    for (int kb = 0; kb < kblocks; kb += 3) {
+      if (kb + 2 < kblocks) load_kb(kb + 2, v2);
+      store_kb(kb, v0);
+      if (kb + 1 < kblocks) {
+        if (kb + 3 < kblocks) load_kb(kb + 3, v0);
+        store_kb(kb + 1, v1);
+      }
+      if (kb + 2 < kblocks) {
+        if (kb + 4 < kblocks) load_kb(kb + 4, v1);
+        store_kb(kb + 2, v2);
+      }
     }
+    if (warp >= 6) goto workers_done;                // the epilogue needs one warp per TMEM lane quarter: warps 2..5
     // ---- epilogue: thread == output row (TMEM lane)
     const int row = (warp & 3) * 32 + lane;
     const uint32_t tlane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
@@ -219,6 +245,7 @@ skinny_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
     }
     tc_fence_before();
   }
+workers_done:
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();

@@ -140,7 +140,7 @@ class MACCell(object):
 
     def __init__(self, vecQuestions, questionWords, questionCntxWords, questionLengths, knowledgeBase,
                  memoryDropout, readDropout, writeDropout, batchSize, train, reuse=None, *,
-                 config=None, params=None, prec="fp32", seed=0, save_for_backward=False, fold_y=None):
+                 config=None, params=None, prec="fp32", seed=0, save_for_backward=False, fold_y=None, small_tc=None):
         self.lib = _lib.load()
         self.cfg = config if config is not None else _defaults["config"]
         self.params = params if params is not None else _defaults["params"]
@@ -198,6 +198,31 @@ class MACCell(object):
         self._y_for = -1
         self.kb_bf16 = None
         self.save_for_backward = bool(save_for_backward)
+        # whole-step form (mac_step_fused): the previous step's plain write unit and this step's memory projection run in
+        # the prologue of the fused read-step kernel -> ONE launch per reasoning step.  bf16 inference, shared cells, plain
+        # write unit (no self-attention / gate / write dropout), all dropouts at 1, a CTA pair per sample (d = 512,
+        # 128 < N <= 256).  OPT-IN (MAC_STEP_FUSED=1): measured on the B200 it is slower (22.3k vs 28.3k reasoning-steps/s
+        # at 6 passes in flight) and less accurate (memory 3.8e-3 vs 4.7e-4): per-sample matrix-vector products read the
+        # write / projY weights once per CTA pair -- 98 MB of L2 traffic per step instead of 3 MB for the batched GEMMs.
+        self._step_fused = bool(
+            self._read_hoist and self.prec == PREC["bf16"] and self._fused_write and not (c.writeSelfAtt or c.writeGate)
+            and not (c.writeDropout < 1.0 and float(writeDropout) < 1.0) and float(readDropout) >= 1.0
+            and float(memoryDropout) >= 1.0 and os.environ.get("MAC_STEP_FUSED", "0") == "1"
+            and os.environ.get("MAC_READ_FUSED", "1") != "0"
+            and self.lib.mac_step_fused_supported(B, N, d) == 1)
+        # bf16 inference: the batch-sized projections of the step (projY, write unit, gate, ctrlProj) on tensor cores as
+        # three-pass split-bf16 products (mac_linear_tc_small_fwd, fp32-class accuracy): 16-32 independent CTAs that can run
+        # beside another pass's 128-CTA read kernel, which the 8-CTA-cluster fp32 kernel cannot.  Measured on the B200
+        # (headline shape): 29.9k vs 28.4k reasoning-steps/s with 6 passes in flight, but 15.9k vs 21.4k with ONE pass (the
+        # kernel's own latency is 2x the cluster kernel's), so it is the THROUGHPUT form: small_tc=True (callers with
+        # several passes in flight: bench.py, serving.HostPipeline), or MAC_SMALL_TC=1; default off.
+        want_tc = (os.environ.get("MAC_SMALL_TC", "0") == "1") if small_tc is None else bool(small_tc)
+        self._small_tc = bool(want_tc and self.prec == PREC["bf16"] and not save_for_backward and B <= 128 and d % 64 == 0
+                              and self._fused_write and os.environ.get("MAC_SMALL_TC", "1") != "0")
+        if self._small_tc:        # one launch for the write unit + the next projY: the folded form, whatever fold_y says
+            self._fold_y = (self._read_hoist and self._fused_write and not (c.writeSelfAtt or c.writeGate)
+                            and not (c.writeDropout < 1.0 and float(writeDropout) < 1.0))
+        self._pending_write = None       # step index i whose memory _hm[i] = write(_hm[i-1], _hi[i]) has not been launched yet
         recurrent_ctrl_ok = (c.controlFeedPrev and self._fused_control and not (c.controlWholeQ or c.controlContinuous
                                                                                 or c.unsharedCells))
         if self.save_for_backward and (not (self._fused_read and self._fused_write)
@@ -235,6 +260,30 @@ class MACCell(object):
         check(self.lib.mac_linear_fwd(arr_p, arr_k, arr_ld, n, ptr(W), ptr(b), float(bias_const), code, ptr(out),
                                       out.stride(0), M, W.shape[1], ptr(self.ws.lin), self.ws.lin_bytes, stream_ptr()),
               "mac_linear_fwd")
+        return out
+
+    def _split_weight(self, key, W):
+        """bf16 hi / lo halves [out, in] of an fp32 [in, out] weight (mac_pack_weight_bf16_split), cached per parameter version."""
+        def build():
+            hi = torch.empty((W.shape[1], W.shape[0]), dtype=torch.bfloat16, device=W.device)
+            lo = torch.empty_like(hi)
+            check(self.lib.mac_pack_weight_bf16_split(ptr(W), ptr(hi), ptr(lo), W.shape[0], W.shape[1], stream_ptr()), "pack_split")
+            return hi, lo
+        return self.params.derived(("split16", key), build)
+
+    def _linear_tc(self, xs, key, W, b, out, act="NON", bias_const=0.0, y2=None, n_split=0, gate=None):
+        """ops.linear on [M <= 128, sum k] segments as a three-pass split-bf16 tcgen05 product (mac_linear_tc_small_fwd).
+        `gate` = (new, old, z_out): the write gate epilogue (mac_cell.py:358-367)."""
+        n = len(xs)
+        hi, lo = self._split_weight(key, W)
+        arr_p = (ctypes.c_void_p * n)(*[x.data_ptr() for x in xs])
+        arr_k = (ctypes.c_int * n)(*[x.shape[1] for x in xs])
+        arr_ld = (ctypes.c_int * n)(*[x.stride(0) for x in xs])
+        gn, go, gz = gate if gate is not None else (None, None, None)
+        check(self.lib.mac_linear_tc_small_fwd(arr_p, arr_k, arr_ld, n, ptr(hi), ptr(lo), ptr(b), float(bias_const),
+                                               self._act_code(act), ptr(out), out.stride(0), ptr(y2), int(n_split), ptr(gn),
+                                               ptr(go), ptr(gz), xs[0].shape[0], W.shape[1], stream_ptr()),
+              "mac_linear_tc_small_fwd")
         return out
 
     def _attend(self, cc, cc_t, cc_b, inw, in_b, in_r, outw, out_b, out_r, lengths, w, b, att, out, nsteps, S):
@@ -293,6 +342,7 @@ class MACCell(object):
         self._mem_in = self._new(B, d)
         self._y_next = self._new(B, d)
         self._y_for = -1
+        self._pending_write = None
         if self.save_for_backward:
             self._ctrl_saved = {}
             M = B * self.N
@@ -433,6 +483,9 @@ class MACCell(object):
                 check(self.lib.mac_read_invariant(kb32, ptr(self.kb_bf16), ctypes.byref(rw), self.prec,
                                                   ptr(inv), nbytes, B, N, d, stream_ptr()), "mac_read_invariant")
                 self._read_inv[name] = inv
+            if _y_pre is None and self._small_tc:
+                Wy, by = self.params.lin("MACCell/read" + name + "/mulmemInter/", "projY")
+                _y_pre = self._linear_tc([memory], ("projY", name), Wy, by, self._y_next)
             check(self.lib.mac_read_fwd_inv(kb32, ptr(self.kb_bf16), ptr(self._read_inv[name]), ptr(_y_pre),
                                             ptr(memory), ptr(control), ctypes.byref(rw), self.prec, ptr(info), ptr(att),
                                             ptr(self.ws.read), self.ws.read_bytes, B, N, d, stream_ptr()),
@@ -487,6 +540,10 @@ class MACCell(object):
         i = self.iteration
         if not self._fused_write:
             return self._write_general(memory, info, control, contControl, name, _out, _gate_out)
+        if _y_next is not None and self._small_tc:
+            Wf, bf = self._folded_write_weights(name)
+            out = _out if _out is not None else self._new(B, d)
+            return self._linear_tc([memory, info], ("foldY", name), Wf, bf, out, y2=_y_next, n_split=d)
         if _y_next is not None:
             Wf, bf = self._folded_write_weights(name)
             out = _out if _out is not None else self._new(B, d)
@@ -499,7 +556,10 @@ class MACCell(object):
             selfControl = contControl if c.writeSelfAttMod == "CONT" else control
             W, b = self.params.lin(sc, "ctrlProj")
             keep = self.save_for_backward
-            selfControl = self._linear([selfControl], W, b, self._sc[i] if keep else self._new(B, d))
+            if self._small_tc:
+                selfControl = self._linear_tc([selfControl], ("ctrlProj", name), W, b, self._new(B, d))
+            else:
+                selfControl = self._linear([selfControl], W, b, self._sc[i] if keep else self._new(B, d))
             lsc = sc + "inter2attselfAttention/inter2logits/linearLayerlogits/"
             att = self._new(B, i + 1)
             selfSmry = self._ss[i] if keep else self._new(B, d)
@@ -515,6 +575,16 @@ class MACCell(object):
             Wg, bg = self.params.lin(sc, "gate")
             gate = _gate_out if _gate_out is not None else self._new(B, d)
         out = _out if _out is not None else self._new(B, d)
+        if self._small_tc:
+            segs = [memory, info] + ([selfSmry] if selfSmry is not None else [])
+            if c.writeGate:
+                mnew = self._linear_tc(segs, ("newMemory", name), Ww, bw, self._new(B, d))
+                self._linear_tc([control], ("gate", name), Wg, bg, out, bias_const=float(c.writeGateBias),
+                                gate=(mnew, memory, gate))
+                self.attentions["gate"].append(gate)
+            else:
+                self._linear_tc(segs, ("newMemory", name), Ww, bw, out)
+            return out
         check(self.lib.mac_write_fwd(ptr(memory), ptr(info), ptr(selfSmry), ptr(control), ptr(Ww), ptr(bw), ptr(Wg),
                                      ptr(bg), float(c.writeGateBias), ptr(out), ptr(gate), ptr(self.ws.write),
                                      self.ws.write_bytes, B, d, stream_ptr()), "mac_write_fwd")
@@ -707,6 +777,10 @@ class MACCell(object):
         if c.controlWholeQ:                                                            # mac_cell.py:455-456
             self._hc[i + 1].copy_(self.vecQuestions)
             newControl = self._hc[i + 1]
+        if self._step_fused:
+            newMemory = self._whole_step(i, memory, newControl, cellName)
+            self._set_histories(i + 1)
+            return self.none, MACCellTuple(newControl, newMemory)
         info = self.read(self.knowledgeBase, memory, newControl, name=cellName, _att_out=self._att_kb[i],
                          _out=self._hi[i + 1], _y_pre=self._y_next if self._y_for == i else None)
         if c.writeDropout < 1.0 and self.dropouts["write"] < 1.0:                      # mac_cell.py:461-463
@@ -718,6 +792,73 @@ class MACCell(object):
         self._y_for = i + 1 if fold else -1
         self._set_histories(i + 1)                                                     # mac_cell.py:472-474
         return self.none, MACCellTuple(newControl, newMemory)
+
+    # ------------------------------------------------------------------ whole step as one launch (inference)
+    def _ensure_read_inv(self, name):
+        """P = KB @ Wx + bx and Q = P @ Wm[d:2d] + bm, once per forward (mac_read_invariant)."""
+        if name not in self._read_inv:
+            B, N, d = self.B, self.N, self.d
+            rw = self._read_weights(name)
+            kb32 = None if self.knowledgeBase.dtype == torch.bfloat16 else ptr(self.knowledgeBase)
+            nbytes = self.lib.mac_read_invariant_bytes(B, N, d, self.prec)
+            inv = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            check(self.lib.mac_read_invariant(kb32, ptr(self.kb_bf16), ctypes.byref(rw), self.prec, ptr(inv), nbytes, B, N, d,
+                                              stream_ptr()), "mac_read_invariant")
+            self._read_inv[name] = inv
+        return self._read_inv[name]
+
+    def _step_weights_bf16(self, name):
+        """bf16 [out, in] copies of the write unit's newMemory weight and of projY for the in-kernel matrix-vector products."""
+        def build():
+            Ww, _ = self.params.lin("MACCell/write" + name + "/", "newMemory")
+            Wy, _ = self.params.lin("MACCell/read" + name + "/mulmemInter/", "projY")
+            out = []
+            for t in (Ww, Wy):
+                o = torch.empty((t.shape[1], t.shape[0]), dtype=torch.bfloat16, device=t.device)
+                check(self.lib.mac_pack_weight_bf16(ptr(t), ptr(o), t.shape[0], t.shape[1], stream_ptr()), "pack")
+                out.append(o)
+            return tuple(out)
+        return self.params.derived(("stepW16", name), build)
+
+    def _whole_step(self, i, memory, control, name):
+        """Step i as ONE launch: memory_i = write(memory_{i-1}, info_{i-1}) (deferred from the previous call), y_i, read_i.
+        The memory this call returns, `_hm[i+1]`, is produced by the NEXT call's kernel (or by `finish()` / the last step):
+        consumers inside the unroll only hand it back to `__call__`."""
+        B, N, d = self.B, self.N, self.d
+        rw = self._read_weights(name)
+        inv = self._ensure_read_inv(name)
+        Ww16, Wy16 = self._step_weights_bf16(name)
+        _, bw = self.params.lin("MACCell/write" + name + "/", "newMemory")
+        deferred = (self._pending_write == i and i > 0 and memory.data_ptr() == self._hm[i].data_ptr())
+        if not deferred:
+            self.finish()                                   # a pending memory belongs to an earlier, abandoned step chain
+        mem_prev = self._hm[i - 1] if deferred else memory
+        info_prev = self._hi[i] if deferred else None
+        att, info = self._att_kb[i], self._hi[i + 1]
+        check(self.lib.mac_step_fused(ptr(inv), ptr(self.kb_bf16), ptr(mem_prev), ptr(info_prev), ptr(control),
+                                      ctypes.byref(rw), ptr(Ww16), ptr(bw), ptr(Wy16), ptr(self._hm[i]) if deferred else None,
+                                      ptr(info), ptr(att), B, N, d, stream_ptr()), "mac_step_fused")
+        self.attentions["kb"].append(att)
+        if not deferred and memory.data_ptr() != self._hm[i].data_ptr():
+            self._hm[i].copy_(memory)                       # keep the history consistent with a caller-supplied memory
+        self._pending_write = i + 1
+        if i + 1 >= self.L:
+            self.finish()
+        return self._hm[i + 1]
+
+    def finish(self):
+        """Materialise a memory whose write unit was deferred into the next step's kernel (whole-step form)."""
+        j = self._pending_write
+        if j is None:
+            return
+        self._pending_write = None
+        saved, self._step_fused = self._step_fused, False
+        try:
+            self.iteration, it = j - 1, self.iteration
+            self.write(self._hm[j - 1], self._hi[j], self._hc[j], self.contControl, name="", _out=self._hm[j])
+            self.iteration = it
+        finally:
+            self._step_fused = saved
 
     def _read_inter_width(self):
         """Width of the tensor inter2att drops (mac_cell.py:209-266): the fused family ends in memDim columns."""
@@ -766,4 +907,5 @@ def mac_network(cell, netLength):
     for i in range(netLength):
         cell.iteration = i
         _, state = cell(none, state)
+    cell.finish()          # whole-step form: the last write unit, if the unroll stopped before cell.L steps
     return state.control, state.memory

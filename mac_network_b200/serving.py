@@ -70,7 +70,7 @@ def bind_to_gpu_numa(device_index):
 
 
 class _Slot(object):
-    def __init__(self, cfg, params, shape, prec, host_kb_bf16, use_graph, fold_y=None):
+    def __init__(self, cfg, params, shape, prec, host_kb_bf16, use_graph, fold_y=None, small_tc=None):
         B, S, N, d, L = shape
         dev = torch.device("cuda", torch.cuda.current_device())
         self.stream = torch.cuda.Stream()
@@ -83,7 +83,8 @@ class _Slot(object):
         x = self.x
         # questionWords is unused with controlContextual (mac_cell.py:570); the cell takes the contextual words for both
         self.cell = MACCell(x["vecQuestions"], x["questionCntxWords"], x["questionCntxWords"], x["questionLengths"],
-                            x["knowledgeBase"], 1.0, 1.0, 1.0, B, False, config=cfg, params=params, prec=prec, fold_y=fold_y)
+                            x["knowledgeBase"], 1.0, 1.0, 1.0, B, False, config=cfg, params=params, prec=prec, fold_y=fold_y,
+                            small_tc=small_tc)
         self.L = L
         self.graph = None
         with torch.cuda.stream(self.stream):
@@ -129,7 +130,9 @@ class HostPipeline(object):
                 self.host_kb_bf16 = False
         if fold_y is None:
             fold_y = slots < 4          # several batches in flight: the unfolded write + projY GEMMs pack better (mac_cell.py)
-        self.slots = [_Slot(cfg, params, shape, prec, self.host_kb_bf16, use_graph, fold_y) for _ in range(max(1, slots))]
+        # several batches in flight: the tensor-core form of the batch-sized projections (see MACCell.__init__)
+        self.slots = [_Slot(cfg, params, shape, prec, self.host_kb_bf16, use_graph, fold_y, small_tc=(slots >= 2))
+                      for _ in range(max(1, slots))]
         self._cast_for = None
         self._next = 0
         B, S, N, d, L = shape

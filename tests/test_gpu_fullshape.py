@@ -185,3 +185,53 @@ def test_backward_full_shape_matches_autograd(variant, shape, dp):
     bad = {k: v for k, v in worst.items() if v > 6e-4}
     assert not bad, (bad, {k: round(v, 7) for k, v in worst.items()})
     print("full-shape backward worst gradient max-rel:", max(worst.values()))
+
+
+def test_whole_step_kernel_matches_separate_launches(monkeypatch):
+    """mac_step_fused (write unit of the previous step + projY in the fused kernel's prologue, ONE launch per reasoning step)
+    against the same cell with read / write / projY as separate launches (MAC_STEP_FUSED=0), headline shape.  The only
+    arithmetic difference is bf16 instead of fp32 weights in the two batch-sized matrix-vector products."""
+    cfg, inputs, params, ref = headline_case()
+    L = SHAPES["headline"][4]
+    from mac_network_b200 import _lib
+    monkeypatch.setenv("MAC_STEP_FUSED", "1")        # opt-in form (slower and less accurate than the default: DESIGN.md)
+    n0 = _lib.load().mac_b200_launch_count()
+    fused, cell = run_gpu(cfg, params, inputs, L, prec="bf16")
+    n_fused = _lib.load().mac_b200_launch_count() - n0
+    assert cell._step_fused, "whole-step form not selected at the headline shape"
+    monkeypatch.setenv("MAC_STEP_FUSED", "0")
+    n0 = _lib.load().mac_b200_launch_count()
+    sep, cell2 = run_gpu(cfg, params, inputs, L, prec="bf16")
+    n_sep = _lib.load().mac_b200_launch_count() - n0
+    assert not cell2._step_fused
+    print("launches per 12-step pass: whole-step %d, separate %d" % (n_fused, n_sep))
+    assert n_fused < n_sep
+    for k in ("memory", "info", "att_kb"):
+        e = max(max_rel(fused[k][i], sep[k][i]) for i in range(L))
+        print("whole-step vs separate launches,", k, e)
+        assert e < 8e-3, (k, e)        # bf16 weights on the state path: memory 3.8e-3 vs the oracle (measured)
+    assert np.array_equal(fused["control"], sep["control"])
+
+
+@pytest.mark.parametrize("variant", ["args", "gqa"])
+def test_bf16_throughput_form_small_projections_on_tensor_cores(monkeypatch, variant):
+    """The throughput form of the bf16 cell (MACCell(small_tc=True) / MAC_SMALL_TC=1: projY, write unit, gate and ctrlProj
+    as three-pass split-bf16 tcgen05 products, write unit folded with the next projY) against the fp64 oracle at the
+    headline and GQA shapes: same bounds as the default form (the split keeps these projections at fp32-class accuracy)."""
+    monkeypatch.setenv("MAC_SMALL_TC", "1")
+    if variant == "args":
+        cfg, inputs, params, ref = headline_case()
+        L = SHAPES["headline"][4]
+    else:
+        shape = SHAPES["gqa"]
+        cfg, inputs, params, ref = headline_case("gqa", shape, seeds=(41, 42, 43))
+        L = shape[4]
+    got, cell = run_gpu(cfg, params, inputs, L, prec="bf16")
+    assert cell._small_tc
+    errs = {k: max(max_rel(got[k][i], ref[k][i]) for i in range(L)) for k in PER_STEP}
+    print("bf16 throughput form (%s) worst per-step max-rel:" % variant, errs)
+    assert errs["control"] < 1e-4
+    assert errs["memory"] < 1.5e-3 and errs["info"] < 4e-3 and errs["att_kb"] < 3e-3, errs
+    if variant == "gqa":
+        g = max(max_rel(got["att_gate"][i], ref["att_gate"][i]) for i in range(L))
+        assert g < 1.5e-3, g
