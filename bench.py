@@ -666,7 +666,12 @@ def train_arm(steps, warmup, rank, world, dist):
     B, S, N, d, L = shape
     cfg = MACConfig.args("args", netLength=L)
     pv = perturb_biases(init_params(cfg, L, seed=100), seed=101)
-    tr = DPTrainer(cfg, L, param_values=pv, seed=7, rank=rank, world=world, classifier=(28, [512]))   # CLEVR: 28 answers
+    # read unit's forward and backward products on tcgen05 tensor cores (bf16 operands, fp32 accumulation / master weights /
+    # optimizer state): the DP default since round 2 (gated by tests/test_zzz_tensor_core_training.py); MAC_TRAIN_FP32=1
+    # measures the all-fp32 SIMT form instead (38.9 ms per step in round 1)
+    tc = os.environ.get("MAC_TRAIN_FP32", "0") != "1"
+    tr = DPTrainer(cfg, L, param_values=pv, seed=7, rank=rank, world=world, classifier=(28, [512]),   # CLEVR: 28 answers
+                   prec="bf16" if tc else "fp32", bwd_tc=tc)
     inp = make_inputs(B, S, N, d, seed=4321 + 1000 * rank)
     batch = {k: torch.from_numpy(v).cuda() for k, v in inp.items()}
     answers = torch.from_numpy(np.random.RandomState(5 + rank).randint(0, 28, size=(B,)).astype(np.int32)).cuda()
@@ -695,8 +700,9 @@ def train_arm(steps, warmup, rank, world, dist):
         sync = all(bool(torch.equal(allc[0], c)) for c in allc)
     out = {"value": steps * L * world / t, "unit": UNIT, "ms_per_step": t / steps * 1e3, "steps": steps,
            "what": "DP training step: train-mode cell forward + output unit + mean softmax-CE over the global batch + hand-written "
-                   "backward + all-reduce of the flat gradient bucket (%.1f MB, NCCL) + fused clip/Adam/EMA; B=%d per GPU, "
-                   "fp32 path" % (tr.params.numel * 4 / 1e6, B),
+                   "backward + all-reduce of the flat gradient bucket (%.1f MB, NCCL) + fused clip/Adam/EMA; B=%d per GPU, %s"
+                   % (tr.params.numel * 4 / 1e6, B, "read-unit forward + backward products on tcgen05 (bf16 operands, fp32 "
+                      "accumulate, fp32 master weights)" if tc else "fp32 path"),
            "replicas_in_sync": sync}
     del tr
     torch.cuda.empty_cache()

@@ -38,18 +38,26 @@ struct TmapKey {
 // swizzle: 0 none, 1 128B.  Returns MAC_OK or MAC_ERR_ARCH / MAC_ERR_INVALID.
 inline int make_tmap_2d(CUtensorMap* out, const void* base, int dtype, uint64_t rows, uint64_t cols,
                         uint64_t row_stride_bytes, uint32_t box_rows, uint32_t box_cols, int swizzle) {
+  // direct-mapped cache of 2048 descriptors (a training step of netLength 12 uses a few hundred distinct (pointer, geometry)
+  // pairs; the 64-entry linear cache of round 1 thrashed there and every launch paid a cuTensorMapEncodeTiled)
+  constexpr int NSLOT = 2048;
   static std::mutex mu;
-  static TmapKey keys[64];
-  static CUtensorMap maps[64];
-  static int used = 0, next = 0;
+  static TmapKey* keys = new TmapKey[NSLOT]();
+  static CUtensorMap* maps = new CUtensorMap[NSLOT];
+  static bool* used = new bool[NSLOT]();
   TmapKey k;
   memset(&k, 0, sizeof(k));
   k.base = base; k.dtype = dtype; k.swizzle = swizzle; k.rows = rows; k.cols = cols;
   k.row_stride_bytes = row_stride_bytes; k.box_rows = box_rows; k.box_cols = box_cols;
+  uint64_t h = 1469598103934665603ull;
+  {
+    const unsigned char* kp = reinterpret_cast<const unsigned char*>(&k);
+    for (size_t i = 0; i < sizeof(TmapKey); ++i) h = (h ^ kp[i]) * 1099511628211ull;
+  }
+  const int slot = (int)(h % NSLOT);
   {
     std::lock_guard<std::mutex> g(mu);
-    for (int i = 0; i < used; ++i)
-      if (keys[i] == k) { *out = maps[i]; return MAC_OK; }
+    if (used[slot] && keys[slot] == k) { *out = maps[slot]; return MAC_OK; }
   }
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) return MAC_ERR_ARCH;
@@ -64,9 +72,9 @@ inline int make_tmap_2d(CUtensorMap* out, const void* base, int dtype, uint64_t 
   if (r != CUDA_SUCCESS) return MAC_ERR_INVALID;
   {
     std::lock_guard<std::mutex> g(mu);
-    const int slot = used < 64 ? used++ : (next++ & 63);
     keys[slot] = k;
     maps[slot] = *out;
+    used[slot] = true;
   }
   return MAC_OK;
 }
