@@ -50,7 +50,10 @@ enum { MAC_ACT_NON = 0, MAC_ACT_TANH = 1, MAC_ACT_SIGMOID = 2, MAC_ACT_ELU = 3, 
 /* arithmetic of the d x d projections */
 enum {
   MAC_PREC_FP32 = 0, /* fp32 FMA pipe, fp32 accumulate: the <=1e-4 parity configuration */
-  MAC_PREC_BF16 = 1  /* bf16 operands on tcgen05 tensor cores, fp32 accumulate in TMEM: the headline configuration */
+  MAC_PREC_BF16 = 1, /* bf16 operands on tcgen05 tensor cores, fp32 accumulate in TMEM: the headline configuration */
+  MAC_PREC_TC32 = 2  /* split-bf16 on tcgen05 (x = hi + lo, three of the four partial products, fp32 accumulate): a tensor-core
+                        path inside the 1e-4 parity bar.  Inference form only (mac_read_invariant / mac_read_fwd_inv); fp32
+                        knowledge base; everything outside the three [B*N, .] projections as in MAC_PREC_FP32 */
 };
 
 int mac_b200_abi_version(void);
@@ -115,6 +118,8 @@ typedef struct mac_read_weights {
   const float* wr;  float br;          /* read/inter2att/inter2logits/linearLayerlogits [d], []   */
   /* bf16 [out,in] copies of Wx, Wm, Wm2 (mac_pack_weight_bf16); NULL for MAC_PREC_FP32 */
   const void* Wx_bf16; const void* Wm_bf16; const void* Wm2_bf16;
+  /* MAC_PREC_TC32 only: split-bf16 copies [out, 3*in] = [hi | hi | lo] (mac_pack_weight_split3) of Wx, Wm[0:d], Wm[d:2d], Wm2 */
+  const void* Wx_s3; const void* Wma_s3; const void* Wmb_s3; const void* Wm2_s3;
 } mac_read_weights;
 
 int mac_read_fwd(const float* kb, const void* kb_bf16, const float* memory_in, const float* control,
@@ -239,6 +244,9 @@ int mac_host_cast_bf16_end(void);
  *   {NON, ELU}, b required).  Requires K % 64 == 0 and n_out % 128 == 0.
  * --------------------------------------------------------------------------------------------- */
 int mac_pack_weight_bf16(const float* W, void* Wt_bf16, int K, int n_out, mac_stream_t stream);
+/* fp32 W[K, n_out] -> bf16 Wt3[n_out, 3K] = [hi | hi | lo] (hi = bf16(W), lo = bf16(W - hi)): the B operand of the split-bf16
+ * products of MAC_PREC_TC32 (see tc3_gemm in csrc/tc_gemm.cuh).  A row block of a taller weight is passed as W + k0*n_out. */
+int mac_pack_weight_split3(const float* W, void* Wt3_bf16, int K, int n_out, mac_stream_t stream);
 int mac_linear_tc_fwd(const void* x_bf16, const void* wt_bf16, const float* b, int act, void* y, int y_is_bf16,
                       int M, int K, int n_out, mac_stream_t stream);
 

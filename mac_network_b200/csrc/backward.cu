@@ -181,7 +181,22 @@ __global__ void __launch_bounds__(256) kb_attend_bwd_kernel(const float* __restr
   __syncthreads();
   const float dot = s_dot;
   const int n0 = blockIdx.x * 32;
-  if (tid < 32 && n0 + tid < N) dkl[(size_t)b * N + n0 + tid] = a[n0 + tid] * (dk[n0 + tid] - dot);
+  // dkl[n] = ka[n] * (dka[n] - sum_m ka[m] dka[m]) cancels catastrophically in fp32 when the attention is peaked (ka[n] -> 1:
+  // dka[n] - dot is the difference of two nearly equal numbers, and that n carries most of the gradient).  The same value as a
+  // sum of weighted differences, ka[n] * sum_m ka[m] * (dka[n] - dka[m]), has no such cancellation; O(N^2) per sample is
+  // nothing at N = 196.  8 lanes per n (tid / 8 -> n, tid % 8 -> slice of m), reduced with shuffles.
+  {
+    const int n = n0 + (tid >> 3), part_i = tid & 7;
+    float acc = 0.f;
+    if (n < N) {
+      const float dn = dk[n];
+      for (int m = part_i; m < N; m += 8) acc = fmaf(a[m], dn - dk[m], acc);
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    if (n < N && part_i == 0) dkl[(size_t)b * N + n] = a[n] * acc;
+  }
   if (blockIdx.x == 0 && dbr_part) {
     // sum_n dkl = sum ka*dka - dot*sum ka = dot - dot*1 = 0 up to round-off; computed explicitly for fidelity
     float s = 0.f;

@@ -134,6 +134,7 @@ extern "C" size_t mac_read_workspace_bytes(int B, int N, int d, int prec) {
   size_t a, b, c, e, f, g;
   size_t fp32 = read_ws_layout(B, N, d, &a, &b, &c, &e, &f, &g);
   if (prec == MAC_PREC_BF16) return fp32 + tc_read_extra_workspace_bytes(B, N, d);
+  if (prec == MAC_PREC_TC32) return fp32 + tc3_extra_workspace_bytes(B, N, d);
   return fp32;
 }
 
@@ -141,6 +142,7 @@ extern "C" size_t mac_read_workspace_bytes(int B, int N, int d, int prec) {
 static size_t read_inv_fp32_bytes(int B, int N, int d) { return (size_t)2 * B * N * d * 4 + 256; }
 
 extern "C" size_t mac_read_invariant_bytes(int B, int N, int d, int prec) {
+  if (prec == MAC_PREC_TC32) return tc3_invariant_bytes(B, N, d);
   return prec == MAC_PREC_BF16 ? tc_read_invariant_bytes(B, N, d) : read_inv_fp32_bytes(B, N, d);
 }
 
@@ -153,6 +155,7 @@ extern "C" int mac_read_invariant(const float* kb, const void* kb_bf16, const ma
   if ((kb && !mac_aligned16(kb)) || !mac_aligned16(inv)) return MAC_ERR_ALIGN;
   if (inv_bytes < mac_read_invariant_bytes(B, N, d, prec)) return MAC_ERR_WORKSPACE;
   if (prec == MAC_PREC_BF16) return tc_read_invariant(kb_bf16, w, inv, inv_bytes, B, N, d, stream);
+  if (prec == MAC_PREC_TC32) return tc3_read_invariant(kb, w, inv, inv_bytes, B, N, d, stream);
   const int M = B * N;
   float* P = reinterpret_cast<float*>(inv);
   float* Q = P + (size_t)M * d;
@@ -276,7 +279,12 @@ static int read_fwd_impl(const float* kb, const void* kb_bf16, const void* inv, 
     // the whole step (P*y, both projections, logits, softmax, weighted sum) as ONE kernel: read_step.cuh
     return read_step_launch(inv, kb_bf16, y, control, w, att, info, B, N, d, stream);
   }
-  if (inv && prec == MAC_PREC_BF16) {
+  if (prec == MAC_PREC_TC32) {
+    if (!inv) return MAC_ERR_UNSUPPORTED;          // split-bf16 products: inference form only
+    int st = tc3_read_chain_inv(inv, y, control, w, parts, &nparts, ws + fp32_total, workspace_bytes - fp32_total, B, N, d,
+                                stream);
+    if (st != MAC_OK) return st;
+  } else if (inv && prec == MAC_PREC_BF16) {
     int st = tc_read_chain_inv(inv, y, control, w, parts, &nparts, ws + fp32_total, workspace_bytes - fp32_total, B, N,
                                d, stream);
     if (st != MAC_OK) return st;
@@ -470,6 +478,15 @@ extern "C" int mac_pack_weight_bf16(const float* W, void* Wt_bf16, int K, int N,
   if (!W || !Wt_bf16 || K <= 0 || N <= 0) return MAC_ERR_INVALID;
   dim3 grid((N + 31) / 32, (K + 31) / 32), block(32, 8);
   pack_weight_bf16_kernel<<<grid, block, 0, stream>>>(W, reinterpret_cast<__nv_bfloat16*>(Wt_bf16), K, N);
+  MAC_LAUNCH_CHECK();
+  return MAC_OK;
+}
+
+extern "C" int mac_pack_weight_split3(const float* W, void* Wt3_bf16, int K, int N, mac_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!W || !Wt3_bf16 || K <= 0 || N <= 0) return MAC_ERR_INVALID;
+  dim3 grid((N + 31) / 32, (K + 31) / 32), block(32, 8);
+  pack_weight_split3_kernel<<<grid, block, 0, stream>>>(W, reinterpret_cast<__nv_bfloat16*>(Wt3_bf16), K, N);
   MAC_LAUNCH_CHECK();
   return MAC_OK;
 }

@@ -236,6 +236,9 @@ class MACCell(object):
             raise NotImplementedError("training forward on tensor cores needs d % 128 == 0 and an fp32 knowledge base")
         if self.prec != PREC["fp32"] and not self._fused_read:
             raise NotImplementedError("the tensor-core projections cover the fused read unit only")
+        if self.prec == PREC["tc32"] and (save_for_backward or not self._read_hoist or float(readDropout) < 1.0 or d % 128):
+            raise NotImplementedError('prec="tc32" (split-bf16 tensor-core projections inside the 1e-4 bar) is the inference '
+                                      "form of the fused read unit: shared cells, readDropout = 1, d % 128 == 0")
         if self._kb_given_bf16 and not (self.prec == PREC["bf16"] and self._read_hoist and float(readDropout) >= 1.0):
             raise NotImplementedError("a bf16 knowledge base is accepted by the bf16 inference path only")
 
@@ -452,6 +455,14 @@ class MACCell(object):
                 return o
             keep = p.derived(("bf16", sc), lambda: (pack(Wx), pack(Wm), pack(Wm2)))
             rw.Wx_bf16, rw.Wm_bf16, rw.Wm2_bf16 = (t.data_ptr() for t in keep)
+        if self.prec == PREC["tc32"]:
+            def pack3(t):      # fp32 [in, out] -> bf16 [out, 3*in] = [hi | hi | lo]
+                o = torch.empty((t.shape[1], 3 * t.shape[0]), dtype=torch.bfloat16, device=t.device)
+                check(self.lib.mac_pack_weight_split3(ptr(t), ptr(o), t.shape[0], t.shape[1], stream_ptr()), "pack3")
+                return o
+            d_ = self.d
+            keep3 = p.derived(("split3", sc), lambda: (pack3(Wx), pack3(Wm[:d_]), pack3(Wm[d_:]), pack3(Wm2)))
+            rw.Wx_s3, rw.Wma_s3, rw.Wmb_s3, rw.Wm2_s3 = (t.data_ptr() for t in keep3)
         self._rw[name] = rw
         return rw
 
