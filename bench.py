@@ -486,6 +486,13 @@ def run_ours(args):
     if world > 1 and os.environ.get("MAC_NO_NUMA_BIND", "0") != "1":
         from mac_network_b200.serving import bind_to_gpu_numa
         numa = bind_to_gpu_numa(local)
+    # how many ranks stage their batches through this rank's socket (they share its memory bandwidth)
+    ranks_on_node = 1
+    if dist is not None:
+        nodes = [None] * world
+        dist.all_gather_object(nodes, numa.get("numa_node", -1))
+        ranks_on_node = max(1, sum(1 for x in nodes if x == numa.get("numa_node", -1)))
+    numa["ranks_on_node"] = ranks_on_node
     shape = SHAPES[WORKLOAD]
     B, S, N, d, L = shape
     cfg = MACConfig.args("args", netLength=L)
@@ -556,7 +563,8 @@ def run_ours(args):
     del slots
     torch.cuda.empty_cache()
     pipe = HostPipeline(cfg, params, shape, prec=args.prec, slots=ND, use_graph=use_graph, fold_y=fold_y,
-                        cast_threads=cast_threads_for(world, numa))
+                        cast_threads=cast_threads_for(world, numa),
+                        host_cast=None if ranks_on_node <= 1 else False)      # see HostPipeline: socket memory bandwidth
     h2d_bytes, d2h_bytes = pipe.h2d_bytes, pipe.d2h_bytes
     e2e_host_cast, e2e_cast_threads, pipe_cast_ms = pipe.host_kb_bf16, pipe.cast_threads, pipe.cast_ms
 

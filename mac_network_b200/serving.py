@@ -110,13 +110,19 @@ class HostPipeline(object):
     ticket.  `result(ticket)` blocks until that batch is done and returns pinned host tensors (final control / memory
     state, per-step KB and question attention maps) that stay valid until the slot is reused `slots` submits later."""
 
-    def __init__(self, cfg, params, shape, prec="bf16", slots=4, use_graph=True, cast_threads=None, fold_y=None):
+    def __init__(self, cfg, params, shape, prec="bf16", slots=4, use_graph=True, cast_threads=None, fold_y=None,
+                 host_cast=None):
+        """`host_cast`: None = decide here (bf16 path: cast the knowledge base to bf16 on the host if that is faster than the
+        PCIe time it saves); False = never.  Callers that run several ranks per socket pass False: the cast makes a pass touch
+        ~57 MB of host DRAM (fp32 read + bf16 write + DMA read) instead of 31 MB, and the ranks of one socket share its memory
+        bandwidth -- measured on the 2-socket B200 host: 26.4k reasoning-steps/s end to end with one rank, 29.0k TOTAL with two
+        ranks on the same socket, i.e. the cast was bandwidth-bound at ~135 GB/s of host DRAM traffic per socket."""
         self.lib = _lib.load()
         self.shape = shape
         self.prec = prec
         self.host_kb_bf16 = (prec == "bf16" and os.environ.get("MAC_NO_HOST_CAST", "0") != "1"
                              and os.environ.get("MAC_NO_READ_HOIST", "0") != "1" and cfg.is_fast_path
-                             and not cfg.unsharedCells)
+                             and not cfg.unsharedCells and host_cast is not False)
         self.cast_threads = int(cast_threads) if cast_threads else max(1, min(12, usable_cpus() - 2))
         if os.environ.get("MAC_HOST_CAST_THREADS"):
             self.cast_threads = max(1, int(os.environ["MAC_HOST_CAST_THREADS"]))
