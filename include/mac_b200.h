@@ -235,6 +235,10 @@ int mac_host_cast_bf16(const float* src, void* dst_bf16, long long n, int nthrea
 int mac_host_cast_bf16_begin(const float* src, void* dst_bf16, long long n, int nthreads);
 int mac_host_cast_bf16_end(void);
 
+/* HOST: CRC-32C (Castagnoli) of n bytes continuing from `crc` (0 to start): the checksum TensorFlow's checkpoint format stores
+ * per tensor and per index block (mac_network_b200/tf_bundle.py reads / writes real `weights{epoch}.ckpt` files, main.py:163-201). */
+uint32_t mac_host_crc32c(const void* data, long long n, uint32_t crc);
+
 /* ------------------------------------------------------------------------------------------------
  * Tensor-core (MAC_PREC_BF16) helpers.
  * mac_pack_weight_bf16: fp32 W[K, n_out] (the reference's [in, out] layout, ops.py:304) -> bf16 Wt[n_out, K], the

@@ -68,6 +68,7 @@ PROTOTYPES = {
     "mac_host_cast_bf16": (c_int, [c_fp, c_fp, c_ll, c_int]),
     "mac_host_cast_bf16_begin": (c_int, [c_fp, c_fp, c_ll, c_int]),
     "mac_host_cast_bf16_end": (c_int, []),
+    "mac_host_crc32c": (ctypes.c_uint32, [c_fp, c_ll, ctypes.c_uint32]),
     "mac_linear_bwd": (c_int, [ctypes.POINTER(c_fp), ctypes.POINTER(c_int), ctypes.POINTER(c_int), c_int, c_fp, c_fp, c_int,
                                ctypes.POINTER(c_fp), ctypes.POINTER(c_int), ctypes.POINTER(c_int), c_fp, c_fp, c_int, c_int,
                                c_fp, c_sz, c_fp]),

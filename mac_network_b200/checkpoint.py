@@ -2,9 +2,10 @@
 
 * Weights are exchanged under the reference's TensorFlow variable names (`macModel/MACnetwork/MACCell/...`,
   `main.py:163-201`, Appendix B), including the EMA shadows `<name>/ExponentialMovingAverage` (`model.py:659-667`).
-  TensorFlow's binary checkpoint format needs TensorFlow; the interchange container here is a flat `.npz` with those
-  names as keys, which `tf.train.load_checkpoint(...)`-side tooling can produce with a ten-line script
-  (`{n: reader.get_tensor(n) for n in reader.get_variable_to_shape_map()}`).
+  `save_tf_checkpoint` / `load_tf_checkpoint` read and write TensorFlow's own checkpoint format (the `.index` +
+  `.data-00000-of-00001` pair of `tf.train.Saver`, `main.py:163-201`) without TensorFlow (`tf_bundle.py`), so trained
+  `weights{epoch}.ckpt` files of the reference load directly; the flat `.npz` container with the same names as keys stays
+  as the light-weight form.
 * `save_training_state` / `load_training_state` add what `tf.train.Saver()` with no variable list also writes
   (`main.py:163-165`): the Adam slots under TF's slot names `<variable>/Adam` (m) and `<variable>/Adam_1` (v), and the
   `beta1_power` / `beta2_power` accumulators (= beta^step), so a run resumes with the same optimizer trajectory
@@ -36,6 +37,39 @@ def save_checkpoint(path, params, ema_flat=None):
             out[MODEL_SCOPE + name + EMA_SUFFIX] = ema[o:o + n].reshape(shape)
     np.savez(path, **out)
     return list(out)
+
+
+def save_tf_checkpoint(prefix, values, ema_values=None, extra=None):
+    """Write {variable name without the model scope: array} (+ EMA shadows, + extra entries such as global_step) as a real
+    TensorFlow checkpoint `<prefix>.index` / `<prefix>.data-00000-of-00001`, plus the `checkpoint` state file
+    `tf.train.latest_checkpoint` reads (`main.py:171-178`)."""
+    import os
+    from .tf_bundle import write_tensor_bundle
+    out = {MODEL_SCOPE + k: np.asarray(v, dtype=np.float32) for k, v in values.items()}
+    if ema_values is not None:
+        out.update({MODEL_SCOPE + k + EMA_SUFFIX: np.asarray(v, dtype=np.float32) for k, v in ema_values.items()})
+    if extra:
+        out.update(extra)
+    names = write_tensor_bundle(prefix, out)
+    base = os.path.basename(prefix)
+    with open(os.path.join(os.path.dirname(prefix) or ".", "checkpoint"), "w") as fh:
+        fh.write('model_checkpoint_path: "%s"\nall_model_checkpoint_paths: "%s"\n' % (base, base))
+    return names
+
+
+def load_tf_checkpoint(prefix, use_ema=False, verify=True):
+    """{variable name without the model scope: array} from a TensorFlow checkpoint written by the reference (or by
+    `save_tf_checkpoint`), ready for `MACParams(values=...)`; `use_ema=True` substitutes the EMA shadows (`main.py:717-719`).
+    Optimizer slots, power accumulators and variables outside the model scope are skipped."""
+    from .tf_bundle import read_tensor_bundle
+    raw = read_tensor_bundle(prefix, verify=verify)
+    vals = {}
+    for k, v in raw.items():
+        if not k.startswith(MODEL_SCOPE) or k.endswith((EMA_SUFFIX, "/Adam", "/Adam_1")):
+            continue
+        src = k + EMA_SUFFIX if (use_ema and k + EMA_SUFFIX in raw) else k
+        vals[k[len(MODEL_SCOPE):]] = np.asarray(raw[src], dtype=np.float32)
+    return vals
 
 
 ADAM_M, ADAM_V = "/Adam", "/Adam_1"          # tf.train.AdamOptimizer slot names

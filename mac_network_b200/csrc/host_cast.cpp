@@ -136,3 +136,38 @@ extern "C" int mac_host_cast_bf16(const float* src, void* dst_bf16, long long n,
   pool_for(nthreads)->run(src, reinterpret_cast<uint16_t*>(dst_bf16), n);
   return MAC_OK;
 }
+
+// CRC-32C (Castagnoli), the checksum of TensorFlow checkpoint ("tensor bundle") tensors and index blocks
+// (mac_network_b200/tf_bundle.py): hardware instruction where the compiler targets SSE4.2, else a byte table.
+#if defined(__SSE4_2__)
+#include <nmmintrin.h>
+#endif
+extern "C" uint32_t mac_host_crc32c(const void* data, long long n, uint32_t crc) {
+  const unsigned char* p = reinterpret_cast<const unsigned char*>(data);
+  uint32_t c = crc ^ 0xFFFFFFFFu;
+#if defined(__SSE4_2__)
+  uint64_t c64 = c;
+  while (n >= 8) {
+    uint64_t v;
+    memcpy(&v, p, 8);
+    c64 = _mm_crc32_u64(c64, v);
+    p += 8;
+    n -= 8;
+  }
+  c = (uint32_t)c64;
+  while (n-- > 0) c = _mm_crc32_u8(c, *p++);
+#else
+  static uint32_t table[256];
+  static bool init = false;
+  if (!init) {
+    for (uint32_t i = 0; i < 256; ++i) {
+      uint32_t x = i;
+      for (int k = 0; k < 8; ++k) x = (x >> 1) ^ ((x & 1u) ? 0x82F63B78u : 0u);
+      table[i] = x;
+    }
+    init = true;
+  }
+  while (n-- > 0) c = table[(c ^ *p++) & 0xFFu] ^ (c >> 8);
+#endif
+  return c ^ 0xFFFFFFFFu;
+}
