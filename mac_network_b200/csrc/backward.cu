@@ -231,38 +231,73 @@ __global__ void __launch_bounds__(256) kb_attend_bwd_kernel(const float* __restr
 //   T = I1*c ; I2 = ELU(T) ; I2d = I2*mask*scale ; kl = I2d.wr + br
 //   dI2 = dkl*wr*mask*scale ; dT = dI2*ELU'(T) ; dI1 = dT*c ; dc[b,:] += sum_n dT*I1 ; dwr_part[b,:] += sum_n dkl*I2d
 //   dbm2_part[b,:] += sum_n dI1
-// grid (ceil(d/128), B), 128 threads (column per thread, loop over the sample's N rows)
-__global__ void __launch_bounds__(128) read_bwd_logits_kernel(
+// grid (ceil(d/128), B), 256 threads: thread = (column quad q = tid % 32: 4 consecutive columns, row group rg = tid / 32 of 8).
+// One Philox draw serves the quad's four elements (round 1: one thread per column recomputed the draw four times and walked the
+// N rows serially: 131 us per launch, 11.7 % of a tensor-core training step); the eight row groups are reduced in shared memory
+// in a fixed order, so the per-sample sums stay deterministic.
+__global__ void __launch_bounds__(256) read_bwd_logits_kernel(
     const float* __restrict__ I1, const float* __restrict__ ctrl, const float* __restrict__ wr,
     const float* __restrict__ dkl, uint32_t thresh, float scale, uint64_t seed, int step, float* __restrict__ dI1,
     float* __restrict__ dc, float* __restrict__ dwr_part, float* __restrict__ dbm2_part, int N, int d) {
-  const int k = blockIdx.x * 128 + threadIdx.x, b = blockIdx.y;
-  if (k >= d) return;
-  const float c = ctrl[(size_t)b * d + k], w = __ldg(wr + k);
-  float sdc = 0.f, sdw = 0.f, sdb = 0.f;
-  for (int n = 0; n < N; ++n) {
-    const size_t row = (size_t)b * N + n;
-    const float i1 = I1[row * d + k];
-    const float t = i1 * c;
-    const float i2 = elu_f(t);
-    float m = 1.f;
-    if (thresh) {
-      const uint64_t e = row * (uint64_t)d + (uint64_t)k;
-      const Philox4 r = philox4x32_10(seed, e >> 2, MAC_SITE_READ_INTER, (uint32_t)step);
-      const uint32_t bits = (k & 3) == 0 ? r.x : (k & 3) == 1 ? r.y : (k & 3) == 2 ? r.z : r.w;
-      m = ((bits >> 8) >= thresh) ? scale : 0.f;
+  __shared__ float s_red[3][8][128];
+  const int q = threadIdx.x & 31, rg = threadIdx.x >> 5, b = blockIdx.y;
+  const int k = blockIdx.x * 128 + q * 4;
+  const bool ok = k < d;                       // d % 4 == 0: a quad is inside or outside as a whole
+  float sdc[4] = {0.f, 0.f, 0.f, 0.f}, sdw[4] = {0.f, 0.f, 0.f, 0.f}, sdb[4] = {0.f, 0.f, 0.f, 0.f};
+  if (ok) {
+    const float4 c4 = *reinterpret_cast<const float4*>(ctrl + (size_t)b * d + k);
+    const float4 w4 = __ldg(reinterpret_cast<const float4*>(wr + k));
+    const float c[4] = {c4.x, c4.y, c4.z, c4.w}, w[4] = {w4.x, w4.y, w4.z, w4.w};
+    for (int n = rg; n < N; n += 8) {
+      const size_t row = (size_t)b * N + n;
+      const float4 i4 = *reinterpret_cast<const float4*>(I1 + row * d + k);
+      const float i1[4] = {i4.x, i4.y, i4.z, i4.w};
+      float m[4] = {1.f, 1.f, 1.f, 1.f};
+      if (thresh) {
+        const uint64_t e = row * (uint64_t)d + (uint64_t)k;
+        const Philox4 r = philox4x32_10(seed, e >> 2, MAC_SITE_READ_INTER, (uint32_t)step);
+        m[0] = ((r.x >> 8) >= thresh) ? scale : 0.f;
+        m[1] = ((r.y >> 8) >= thresh) ? scale : 0.f;
+        m[2] = ((r.z >> 8) >= thresh) ? scale : 0.f;
+        m[3] = ((r.w >> 8) >= thresh) ? scale : 0.f;
+      }
+      const float g = dkl[row];
+      float o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float t = i1[j] * c[j];
+        const float i2 = elu_f(t);
+        const float dT = g * w[j] * m[j] * (t > 0.f ? 1.f : i2 + 1.f);
+        o[j] = dT * c[j];
+        sdc[j] = fmaf(dT, i1[j], sdc[j]);
+        sdw[j] = fmaf(g, i2 * m[j], sdw[j]);
+        sdb[j] += o[j];
+      }
+      *reinterpret_cast<float4*>(dI1 + row * d + k) = make_float4(o[0], o[1], o[2], o[3]);
     }
-    const float g = dkl[row];
-    const float dT = g * w * m * (t > 0.f ? 1.f : i2 + 1.f);
-    const float di1 = dT * c;
-    dI1[row * d + k] = di1;
-    sdc = fmaf(dT, i1, sdc);
-    sdw = fmaf(g, i2 * m, sdw);
-    sdb += di1;
   }
-  dc[(size_t)b * d + k] += sdc;
-  dwr_part[(size_t)b * d + k] += sdw;
-  dbm2_part[(size_t)b * d + k] += sdb;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    s_red[0][rg][q * 4 + j] = sdc[j];
+    s_red[1][rg][q * 4 + j] = sdw[j];
+    s_red[2][rg][q * 4 + j] = sdb[j];
+  }
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int kk = blockIdx.x * 128 + threadIdx.x;
+    if (kk < d) {
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        a0 += s_red[0][g][threadIdx.x];
+        a1 += s_red[1][g][threadIdx.x];
+        a2 += s_red[2][g][threadIdx.x];
+      }
+      dc[(size_t)b * d + kk] += a0;
+      dwr_part[(size_t)b * d + kk] += a1;
+      dbm2_part[(size_t)b * d + kk] += a2;
+    }
+  }
 }
 
 // dP = dI0[:, :d]*y + dI0[:, d:] ; dy[b,:] = sum_n dI0[:, :d]*P ; dbx_part[b,:] += sum_n dP     (ops.py:694-719)
@@ -452,7 +487,7 @@ extern "C" int mac_read_bwd(const float* kb, const float* memory_in, const float
   st = mac_kb_attend_bwd(kb, att, dinfo, dka, dkl, dkb, dbr_part, B, N, d, stream_);
   if (st != MAC_OK) return st;
   // (2) logits epilogue backward -> dI1, dcontrol, dwr, dbm2
-  read_bwd_logits_kernel<<<dim3((d + 127) / 128, B), 128, 0, stream>>>(I1, control, w->wr, dkl, thr, scale, seed, step,
+  read_bwd_logits_kernel<<<dim3((d + 127) / 128, B), 256, 0, stream>>>(I1, control, w->wr, dkl, thr, scale, seed, step,
                                                                       bufA, dcontrol, dwr_part, dbm2_part, N, d);
   MAC_LAUNCH_CHECK();
   // (3) I1 = H @ Wm2 + bm2:  dWm2 += H^T dI1 ;  dZ = (dI1 @ Wm2^T) * ELU'(Z)
@@ -546,13 +581,16 @@ extern "C" int mac_read_bwd(const float* kb, const float* memory_in, const float
 // dropout mask on dKB); the arithmetic of every pass is the forward's, so the masks and saved tensors are shared.
 // Requires d % 128 == 0 and (B*N) % 64 == 0 (the UMMA K block); otherwise MAC_ERR_UNSUPPORTED (use mac_read_bwd).
 // ------------------------------------------------------------------------------------------------------------------
+extern "C" int mac_tc_wgrad_splitk_(const void* xT, const void* gT, float* dW, float* partial, int in_dim, int out_dim, int K,
+                                    mac_stream_t stream_);
+extern "C" size_t mac_tc_wgrad_partial_bytes_(int in_dim, int out_dim);
 static size_t rbt_align(size_t x) { return (x + 1023) & ~(size_t)1023; }
 
 extern "C" size_t mac_read_bwd_tc_workspace_bytes(int B, int N, int d) {
   const size_t M = (size_t)B * N;
   return mac_read_bwd_workspace_bytes(B, N, d) + 1024 + rbt_align(M * 2 * d * 2) /*g16*/ + rbt_align(2 * d * M * 2) /*xT16*/ +
          rbt_align(d * M * 2) /*gT16*/ + rbt_align((size_t)2 * d * d * 2) /*w16*/ + rbt_align(M * 2 * d * 4) /*tmp32*/ +
-         rbt_align((size_t)2 * d * d * 4) /*dWtmp*/;
+         rbt_align(mac_tc_wgrad_partial_bytes_(2 * d, d)) /*dWtmp: split-K partials of the largest weight gradient*/;
 }
 
 extern "C" int mac_read_bwd_tc(const float* kb, const float* memory_in, const float* control, const mac_read_weights* w,
@@ -606,9 +644,7 @@ extern "C" int mac_read_bwd_tc(const float* kb, const float* memory_in, const fl
   auto wgrad = [&](const void* xT, int in, const float* G, float* dW) -> int {
     int s = mac_pack_weight_bf16(G, gT16, M, d, stream_);                                   // G [M, d] -> G^T [d, M]
     if (s != MAC_OK) return s;
-    s = mac_linear_tc_fwd(xT, gT16, nullptr, MAC_ACT_NON, dWtmp, 0, in, M, d, stream_);     // [in, d] = xT @ (G^T)^T
-    if (s != MAC_OK) return s;
-    return mac_axpy(dW, dWtmp, 1.f, (long long)in * d, stream_);
+    return mac_tc_wgrad_splitk_(xT, gT16, dW, dWtmp, in, d, M, stream_);                          // dW[in, d] += xT @ (G^T)^T, split-K
   };
   // dgrad: out[M, in] = G[M, d] @ W[in, d]^T   (W fp32 in its own [in, out = d] layout)
   auto dgrad = [&](const float* G, const float* W, int in, float* out) -> int {
@@ -621,7 +657,7 @@ extern "C" int mac_read_bwd_tc(const float* kb, const float* memory_in, const fl
   // (1) info = sum_n att*KB ; att = softmax(kl):  dkl, dKB += att (x) dinfo
   RBT(mac_kb_attend_bwd(kb, att, dinfo, dka, dkl, dkb, dbr_part, B, N, d, stream_));
   // (2) logits epilogue backward -> dI1 (bufA), dcontrol, dwr, dbm2
-  read_bwd_logits_kernel<<<dim3((d + 127) / 128, B), 128, 0, stream>>>(I1, control, w->wr, dkl, thr, scale, seed, step,
+  read_bwd_logits_kernel<<<dim3((d + 127) / 128, B), 256, 0, stream>>>(I1, control, w->wr, dkl, thr, scale, seed, step,
                                                                       bufA, dcontrol, dwr_part, dbm2_part, N, d);
   MAC_LAUNCH_CHECK();
   // (3) I1 = H @ Wm2 + bm2:  dWm2 += H^T dI1 ;  dZ = (dI1 @ Wm2^T) * ELU'(H)

@@ -51,6 +51,8 @@ struct TcGemmParams {
   float e_scale;
   uint64_t seed;
   int e_site, step;
+  int ksplit;              // split-K (TC_EPI_F32 only, single-CTA kernel): the K range is cut into `ksplit` equal slices, each an
+  long long split_stride;  //   extra "tile" writing its fp32 partial to outf + slice * split_stride; 0 / 1 = off
   int debug;               // MAC_TC_DEBUG (profiling experiments only): 1 skip epilogue math/stores, 2 skip MMA, 4 skip TMA
 };
 
@@ -205,8 +207,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = (p.M + TC_BM - 1) / TC_BM;
   const int n_tiles = p.N / BN;
-  const int num_tiles = m_tiles * n_tiles;
-  const int kblocks = p.K / TC_BK;
+  const int ksplit = p.ksplit > 1 ? p.ksplit : 1;
+  const int mn_tiles = m_tiles * n_tiles;
+  const int num_tiles = mn_tiles * ksplit;                 // tile t = (K slice t / mn_tiles, output tile t % mn_tiles)
+  const int kblocks = p.K / TC_BK / ksplit;                // k-blocks per slice
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a0);
@@ -235,8 +239,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int mt = t / n_tiles, nt = t % n_tiles;
-        for (int kb = 0; kb < kblocks; ++kb) {
+        const int tt = t % mn_tiles, kb0 = (t / mn_tiles) * kblocks;
+        const int mt = tt / n_tiles, nt = tt % n_tiles;
+        for (int kb = kb0; kb < kb0 + kblocks; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           unsigned char* sa = tiles + stage * C::STAGE_BYTES;
           unsigned char* sb = sa + C::A_BYTES;
@@ -346,7 +351,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     const float* vec_src = (EPI == TC_EPI_P) ? p.y : (EPI == TC_EPI_LOGITS ? p.ctrl : nullptr);
     int it = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-      const int mt = t / n_tiles, nt = t % n_tiles;
+      const int tt = t % mn_tiles;
+      const int mt = tt / n_tiles, nt = tt % n_tiles;
+      float* const outf_t = p.outf + (size_t)(t / mn_tiles) * (size_t)p.split_stride;      // split-K partial (slice 0: outf)
       const int acc = it % C::NBUF;
       const uint32_t acc_phase = (it / C::NBUF) & 1;
       // ---- stage this tile's parameters in shared memory while the MMAs of the tile are still running:
@@ -485,7 +492,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             w0[j + 2] = act_ct<ACT>(__uint_as_float(r[j + 2]) + b0.z);
             w0[j + 3] = act_ct<ACT>(__uint_as_float(r[j + 3]) + b0.w);
           }
-          store_f32_chunk(w0, p.outf, row0, n0);
+          store_f32_chunk(w0, outf_t, row0, n0);
         } else {  // TC_EPI_LOGITS
           const float4* c4 = vec_smem ? reinterpret_cast<const float4*>(vrow + c0)
                                       : reinterpret_cast<const float4*>(p.ctrl + (size_t)bidx * p.N + n0);
@@ -891,7 +898,7 @@ inline int tc_gemm_launch_t(const CUtensorMap& ma0, const CUtensorMap& ma1, cons
                             const TcGemmParams& p, cudaStream_t stream) {
   auto kern = tc_gemm_kernel<BM, BN, EPI, ACT>;
   MAC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BM, BN>::SMEM_BYTES));
-  const int tiles = ((p.M + BM - 1) / BM) * (p.N / BN);
+  const int tiles = ((p.M + BM - 1) / BM) * (p.N / BN) * (p.ksplit > 1 ? p.ksplit : 1);
   // persistent grid balanced over the rounds: same makespan as one CTA per SM, but e.g. 196 tiles run as 98 CTAs x 2
   // tiles (epilogue of the first overlaps the MMAs of the second) and leave 50 SMs to concurrent streams
   const int rounds = (tiles + tc_num_sms() - 1) / tc_num_sms();
@@ -1012,7 +1019,7 @@ inline int tc_gemm_launch(const void* a0, int K0, const void* a1, int K1, const 
   bool pair = false;
   if (const char* e = getenv("MAC_TC_PAIR"))
     pair = atoi(e) != 0 && (p.N % 256 == 0) && p.M > 128 && p.epi != TC_EPI_ADDACT && p.epi != TC_EPI_ACT_SPLIT &&
-           lda0 == K0 && lda1 == K1;
+           lda0 == K0 && lda1 == K1 && p.ksplit <= 1;
   if (pair) {
     if (nparts_per_row) *nparts_per_row = (p.N / 256) * 2;
     p.K = K0 + K1;
@@ -1212,6 +1219,52 @@ inline int tc_read_chain_inv(const void* inv, const float* y, const float* contr
   return tc_gemm_launch(H, d, nullptr, 0, w->Wm2_bf16, p, stream, nparts);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Weight gradients on tensor cores: dW[in, out] (+)= X^T[in, M] @ G^T[out, M]^T with K = M = B*N (12 544 at the headline shape)
+// and only (in/128) x (out/256) = 8-16 output tiles: one K loop of 196 k-blocks per CTA left 130+ SMs idle (44.7 us per
+// launch, 12 % of a tensor-core training step).  Split-K: the K range is cut into S slices, every (slice, tile) is a tile of the
+// persistent kernel and writes its fp32 partial; the partials are summed in slice order (deterministic) into dW.
+__global__ void splitk_accum_kernel(const float4* __restrict__ part, float4* __restrict__ dst, long long n4, int S,
+                                    long long stride4, int accumulate) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 a = accumulate ? dst[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s_ = 0; s_ < S; ++s_) {
+    const float4 v = part[i + s_ * stride4];
+    a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+  }
+  dst[i] = a;
+}
+
+// largest S <= 28 that divides K / 64, keeps >= 2 k-blocks per slice and at most two waves of tiles
+inline int tc_pick_ksplit(int K, int out_tiles) {
+  const int kblocks = K / TC_BK;
+  int best = 1;
+  for (int S = 2; S <= 28; ++S)
+    if (kblocks % S == 0 && kblocks / S >= 2 && out_tiles * S <= 2 * tc_num_sms()) best = S;
+  return best;
+}
+inline size_t tc_wgrad_partial_bytes(int in_dim, int out_dim) { return (size_t)28 * in_dim * out_dim * 4; }
+
+// dW[in, out] += xT[in, K] @ gT[out, K]^T   (both bf16, K-major); `partial` holds tc_wgrad_partial_bytes(in, out)
+inline int tc_wgrad_splitk(const void* xT, const void* gT, float* dW, float* partial, int in_dim, int out_dim, int K,
+                           cudaStream_t stream) {
+  if ((in_dim % 128) || (out_dim % 128) || (K % TC_BK)) return MAC_ERR_UNSUPPORTED;
+  TcGemmParams p{};
+  p.M = in_dim; p.N = out_dim; p.act = MAC_ACT_NON; p.bias = nullptr; p.ldo = out_dim; p.rows_per_batch = 1;
+  p.epi = TC_EPI_F32; p.outf = partial;
+  const int out_tiles = (in_dim / 128) * (out_dim / (out_dim % 256 == 0 ? 256 : 128));
+  const int S = tc_pick_ksplit(K, out_tiles);
+  p.ksplit = S; p.split_stride = (long long)in_dim * out_dim;
+  int st = tc_gemm_launch(xT, K, nullptr, 0, gT, p, stream);
+  if (st != MAC_OK) return st;
+  const long long n4 = (long long)in_dim * out_dim / 4;
+  splitk_accum_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const float4*>(partial),
+                                                                       reinterpret_cast<float4*>(dW), n4, S, n4, 1);
+  MAC_LAUNCH_CHECK();
+  return MAC_OK;
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // "tc32": the read unit's three [B*N, .] projections as SPLIT-bf16 products on the tensor cores, for the <= 1e-4 parity bar

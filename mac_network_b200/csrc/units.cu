@@ -482,6 +482,13 @@ extern "C" int mac_pack_weight_bf16(const float* W, void* Wt_bf16, int K, int N,
   return MAC_OK;
 }
 
+// internal (not in the ABI header): split-K weight gradient for backward.cu, which does not include the tensor-core templates
+extern "C" int mac_tc_wgrad_splitk_(const void* xT, const void* gT, float* dW, float* partial, int in_dim, int out_dim, int K,
+                                    mac_stream_t stream_) {
+  return tc_wgrad_splitk(xT, gT, dW, partial, in_dim, out_dim, K, reinterpret_cast<cudaStream_t>(stream_));
+}
+extern "C" size_t mac_tc_wgrad_partial_bytes_(int in_dim, int out_dim) { return tc_wgrad_partial_bytes(in_dim, out_dim); }
+
 extern "C" int mac_pack_weight_split3(const float* W, void* Wt3_bf16, int K, int N, mac_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (!W || !Wt3_bf16 || K <= 0 || N <= 0) return MAC_ERR_INVALID;

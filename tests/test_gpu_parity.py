@@ -275,11 +275,12 @@ def test_step_invariant_read_hoist_is_the_same_function(monkeypatch, prec, varia
 
 
 @pytest.mark.parametrize("prec", ["bf16", "fp32"])
-def test_host_pipeline_matches_direct_cell(prec):
+def test_host_pipeline_matches_direct_cell(prec, monkeypatch):
     """serving.HostPipeline (host fp32 in -> [host bf16 cast] -> H2D -> graph -> D2H) returns what the cell computes from
     device-resident inputs; in-flight slots do not mix batches up."""
     from mac_network_b200.mac_cell import MACParams
     from mac_network_b200.serving import HostPipeline
+    monkeypatch.setenv("MAC_SMALL_TC", "1")      # the pipeline's cells use the throughput form (small_tc): same form for the direct cell
     B, S, N, d, L = 8, 6, 49, 128, 3
     cfg = MACConfig.args("args", netLength=L, memDim=d, ctrlDim=d, attDim=d)
     pv = perturb_biases(init_params(cfg, L, seed=82), seed=83)
