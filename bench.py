@@ -80,6 +80,14 @@ def peaks():
     return {"hbm": 6650.0, "tensor_burst": 1590.0, "tensor_sustained": 1400.0, "src": "fallback (B200_PROFILING.md)"}
 
 
+def local_device():
+    """This rank's CUDA device: LOCAL_RANK, re-ordered so that a job of fewer ranks than GPUs spreads over the sockets
+    (serving.device_for_rank: GPUs 0-3 hang off NUMA node 0 and 4-7 off node 1 on the 8-GPU boxes)."""
+    from mac_network_b200.serving import device_for_rank
+    lr = int(os.environ.get("LOCAL_RANK", "0"))
+    return device_for_rank(lr, int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1"))))
+
+
 class ClockSampler(object):
     """nvidia-smi sampled DURING the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -88,6 +96,15 @@ class ClockSampler(object):
 
     def __init__(self, index):
         self.index, self.proc, self.lines = index, None, []
+        try:        # address the GPU by PCI bus id: the CUDA index is not nvidia-smi's when devices are masked / re-ordered
+            prop = torch.cuda.get_device_properties(index)
+            bus = "%08x:%02x:%02x.0" % (getattr(prop, "pci_domain_id", 0), prop.pci_bus_id, prop.pci_device_id)
+            out = subprocess.run(["nvidia-smi", "-i", bus, "--query-gpu=index", "--format=csv,noheader"],
+                                 capture_output=True, text=True, timeout=20)
+            if out.returncode == 0 and out.stdout.strip().isdigit():
+                self.index = int(out.stdout.strip())
+        except Exception:
+            pass
 
     def start(self):
         try:
@@ -474,7 +491,7 @@ def run_ours(args):
     from mac_network_b200.mac_cell import MACParams
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    local = local_device()
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
@@ -493,6 +510,7 @@ def run_ours(args):
         dist.all_gather_object(nodes, numa.get("numa_node", -1))
         ranks_on_node = max(1, sum(1 for x in nodes if x == numa.get("numa_node", -1)))
     numa["ranks_on_node"] = ranks_on_node
+    numa["cuda_device"] = local
     shape = SHAPES[WORKLOAD]
     B, S, N, d, L = shape
     cfg = MACConfig.args("args", netLength=L)
@@ -796,7 +814,7 @@ def run_train(args):
     from mac_network_b200.dp import DPTrainer
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    local = local_device()
     torch.cuda.set_device(local)
     dist = None
     if world > 1:

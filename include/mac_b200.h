@@ -313,6 +313,28 @@ size_t mac_read_bwd_tc_workspace_bytes(int B, int N, int d);
 /* write gate (mac_cell.py:358-367): dmnew = g*z; dmprev += g*(1-z); dpre = g*(mnew-mprev)*z*(1-z) */
 int mac_gate_bwd(const float* g, const float* z, const float* mnew, const float* mprev, float* dmnew, float* dmprev,
                  float* dpre, long long n, mac_stream_t stream);
+/* backward of mac_bcast_op (ops.mul on a broadcast operand, ops.py:694-713), g = dL/dout [B,N,d]; dx [B,N,d] +=, dv [B,d] +=,
+ * dbias_part [B,d] += (mode 1 only); any of the three may be NULL.  `out` (the forward result) is read by mode 2 only. */
+int mac_bcast_op_bwd(const float* x, const float* v, const float* out, const float* g, int mode, float mul_bias, float* dx,
+                     float* dv, float* dbias_part, int B, int N, int d, mac_stream_t stream);
+/* backward of mac_rowdot_fwd (ops.linear with outDim == 1, ops.py:316-317), g = dL/dout [R]: dx_s [R,k_s] += g (x) w_s
+ * (entries / the array may be NULL), dw [sum k] +=, db [1] += (may be NULL).  Deterministic: per-64-row partial sums in the
+ * workspace (mac_rowdot_bwd_workspace_bytes), reduced in block order. */
+int mac_rowdot_bwd(const float* const* x_segs, const int* k_segs, const int* ldx, int nseg, const float* w, const float* g,
+                   float* const* dx_segs, const int* ld_dx, float* dw, float* db, void* workspace, size_t workspace_bytes,
+                   long long R, mac_stream_t stream);
+size_t mac_rowdot_bwd_workspace_bytes(long long R, int k_total);
+/* Batch normalisation of the new memory (mac_cell.py:369-373: tf.contrib.layers.batch_norm(newMemory, decay, center, scale,
+ * is_training, updates_collections=None), epsilon 0.001; rank-2 input = TF's fused path).  x, y [B,d] (y may alias x).
+ * training != 0: batch mean / biased variance normalise, and moving_mean / moving_var move IN PLACE by (1 - decay) towards the
+ * batch mean / the Bessel-corrected batch variance; training == 0: the stored statistics normalise.  gamma / beta may be NULL
+ * (scale / center off).  save_mean, save_invstd [d] are what mac_batchnorm_bwd needs. */
+int mac_batchnorm_fwd(const float* x, const float* gamma, const float* beta, float* moving_mean, float* moving_var, float decay,
+                      float eps, int training, float* y, float* save_mean, float* save_invstd, int B, int d,
+                      mac_stream_t stream);
+/* dx [B,d] += , dgamma [d] +=, dbeta [d] += (each may be NULL); training as in the forward (eval: the statistics are constants) */
+int mac_batchnorm_bwd(const float* x, const float* gamma, const float* save_mean, const float* save_invstd, const float* dy,
+                      int training, float* dx, float* dgamma, float* dbeta, int B, int d, mac_stream_t stream);
 /* dx = dy * act'(.) given the saved activation OUTPUT y */
 int mac_activation_bwd(const float* y, const float* dy, int act, float* dx, long long n, mac_stream_t stream);
 /* out[b,k] (+)= sum_n x[b,n,k] */
@@ -334,6 +356,7 @@ size_t mac_optimizer_workspace_bytes(void);
 /* ------------------------------------------------------------------------------------------------
  * Answer loss of the output unit ("next" row, model.py:593-596): mean sparse softmax cross entropy.
  *   losses[b] = logsumexp(logits[b,:]) - logits[b, labels[b]];  dlogits = (softmax - onehot) * scale
+ *   A label outside [0, A) gives losses[b] = NaN (like TF's GPU kernel) and no one-hot term; nothing is read out of bounds.
  * --------------------------------------------------------------------------------------------- */
 int mac_softmax_xent(const float* logits, const int32_t* labels, float* losses, float* dlogits, float scale,
                      int B, int A, mac_stream_t stream);

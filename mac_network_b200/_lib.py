@@ -83,6 +83,12 @@ PROTOTYPES = {
     "mac_read_bwd_tc_workspace_bytes": (c_sz, [c_int, c_int, c_int]),
     "mac_gate_bwd": (c_int, [c_fp] * 7 + [c_ll, c_fp]),
     "mac_activation_bwd": (c_int, [c_fp, c_fp, c_int, c_fp, c_ll, c_fp]),
+    "mac_batchnorm_fwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_f, c_f, c_int, c_fp, c_fp, c_fp, c_int, c_int, c_fp]),
+    "mac_batchnorm_bwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_fp, c_fp, c_fp, c_int, c_int, c_fp]),
+    "mac_bcast_op_bwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_int, c_f, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_fp]),
+    "mac_rowdot_bwd": (c_int, [ctypes.POINTER(c_fp), ctypes.POINTER(c_int), ctypes.POINTER(c_int), c_int, c_fp, c_fp,
+                               ctypes.POINTER(c_fp), ctypes.POINTER(c_int), c_fp, c_fp, c_fp, ctypes.c_size_t, c_ll, c_fp]),
+    "mac_rowdot_bwd_workspace_bytes": (ctypes.c_size_t, [c_ll, c_int]),
     "mac_colsum": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_int, c_fp]),
     "mac_axpy": (c_int, [c_fp, c_fp, c_f, c_ll, c_fp]),
     "mac_clip_adam_ema_step": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_ll, c_f, c_f, c_f, c_f, c_f, c_f, c_int, c_f, c_fp, c_fp,

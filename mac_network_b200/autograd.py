@@ -294,4 +294,8 @@ def mac_backward(cell, d_control, d_memory, bucket=None, zero_bucket=True, d_vec
     `tc=True`: the read unit's projections on tensor cores in backward too (bf16 operands, fp32 accumulation)."""
     if not getattr(cell, "save_for_backward", False):
         raise RuntimeError("construct the MACCell with save_for_backward=True and run the forward first")
+    if getattr(cell, "_tape", None) is not None:       # flags outside the hand-scheduled sweep: node-by-node (tape.py)
+        if tc:
+            raise NotImplementedError("the tape backward runs the fp32 kernels")
+        return cell._tape.run(d_control, d_memory, bucket, zero_bucket, d_vecq)
     return _Bwd(cell, bucket, zero_bucket, tc=tc).run(d_control, d_memory, d_vecq)

@@ -12,7 +12,6 @@ from dataclasses import dataclass
 # flags of the reference that crash in the reference itself: rejected, not emulated
 _BROKEN = {
     "addNullWord": "mac_cell.py:519,574 (method lacks self; questionLengths undefined)",
-    "memoryBN": "outside hot-path scope (tf.contrib batch_norm, mac_cell.py:370-373)",
     "readCtrlConcatInter": "mac_cell.py:248-266 (dim not updated -> shape mismatch)",
     "writeGateShared": "mac_cell.py:359-367 ([B,d]*[B] does not broadcast)",
 }
@@ -74,7 +73,10 @@ class MACConfig:
     writeGate: bool = False
     writeGateShared: bool = False
     writeGateBias: float = 1.0
-    memoryBN: bool = False
+    memoryBN: bool = False        # batch normalisation of the new memory (mac_cell.py:369-373; config.py:194-199)
+    bnDecay: float = 0.999
+    bnCenter: bool = False
+    bnScale: bool = False
     # dropouts (config.py:202-213) and nonlinearity (config.py:219-223)
     memoryDropout: float = 0.85
     readDropout: float = 0.85

@@ -32,15 +32,43 @@ __global__ void act_bwd_kernel(const float* __restrict__ y, const float* __restr
   dx[i] = dy[i] * g;
 }
 
-// out[b, k] (+)= sum_n x[b, n, k]     grid (ceil(d/128), B), 128 threads
-__global__ void colsum_kernel(const float* __restrict__ x, float* __restrict__ out, int N, int d, int accumulate) {
-  const int k = blockIdx.x * 128 + threadIdx.x, b = blockIdx.y;
-  if (k >= d) return;
-  const float* p = x + (size_t)b * N * d + k;
-  float s = 0.f;
-  for (int n = 0; n < N; ++n) s += p[(size_t)n * d];
-  float* o = out + (size_t)b * d + k;
-  *o = accumulate ? *o + s : s;
+// out[b, k] (+)= sum_n x[b, n, k]     grid (ceil(d/128), B), 256 threads = 32 column quads x 8 row groups (fixed-order reduce)
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, float* __restrict__ out, int N, int d,
+                                                    int accumulate) {
+  __shared__ float s_red[8][128];
+  const int q = threadIdx.x & 31, rg = threadIdx.x >> 5, b = blockIdx.y;
+  const int k = blockIdx.x * 128 + q * 4;
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
+  if (k < d) {
+    const float* p = x + (size_t)b * N * d + k;
+    if (((d & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0)) {
+      for (int n = rg; n < N; n += 8) {
+        const float4 v = *reinterpret_cast<const float4*>(p + (size_t)n * d);
+        s[0] += v.x;
+        s[1] += v.y;
+        s[2] += v.z;
+        s[3] += v.w;
+      }
+    } else {                                   // any width (classifier outputs, outDim == 1): scalar loads
+      for (int n = rg; n < N; n += 8)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (k + j < d) s[j] += p[(size_t)n * d + j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) s_red[rg][q * 4 + j] = s[j];
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int kk = blockIdx.x * 128 + threadIdx.x;
+    if (kk < d) {
+      float a = 0.f;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) a += s_red[g][threadIdx.x];
+      float* o = out + (size_t)b * d + kk;
+      *o = accumulate ? *o + a : a;
+    }
+  }
 }
 
 // write gate backward (mac_cell.py:358-367): m = m'*z + mprev*(1-z), z = sigmoid(pre)
@@ -301,29 +329,222 @@ __global__ void __launch_bounds__(256) read_bwd_logits_kernel(
 }
 
 // dP = dI0[:, :d]*y + dI0[:, d:] ; dy[b,:] = sum_n dI0[:, :d]*P ; dbx_part[b,:] += sum_n dP     (ops.py:694-719)
-__global__ void __launch_bounds__(128) read_bwd_p_kernel(const float* __restrict__ dI0, const float* __restrict__ P,
+// Same thread map as read_bwd_logits_kernel: 32 column quads x 8 row groups, 16-byte accesses, fixed-order reduction.
+__global__ void __launch_bounds__(256) read_bwd_p_kernel(const float* __restrict__ dI0, const float* __restrict__ P,
                                                         const float* __restrict__ y, float* __restrict__ dP,
                                                         float* __restrict__ dy, float* __restrict__ dbx_part, int N,
                                                         int d) {
-  const int k = blockIdx.x * 128 + threadIdx.x, b = blockIdx.y;
-  if (k >= d) return;
-  const float yk = y[(size_t)b * d + k];
-  float sdy = 0.f, sdb = 0.f;
-  for (int n = 0; n < N; ++n) {
-    const size_t row = (size_t)b * N + n;
-    const float top = dI0[row * 2 * d + k], bot = dI0[row * 2 * d + d + k];
-    const float dp = top * yk + bot;
-    dP[row * d + k] = dp;
-    sdy = fmaf(top, P[row * d + k], sdy);
-    sdb += dp;
+  __shared__ float s_red[2][8][128];
+  const int q = threadIdx.x & 31, rg = threadIdx.x >> 5, b = blockIdx.y;
+  const int k = blockIdx.x * 128 + q * 4;
+  float sdy[4] = {0.f, 0.f, 0.f, 0.f}, sdb[4] = {0.f, 0.f, 0.f, 0.f};
+  if (k < d) {
+    const float4 y4 = *reinterpret_cast<const float4*>(y + (size_t)b * d + k);
+    for (int n = rg; n < N; n += 8) {
+      const size_t row = (size_t)b * N + n;
+      const float4 top = *reinterpret_cast<const float4*>(dI0 + row * 2 * d + k);
+      const float4 bot = *reinterpret_cast<const float4*>(dI0 + row * 2 * d + d + k);
+      const float4 p4 = *reinterpret_cast<const float4*>(P + row * d + k);
+      float4 o;
+      o.x = fmaf(top.x, y4.x, bot.x);
+      o.y = fmaf(top.y, y4.y, bot.y);
+      o.z = fmaf(top.z, y4.z, bot.z);
+      o.w = fmaf(top.w, y4.w, bot.w);
+      *reinterpret_cast<float4*>(dP + row * d + k) = o;
+      sdy[0] = fmaf(top.x, p4.x, sdy[0]);
+      sdy[1] = fmaf(top.y, p4.y, sdy[1]);
+      sdy[2] = fmaf(top.z, p4.z, sdy[2]);
+      sdy[3] = fmaf(top.w, p4.w, sdy[3]);
+      sdb[0] += o.x;
+      sdb[1] += o.y;
+      sdb[2] += o.z;
+      sdb[3] += o.w;
+    }
   }
-  dy[(size_t)b * d + k] = sdy;
-  dbx_part[(size_t)b * d + k] += sdb;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    s_red[0][rg][q * 4 + j] = sdy[j];
+    s_red[1][rg][q * 4 + j] = sdb[j];
+  }
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int kk = blockIdx.x * 128 + threadIdx.x;
+    if (kk < d) {
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        a0 += s_red[0][g][threadIdx.x];
+        a1 += s_red[1][g][threadIdx.x];
+      }
+      dy[(size_t)b * d + kk] = a0;
+      dbx_part[(size_t)b * d + kk] += a1;
+    }
+  }
+}
+
+// Backward of mac_bcast_op (ops.mul interaction on a broadcast operand, ops.py:694-713).  g = dL/dout [B,N,d]:
+//   mode 0 MUL: dx += g*(v+mb) ; dv[b,:] += sum_n g*(x+mb)
+//   mode 1 BL : dx += g*v      ; dv[b,:] += sum_n g*x ; dbias_part[b,:] += sum_n g
+//   mode 2 ADD: t = g*(1-out^2): dx += t ; dv[b,:] += sum_n t
+// grid (ceil(d/128), B), 256 threads = 128 columns x 2 row groups; the two groups are added in a fixed order.
+__global__ void __launch_bounds__(256) bcast_op_bwd_kernel(const float* __restrict__ x, const float* __restrict__ v,
+                                                          const float* __restrict__ out, const float* __restrict__ g,
+                                                          int mode, float mb, float* __restrict__ dx,
+                                                          float* __restrict__ dv, float* __restrict__ dbias_part, int N,
+                                                          int d) {
+  __shared__ float s_red[2][128];
+  const int col = threadIdx.x & 127, rg = threadIdx.x >> 7, b = blockIdx.y;
+  const int k = blockIdx.x * 128 + col;
+  float sv = 0.f, sb = 0.f;
+  if (k < d) {
+    const float vk = v[(size_t)b * d + k];
+    for (int n = rg; n < N; n += 2) {
+      const size_t i = ((size_t)b * N + n) * d + k;
+      const float gi = g[i];
+      float gx, gv;
+      if (mode == 0) {
+        gx = gi * (vk + mb);
+        gv = gi * (x[i] + mb);
+      } else if (mode == 1) {
+        gx = gi * vk;
+        gv = gi * x[i];
+        sb += gi;
+      } else {
+        const float o = out[i];
+        gx = gv = gi * (1.f - o * o);
+      }
+      if (dx) dx[i] += gx;
+      sv += gv;
+    }
+  }
+  if (rg == 1) {
+    s_red[0][col] = sv;
+    s_red[1][col] = sb;
+  }
+  __syncthreads();
+  if (rg == 0 && k < d) {
+    if (dv) dv[(size_t)b * d + k] += sv + s_red[0][col];
+    if (dbias_part && mode == 1) dbias_part[(size_t)b * d + k] += sb + s_red[1][col];
+  }
+}
+
+// Backward of mac_rowdot_fwd (ops.linear with outDim == 1, ops.py:316-317): out[r] = sum_s x_s[r,:].w_s + b, g = dL/dout [R]
+//   dx_s[r,:] += g[r]*w_s ;  part[blk, kk] = sum_{r in block blk} g[r]*x[r, kk]   (kk = Ktot: the bias column, x = 1)
+// grid (ceil((Ktot+1)/128), ceil(R/RD_ROWS)), 128 threads (one column each, coalesced over kk).
+constexpr int RD_ROWS = 64;
+__global__ void __launch_bounds__(128) rowdot_bwd_kernel(const float* x0, const float* x1, const float* x2, int k0, int k1,
+                                                        int k2, int ld0, int ld1, int ld2, const float* __restrict__ w,
+                                                        const float* __restrict__ g, float* dx0, float* dx1, float* dx2,
+                                                        int ldd0, int ldd1, int ldd2, float* __restrict__ part,
+                                                        long long R) {
+  const int Ktot = k0 + k1 + k2;
+  const int kk = blockIdx.x * 128 + threadIdx.x;
+  if (kk > Ktot) return;
+  const long long r0 = (long long)blockIdx.y * RD_ROWS, r1 = min(R, r0 + RD_ROWS);
+  const float* x = nullptr;
+  float* dx = nullptr;
+  int ld = 0, ldd = 0, kl = kk;
+  if (kk < k0) { x = x0; dx = dx0; ld = ld0; ldd = ldd0; }
+  else if (kk < k0 + k1) { x = x1; dx = dx1; ld = ld1; ldd = ldd1; kl = kk - k0; }
+  else if (kk < Ktot) { x = x2; dx = dx2; ld = ld2; ldd = ldd2; kl = kk - k0 - k1; }
+  const float wk = kk < Ktot ? __ldg(w + kk) : 0.f;
+  float s = 0.f;
+  for (long long r = r0; r < r1; ++r) {
+    const float gr = g[r];
+    if (x) {
+      s = fmaf(gr, x[r * ld + kl], s);
+      if (dx) dx[r * ldd + kl] += gr * wk;
+    } else {
+      s += gr;
+    }
+  }
+  part[(size_t)blockIdx.y * (Ktot + 1) + kk] = s;
+}
+
+// dw[kk] += sum_blk part[blk, kk] (kk < Ktot) ; db[0] += sum_blk part[blk, Ktot]     fixed order over the blocks
+__global__ void rowdot_bwd_reduce_kernel(const float* __restrict__ part, int nblk, int Ktot, float* __restrict__ dw,
+                                         float* __restrict__ db) {
+  const int kk = blockIdx.x * blockDim.x + threadIdx.x;
+  if (kk > Ktot) return;
+  float s = 0.f;
+  for (int i = 0; i < nblk; ++i) s += part[(size_t)i * (Ktot + 1) + kk];
+  if (kk < Ktot) {
+    if (dw) dw[kk] += s;
+  } else if (db) {
+    db[0] += s;
+  }
+}
+
+// Batch normalisation of the new memory (mac_cell.py:369-373: tf.contrib.layers.batch_norm, rank-2 input -> TF's fused path).
+// x, y [B, d]; one thread per column (B is the batch: tens to hundreds of rows), rows are d floats apart -> coalesced over k.
+//   training: mean / biased variance of the batch normalise; the stored statistics move by (1 - decay) towards the batch mean
+//             and the Bessel-corrected batch variance (what FusedBatchNorm hands to assign_moving_average), in place;
+//   eval:     the stored statistics normalise.
+// save_mean / save_invstd [d] keep what the backward needs.  y may alias x.
+__global__ void batchnorm_fwd_kernel(const float* x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                     float* __restrict__ moving_mean, float* __restrict__ moving_var, float decay, float eps,
+                                     int training, float* y, float* __restrict__ save_mean, float* __restrict__ save_invstd,
+                                     int B, int d) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= d) return;
+  float mean, var;
+  if (training) {
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s += x[(size_t)b * d + k];
+    mean = s / (float)B;
+    float q = 0.f;
+    for (int b = 0; b < B; ++b) {
+      const float c = x[(size_t)b * d + k] - mean;
+      q = fmaf(c, c, q);
+    }
+    var = q / (float)B;
+    const float unbiased = var * ((float)B / (float)max(B - 1, 1));
+    moving_mean[k] -= (moving_mean[k] - mean) * (1.f - decay);
+    moving_var[k] -= (moving_var[k] - unbiased) * (1.f - decay);
+  } else {
+    mean = moving_mean[k];
+    var = moving_var[k];
+  }
+  const float invstd = 1.f / sqrtf(var + eps);
+  const float g = gamma ? gamma[k] : 1.f, bt = beta ? beta[k] : 0.f;
+  for (int b = 0; b < B; ++b) {
+    const size_t i = (size_t)b * d + k;
+    y[i] = (x[i] - mean) * invstd * g + bt;
+  }
+  if (save_mean) save_mean[k] = mean;
+  if (save_invstd) save_invstd[k] = invstd;
+}
+
+// dx += gamma*invstd*(dy - mean_b(dy) - xhat*mean_b(dy*xhat)) (training) or gamma*invstd*dy (eval: constants);
+// dgamma += sum_b dy*xhat ; dbeta += sum_b dy
+__global__ void batchnorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                     const float* __restrict__ save_mean, const float* __restrict__ save_invstd,
+                                     const float* __restrict__ dy, int training, float* __restrict__ dx,
+                                     float* __restrict__ dgamma, float* __restrict__ dbeta, int B, int d) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= d) return;
+  const float mean = save_mean[k], invstd = save_invstd[k], g = gamma ? gamma[k] : 1.f;
+  float s1 = 0.f, s2 = 0.f;
+  for (int b = 0; b < B; ++b) {
+    const size_t i = (size_t)b * d + k;
+    const float gy = dy[i];
+    s1 += gy;
+    s2 = fmaf(gy, (x[i] - mean) * invstd, s2);
+  }
+  if (dx) {
+    const float m1 = training ? s1 / (float)B : 0.f, m2 = training ? s2 / (float)B : 0.f;
+    for (int b = 0; b < B; ++b) {
+      const size_t i = (size_t)b * d + k;
+      dx[i] += g * invstd * (dy[i] - m1 - (x[i] - mean) * invstd * m2);
+    }
+  }
+  if (dgamma) dgamma[k] += s2;
+  if (dbeta) dbeta[k] += s1;
 }
 
 static int launch_colsum(const float* x, float* out, int B, int N, int d, int accumulate, cudaStream_t stream) {
   dim3 grid((d + 127) / 128, B);
-  colsum_kernel<<<grid, 128, 0, stream>>>(x, out, N, d, accumulate);
+  colsum_kernel<<<grid, 256, 0, stream>>>(x, out, N, d, accumulate);
   MAC_LAUNCH_CHECK();
   return MAC_OK;
 }
@@ -334,6 +555,67 @@ extern "C" int mac_axpy(float* dst, const float* src, float alpha, long long n, 
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (!dst || !src || n <= 0) return MAC_ERR_INVALID;
   axpy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(dst, src, alpha, n);
+  MAC_LAUNCH_CHECK();
+  return MAC_OK;
+}
+
+extern "C" int mac_bcast_op_bwd(const float* x, const float* v, const float* out, const float* g, int mode, float mul_bias,
+                                float* dx, float* dv, float* dbias_part, int B, int N, int d, mac_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!x || !v || !g || B <= 0 || N <= 0 || d <= 0 || mode < 0 || mode > 2 || (mode == 2 && !out)) return MAC_ERR_INVALID;
+  bcast_op_bwd_kernel<<<dim3((d + 127) / 128, B), 256, 0, stream>>>(x, v, out, g, mode, mul_bias, dx, dv, dbias_part, N, d);
+  MAC_LAUNCH_CHECK();
+  return MAC_OK;
+}
+
+extern "C" size_t mac_rowdot_bwd_workspace_bytes(long long R, int k_total) {
+  return (size_t)((R + RD_ROWS - 1) / RD_ROWS) * (size_t)(k_total + 1) * sizeof(float) + 256;
+}
+
+extern "C" int mac_rowdot_bwd(const float* const* x_segs, const int* k_segs, const int* ldx, int nseg, const float* w,
+                              const float* g, float* const* dx_segs, const int* ld_dx, float* dw, float* db, void* workspace,
+                              size_t workspace_bytes, long long R, mac_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!x_segs || !k_segs || !ldx || nseg < 1 || nseg > 3 || !w || !g || !workspace || R <= 0) return MAC_ERR_INVALID;
+  const float* x[3] = {nullptr, nullptr, nullptr};
+  float* dx[3] = {nullptr, nullptr, nullptr};
+  int k[3] = {0, 0, 0}, ld[3] = {0, 0, 0}, ldd[3] = {0, 0, 0};
+  for (int i = 0; i < nseg; ++i) {
+    x[i] = x_segs[i]; k[i] = k_segs[i]; ld[i] = ldx[i];
+    if (!x[i] || k[i] <= 0) return MAC_ERR_INVALID;
+    if (dx_segs && dx_segs[i]) { dx[i] = dx_segs[i]; ldd[i] = ld_dx ? ld_dx[i] : k[i]; }
+  }
+  const int Ktot = k[0] + k[1] + k[2];
+  if (workspace_bytes < mac_rowdot_bwd_workspace_bytes(R, Ktot)) return MAC_ERR_WORKSPACE;
+  float* part = reinterpret_cast<float*>(workspace);
+  const int nblk = (int)((R + RD_ROWS - 1) / RD_ROWS);
+  rowdot_bwd_kernel<<<dim3((Ktot + 1 + 127) / 128, nblk), 128, 0, stream>>>(x[0], x[1], x[2], k[0], k[1], k[2], ld[0], ld[1],
+                                                                            ld[2], w, g, dx[0], dx[1], dx[2], ldd[0], ldd[1],
+                                                                            ldd[2], part, R);
+  MAC_LAUNCH_CHECK();
+  rowdot_bwd_reduce_kernel<<<(Ktot + 1 + 127) / 128, 128, 0, stream>>>(part, nblk, Ktot, dw, db);
+  MAC_LAUNCH_CHECK();
+  return MAC_OK;
+}
+
+extern "C" int mac_batchnorm_fwd(const float* x, const float* gamma, const float* beta, float* moving_mean, float* moving_var,
+                                 float decay, float eps, int training, float* y, float* save_mean, float* save_invstd, int B,
+                                 int d, mac_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!x || !moving_mean || !moving_var || !y || B <= 0 || d <= 0 || !(eps > 0.f)) return MAC_ERR_INVALID;
+  batchnorm_fwd_kernel<<<(d + 127) / 128, 128, 0, stream>>>(x, gamma, beta, moving_mean, moving_var, decay, eps, training, y,
+                                                           save_mean, save_invstd, B, d);
+  MAC_LAUNCH_CHECK();
+  return MAC_OK;
+}
+
+extern "C" int mac_batchnorm_bwd(const float* x, const float* gamma, const float* save_mean, const float* save_invstd,
+                                 const float* dy, int training, float* dx, float* dgamma, float* dbeta, int B, int d,
+                                 mac_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!x || !save_mean || !save_invstd || !dy || B <= 0 || d <= 0) return MAC_ERR_INVALID;
+  batchnorm_bwd_kernel<<<(d + 127) / 128, 128, 0, stream>>>(x, gamma, save_mean, save_invstd, dy, training, dx, dgamma, dbeta, B,
+                                                           d);
   MAC_LAUNCH_CHECK();
   return MAC_OK;
 }
@@ -527,7 +809,7 @@ extern "C" int mac_read_bwd(const float* kb, const float* memory_in, const float
     if (st != MAC_OK) return st;
   }
   // (5) I0 = [P*y, P]:  dP, dy, dbx   (dP overwrites bufA)
-  read_bwd_p_kernel<<<dim3((d + 127) / 128, B), 128, 0, stream>>>(bufC, P, y, bufA, dy, dbx_part, N, d);
+  read_bwd_p_kernel<<<dim3((d + 127) / 128, B), 256, 0, stream>>>(bufC, P, y, bufA, dy, dbx_part, N, d);
   MAC_LAUNCH_CHECK();
   // (6) P = dropout(KB) @ Wx + bx:  dWx += Kd^T dP ;  dKB += (dP @ Wx^T) * mask/keep
   if (dWx) {
@@ -673,7 +955,7 @@ extern "C" int mac_read_bwd_tc(const float* kb, const float* memory_in, const fl
   RBT(wgrad(xT16, 2 * d, bufB, dWm));
   RBT(dgrad(bufB, w->Wm, 2 * d, bufC));
   // (5) I0 = [P*y, P]:  dP (bufA), dy, dbx
-  read_bwd_p_kernel<<<dim3((d + 127) / 128, B), 128, 0, stream>>>(bufC, P, y, bufA, dy, dbx_part, N, d);
+  read_bwd_p_kernel<<<dim3((d + 127) / 128, B), 256, 0, stream>>>(bufC, P, y, bufA, dy, dbx_part, N, d);
   MAC_LAUNCH_CHECK();
   // (6) P = dropout(KB) @ Wx + bx:  dWx += Kd^T dP ;  dKB += (dP @ Wx^T) * mask/keep
   const float* kbd = kb;

@@ -416,6 +416,14 @@ inline size_t sgemm_workspace_bytes(int M, int N, int K) {
   return (size_t)splitk * M * N * sizeof(float) + 256;
 }
 
+// 128x128 tiles only where they fill the machine: the batch-sized weight gradients (K = B = 64, M x N = 512 x 512 or
+// 1024 x 512) get 16-32 tiles and at most 2 K slices out of them, 64x64 tiles give 64-128 tiles x 2 slices.
+// (EPI_READ_LOGITS callers size their per-column-tile partial logits with sgemm_tile_n.)
+inline bool sgemm_big_tiles(int M, int N, int K) {
+  return (M >= 512) && (K >= 256 || ((M + 127) / 128) * ((N + 127) / 128) >= 148);
+}
+inline int sgemm_tile_n(int M, int N, int K) { return sgemm_big_tiles(M, N, K) ? 128 : 64; }
+
 inline bool skinny_ok(const SgemmParams& p);
 inline int skinny_launch(const SgemmParams& p, cudaStream_t stream);
 
@@ -425,7 +433,7 @@ inline int sgemm_launch(SgemmParams p, unsigned int* counters, float* partial, s
   if ((p.N & 3) || ((p.K & 3) && p.a_mode < A_TRANS)) return MAC_ERR_INVALID;   // transposed views walk K row by row
   if (allow_splitk && skinny_ok(p) && !getenv("MAC_NO_SKINNY")) return skinny_launch(p, stream);   // M <= 64: cluster/DSMEM split-K kernel
   if (p.a_mode >= A_TRANS && (p.M & 3)) return MAC_ERR_INVALID;
-  const bool big = (p.M >= 512);
+  const bool big = sgemm_big_tiles(p.M, p.N, p.K);
   const int BM = big ? 128 : 64, BN = big ? 128 : 64;
   dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, 1);
   if (p.epi == EPI_READ_LOGITS || counters == nullptr || partial == nullptr) allow_splitk = false;

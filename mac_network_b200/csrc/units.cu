@@ -308,7 +308,7 @@ static int read_fwd_impl(const float* kb, const void* kb_bf16, const void* inv, 
       p.ctrl = control; p.wr = w->wr; p.logit_parts = parts; p.e_thresh = 0u; p.e_scale = 1.f;
       int st = sgemm_launch(p, nullptr, nullptr, 0, stream, false);
       if (st != MAC_OK) return st;
-      nparts = (M >= 512) ? (d + 127) / 128 : (d + 63) / 64;
+      nparts = (d + sgemm_tile_n(M, d, d) - 1) / sgemm_tile_n(M, d, d);
     }
   } else if (prec == MAC_PREC_BF16) {
     int st = tc_read_chain(kb, kb_bf16, y, control, w, thr, scale, seed, step, P, H, I1, parts, &nparts,
@@ -344,7 +344,7 @@ static int read_fwd_impl(const float* kb, const void* kb_bf16, const void* inv, 
       p.e_thresh = thr; p.e_scale = scale; p.e_site = MAC_SITE_READ_INTER; p.seed = seed; p.step = step;
       int st = sgemm_launch(p, nullptr, nullptr, 0, stream, false);
       if (st != MAC_OK) return st;
-      nparts = (M >= 512) ? (d + 127) / 128 : (d + 63) / 64;
+      nparts = (d + sgemm_tile_n(M, d, d) - 1) / sgemm_tile_n(M, d, d);
     }
   }
   if (nparts > 32) return MAC_ERR_UNSUPPORTED;
@@ -676,7 +676,8 @@ __global__ void __launch_bounds__(256) softmax_xent_kernel(const float* __restri
   for (int a = lane; a < A; a += 32) sum += expf(row[a] - mx);
   sum = warp_sum(sum);
   const int lab = labels[b];
-  if (lane == 0) losses[b] = mx + logf(sum) - row[lab];
+  const bool lab_ok = lab >= 0 && lab < A;       // an out-of-range label must not read outside the row: NaN loss, no one-hot
+  if (lane == 0) losses[b] = lab_ok ? mx + logf(sum) - row[lab] : __int_as_float(0x7fc00000);
   const float inv = 1.f / sum;
   for (int a = lane; a < A; a += 32) dlogits[(size_t)b * A + a] = (expf(row[a] - mx) * inv - (a == lab ? 1.f : 0.f)) * scale;
 }

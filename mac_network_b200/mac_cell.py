@@ -225,13 +225,23 @@ class MACCell(object):
         self._pending_write = None       # step index i whose memory _hm[i] = write(_hm[i-1], _hi[i]) has not been launched yet
         recurrent_ctrl_ok = (c.controlFeedPrev and self._fused_control and not (c.controlWholeQ or c.controlContinuous
                                                                                 or c.unsharedCells))
-        if self.save_for_backward and (not (self._fused_read and self._fused_write)
-                                       or not (self._hoist or recurrent_ctrl_ok)):
-            raise NotImplementedError("backward is implemented on the fused path (DESIGN.md section 9)")
-        if self.save_for_backward and (c.controlInWordsProj or c.controlOutWordsProj):
-            # the hand-written backward does not propagate through the shared wordsProj layer (mac_cell.py:578-581): its
-            # weight / bias gradients would silently stay zero and dL/dwords would be wrong
-            raise NotImplementedError("backward through controlInWordsProj / controlOutWordsProj is not implemented")
+        # Backward: the hand-scheduled sweep of autograd._Bwd covers the shipped flag files (fused read + write, control
+        # either memory-independent or the plain recurrent chain); every other working flag combination records its
+        # primitives on a tape (tape.py) and is differentiated node by node.  MAC_TAPE_BWD=1 forces the tape everywhere.
+        if c.memoryBN:                   # the normalised memory is what the next projY sees: no folded write + projY forms
+            self._fold_y = False
+            self._step_fused = False
+        scheduled_bwd_ok = (self._fused_read and self._fused_write and (self._hoist or recurrent_ctrl_ok)
+                            and not c.memoryBN
+                            and not (c.controlInWordsProj or c.controlOutWordsProj)      # wordsProj is outside _Bwd
+                            and not (c.controlFeedPrev and not c.controlFeedPrevAtt)
+                            and not (c.controlFeedPrev and c.writeSelfAtt and c.writeSelfAttMod == "CONT"))
+        self._use_tape = self.save_for_backward and (not scheduled_bwd_ok or os.environ.get("MAC_TAPE_BWD", "0") == "1")
+        self._tape = None
+        if self._use_tape:
+            if self.prec != PREC["fp32"]:
+                raise NotImplementedError("the tape backward (flags outside the shipped files) runs the fp32 kernels")
+            self._hoist = False              # per-step control(): every launch is a tape node
         if self.save_for_backward and self.prec != PREC["fp32"] and (d % 128 or self._kb_given_bf16):
             raise NotImplementedError("training forward on tensor cores needs d % 128 == 0 and an fp32 knowledge base")
         if self.prec != PREC["fp32"] and not self._fused_read:
@@ -263,6 +273,8 @@ class MACCell(object):
         check(self.lib.mac_linear_fwd(arr_p, arr_k, arr_ld, n, ptr(W), ptr(b), float(bias_const), code, ptr(out),
                                       out.stride(0), M, W.shape[1], ptr(self.ws.lin), self.ws.lin_bytes, stream_ptr()),
               "mac_linear_fwd")
+        if self._tape is not None:
+            self._tape.linear(xs, W, b, out, code)
         return out
 
     def _split_weight(self, key, W):
@@ -297,6 +309,8 @@ class MACCell(object):
     def _dropout(self, x, keep, site, step, out):
         check(self.lib.mac_dropout_fwd(ptr(x), float(keep), self.seed, site, step, ptr(out), x.numel(), stream_ptr()),
               "mac_dropout_fwd")
+        if self._tape is not None:
+            self._tape.dropout(x, out, keep, site, step)
         return out
 
     def _new(self, *shape):
@@ -320,6 +334,13 @@ class MACCell(object):
         self._hc = self._new(L + 1, B, d)
         self._hm = self._new(L + 1, B, d)
         self._hi = self._new(L + 1, B, d)
+        if self._use_tape:
+            from .tape import Tape
+            self._tape = Tape(self)
+            self._gC, self._gM = self._tape.register_history(self._hc), self._tape.register_history(self._hm)
+            self._tape.register_history(self._hi)
+            self._tape.init_state(self._hc[0], c.initCtrl, "initCtrl")
+            self._tape.init_state(self._hm[0], c.initMem, "initMem")
         c0 = self.initState("initCtrl", c.ctrlDim, c.initCtrl, B, self._hc[0])
         m0 = self.initState("initMem", c.memDim, c.initMem, B, self._hm[0])
         self._hi[0].copy_(m0)                                                          # mac_cell.py:551
@@ -425,10 +446,14 @@ class MACCell(object):
             logits = self._rowdot(segs, lsc)
             check(self.lib.mac_attend_fwd(ptr(logits), ptr(questionLengths), ptr(outWords), S * d, d, ptr(att), ptr(out),
                                           B, S, d, stream_ptr()), "mac_attend_fwd")
+            if self._tape is not None:
+                self._tape.attend(logits, outWords, att, out, B, S, d)
             self.attentions["question"].append(att)
             return (newContControl if c.controlContinuous else out), newContControl
         self._attend(newContControl, 0, d, inWords, S * d, d, outWords, S * d, d, questionLengths,
                      self.params[lsc + "weights/weight"], self.params.scalar(lsc + "biases/bias"), att, out, 1, S)
+        if self._tape is not None:
+            self._tape.control_attend(newContControl, inWords, outWords, lsc, att, out, S)
         self.attentions["question"].append(att)
         newControl = out
         if c.controlContinuous:
@@ -473,10 +498,11 @@ class MACCell(object):
         i = self.iteration
         keep_m = self.dropouts["memory"]
         if keep_m < 1.0:
+            mem_in = self._mem_in if self._tape is None else self._new(B, d)     # the tape keeps every step's tensor
             if c.memoryVariationalDropout:     # one mask per forward (mac_cell.py:589-590): site MEM_VAR, step 0
-                memory = self._dropout(memory, keep_m, _lib.SITE_MEM_VAR, 0, self._mem_in)
+                memory = self._dropout(memory, keep_m, _lib.SITE_MEM_VAR, 0, mem_in)
             else:
-                memory = self._dropout(memory, keep_m, _lib.SITE_MEM_PLAIN, i, self._mem_in)
+                memory = self._dropout(memory, keep_m, _lib.SITE_MEM_PLAIN, i, mem_in)
         att = _att_out if _att_out is not None else self._new(B, N)
         info = _out if _out is not None else self._new(B, d)
         if not self._fused_read:
@@ -509,6 +535,8 @@ class MACCell(object):
                                     stream_ptr()), "mac_read_fwd")
         if _save is not None and self.prec == PREC["bf16"]:
             self._upcast_saved(_save)
+        if self._tape is not None:
+            self._tape.fused_read(i, name, knowledgeBase, memory, control, info)
         self.attentions["kb"].append(att)
         return info
 
@@ -546,6 +574,29 @@ class MACCell(object):
     def write(self, memory, info, control, contControl=None, name="", reuse=None, _out=None, _gate_out=None,
               _y_next=None):
         """mac_cell.py:305-375 (returns the new memory [B, memDim])."""
+        if not self.cfg.memoryBN:
+            return self._write_unit(memory, info, control, contControl, name, _out, _gate_out, _y_next)
+        pre = self._write_unit(memory, info, control, contControl, name, self._new(self.B, self.d), _gate_out, None)
+        return self._batch_norm(pre, name, _out if _out is not None else self._new(self.B, self.d))
+
+    def _batch_norm(self, x, name, out, eps=1e-3):
+        """mac_cell.py:369-373: tf.contrib.layers.batch_norm(newMemory, decay=bnDecay, center=bnCenter, scale=bnScale,
+        is_training=self.train, updates_collections=None) -- batch statistics (and the in-place update of the stored ones, once
+        per reasoning step) in training, the stored statistics at eval; epsilon is the layer's default 0.001."""
+        c, B, d = self.cfg, self.B, self.d
+        sc = "MACCell/write" + name + "/BatchNorm/"
+        gamma = self.params[sc + "gamma"] if c.bnScale else None
+        beta = self.params[sc + "beta"] if c.bnCenter else None
+        mean, invstd = self._new(d), self._new(d)
+        check(self.lib.mac_batchnorm_fwd(ptr(x), ptr(gamma), ptr(beta), ptr(self.params[sc + "moving_mean"]),
+                                         ptr(self.params[sc + "moving_variance"]), float(c.bnDecay), float(eps),
+                                         int(self.train), ptr(out), ptr(mean), ptr(invstd), B, d, stream_ptr()),
+              "mac_batchnorm_fwd")
+        if self._tape is not None:
+            self._tape.batch_norm(x, out, gamma, beta, mean, invstd, int(self.train))
+        return out
+
+    def _write_unit(self, memory, info, control, contControl, name, _out, _gate_out, _y_next):
         c, B, d = self.cfg, self.B, self.d
         sc = "MACCell/write" + name + "/"
         i = self.iteration
@@ -578,6 +629,8 @@ class MACCell(object):
             self._attend(selfControl, 0, selfControl.stride(0), self._hc, d, B * d, self._hm, d, B * d, None,
                          self.params[lsc + "weights/weight"], self.params.scalar(lsc + "biases/bias"), att, selfSmry,
                          1, i + 1)
+            if self._tape is not None:
+                self._tape.self_attend(selfControl, lsc, att, selfSmry, i + 1, self._gC, self._gM)
             self.attentions["self"].append(att)
         Ww, bw = self.params.lin(sc, "newMemory")
         Wg = bg = None
@@ -602,6 +655,8 @@ class MACCell(object):
         if self.save_for_backward and c.writeGate:
             # the pre-gate memory m' is the first [B,d] block of the write workspace after its 4 KB header
             self._mnew[i].copy_(self.ws.write[4096:4096 + B * d * 4].view(torch.float32).view(B, d))
+        if self._tape is not None:
+            self._tape.fused_write(i, name, memory, info, selfSmry, control, out)
         if c.writeGate:
             self.attentions["gate"].append(gate)
         return out
@@ -628,6 +683,8 @@ class MACCell(object):
         arr_ld = (ctypes.c_int * n)(*[x.stride(0) for x in xs])
         check(self.lib.mac_rowdot_fwd(arr_p, arr_k, arr_ld, n, ptr(self.params[lscope + "weights/weight"]),
                                       self.params.scalar(lscope + "biases/bias"), ptr(out), R, stream_ptr()), "mac_rowdot_fwd")
+        if self._tape is not None:
+            self._tape.rowdot(xs, lscope, out)
         return out
 
     def _bcast(self, x2d, v, mode, N, bias=None, mul_bias=None):
@@ -636,6 +693,16 @@ class MACCell(object):
         mb = self.cfg.mulBias if mul_bias is None else mul_bias
         check(self.lib.mac_bcast_op(ptr(x2d), ptr(v), mode, float(mb), ptr(bias), ptr(out), self.B, N,
                                     x2d.shape[1], stream_ptr()), "mac_bcast_op")
+        if self._tape is not None:
+            self._tape.bcast(x2d, v, mode, mb, bias, out, self.B, N)
+        return out
+
+    def _add_scaled(self, a, b, alpha):
+        """a + alpha * b as a new tensor (the copy is memory plumbing, the arithmetic is mac_axpy)."""
+        out = a.clone()
+        check(self.lib.mac_axpy(ptr(out), ptr(b), float(alpha), out.numel(), stream_ptr()), "mac_axpy")
+        if self._tape is not None:
+            self._tape.add_scaled(a, b, float(alpha), out)
         return out
 
     def _act(self, x, act):
@@ -643,6 +710,8 @@ class MACCell(object):
             return x
         out = self._new(*x.shape)
         check(self.lib.mac_activation(ptr(x), self._act_code(act), ptr(out), x.numel(), stream_ptr()), "mac_activation")
+        if self._tape is not None:
+            self._tape.act(x, out, self._act_code(act))
         return out
 
     def _mul_general(self, x2d, y, dim, N, scope, name, proj, inter_mod, concat_x, concat_proj):
@@ -691,12 +760,16 @@ class MACCell(object):
             # inter2att's linear drops its (concatenated) input (mac_cell.py:266, ops.py:312): ONE mask over [B, N, total
             # width], so the concat is materialised for the flat mask index (memory plumbing) and dropped as one tensor
             cat = segs[0] if len(segs) == 1 else torch.cat(segs, dim=1)
+            if self._tape is not None and len(segs) > 1:
+                self._tape.cat(list(segs), cat)
             segs = [self._dropout(cat, keep_r, _lib.SITE_READ_INTER, self.iteration, self._new(*cat.shape))]
         logits = self._rowdot(segs, sc + "inter2att/inter2logits/linearLayerlogits/")
         feats = projectedKB if c.readSmryKBProj else kb2
         dd = feats.shape[1]
         check(self.lib.mac_attend_fwd(ptr(logits), None, ptr(feats), N * dd, dd, ptr(att), ptr(info), B, N, dd,
                                       stream_ptr()), "mac_attend_fwd")
+        if self._tape is not None:
+            self._tape.attend(logits, feats, att, info, B, N, dd)
         self.attentions["kb"].append(att)
         return info
 
@@ -717,19 +790,17 @@ class MACCell(object):
             self._attend(selfControl, 0, selfControl.stride(0), self._hc, d, B * d, self._hm, d, B * d, None,
                          self.params[lsc + "weights/weight"], self.params.scalar(lsc + "biases/bias"), satt, selfSmry,
                          1, i + 1)
+            if self._tape is not None:
+                self._tape.self_attend(selfControl, lsc, satt, selfSmry, i + 1, self._gC, self._gM)
             self.attentions["self"].append(satt)
         if c.writeInputs == "INFO":
             segs = [info]
         elif c.writeInputs == "SUM":
-            ssum = memory.clone()
-            check(self.lib.mac_axpy(ptr(ssum), ptr(info), 1.0, ssum.numel(), stream_ptr()), "mac_axpy")
-            segs = [ssum]
+            segs = [self._add_scaled(memory, info, 1.0)]
         elif c.writeInputs == "BOTH":
             segs = [memory, info]
             if c.writeConcatMul:                                                          # ops.py:65-78
-                prod = self._new(B, d)
-                check(self.lib.mac_bcast_op(ptr(memory), ptr(info), 0, 0.0, None, ptr(prod), B, 1, d, stream_ptr()), "mul")
-                segs.append(prod)
+                segs.append(self._bcast(memory, info, 0, 1, mul_bias=0.0))
         else:  # MEM
             segs = [memory]
         if selfSmry is not None:
@@ -752,13 +823,12 @@ class MACCell(object):
                              bias_const=c.writeGateBias)
             self.attentions["gate"].append(z)
             # m' * z + m * (1 - z) = m + z * (m' - m)
-            diff = newMemory.clone()
-            check(self.lib.mac_axpy(ptr(diff), ptr(memory), -1.0, diff.numel(), stream_ptr()), "mac_axpy")
-            zd = self._new(B, d)
-            check(self.lib.mac_bcast_op(ptr(diff), ptr(z), 0, 0.0, None, ptr(zd), B, 1, d, stream_ptr()), "mul")
-            newMemory = memory.clone()
-            check(self.lib.mac_axpy(ptr(newMemory), ptr(zd), 1.0, zd.numel(), stream_ptr()), "mac_axpy")
+            diff = self._add_scaled(newMemory, memory, -1.0)
+            zd = self._bcast(diff, z, 0, 1, mul_bias=0.0)
+            newMemory = self._add_scaled(memory, zd, 1.0)
         out.copy_(newMemory)
+        if self._tape is not None:
+            self._tape.copy(out, newMemory)
         return out
 
     # ------------------------------------------------------------------ one reasoning step (mac_cell.py:420-480)
@@ -784,9 +854,13 @@ class MACCell(object):
                                                         _att_out=self._att_q[i], _out=self._hc[i + 1])
             if c.controlContinuous:
                 self._hc[i + 1].copy_(newControl)
+                if self._tape is not None:
+                    self._tape.copy(self._hc[i + 1], newControl)
                 newControl = self._hc[i + 1]
         if c.controlWholeQ:                                                            # mac_cell.py:455-456
             self._hc[i + 1].copy_(self.vecQuestions)
+            if self._tape is not None:
+                self._tape.copy(self._hc[i + 1], self.vecQuestions)
             newControl = self._hc[i + 1]
         if self._step_fused:
             newMemory = self._whole_step(i, memory, newControl, cellName)

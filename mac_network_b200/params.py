@@ -108,6 +108,16 @@ def param_specs(cfg, netLength=None):
             _linear(s, sc, "newMemory", dim, c.memDim)
         if c.writeGate:
             _linear(s, sc, "gate", d, c.memDim)
+        if c.memoryBN:
+            # tf.contrib.layers.batch_norm under the write scope (mac_cell.py:370-373): beta / gamma only with
+            # bnCenter / bnScale; the moving statistics are variables too (non-trainable: their gradient stays zero)
+            bn = sc + "BatchNorm/"
+            if c.bnCenter:
+                s[bn + "beta"] = ((c.memDim,), "zeros")
+            if c.bnScale:
+                s[bn + "gamma"] = ((c.memDim,), "ones")
+            s[bn + "moving_mean"] = ((c.memDim,), "zeros")
+            s[bn + "moving_variance"] = ((c.memDim,), "ones")
     return s
 
 
@@ -118,6 +128,8 @@ def init_params(cfg, netLength=None, seed=0, dtype=np.float32):
     for name, (shape, kind) in param_specs(cfg, netLength).items():
         if kind == "zeros":
             v = np.zeros(shape)
+        elif kind == "ones":
+            v = np.ones(shape)
         elif kind == "normal":
             v = rng.standard_normal(shape)
         else:
@@ -140,4 +152,17 @@ def perturb_biases(params, seed=1, scale=0.1):
             out[k] = np.asarray(scale * rng.standard_normal(v.shape), dtype=v.dtype)
         else:
             out[k] = v
+    # batch-norm variables (memoryBN): their own stream, so that flag sets without them keep the values they always had
+    rng_bn = np.random.RandomState(seed + 7919)
+    for k, v in params.items():
+        tail = k.rsplit("/", 1)[-1]
+        if "/BatchNorm/" not in k:
+            continue
+        n = rng_bn.standard_normal(v.shape)
+        if tail in ("beta", "moving_mean"):
+            out[k] = np.asarray(v + 2 * scale * n, dtype=v.dtype)
+        elif tail == "gamma":
+            out[k] = np.asarray(v * (1.0 + 2 * scale * n), dtype=v.dtype)
+        else:                                                    # moving_variance: positive
+            out[k] = np.asarray(v * (0.5 + np.abs(n)), dtype=v.dtype)
     return out

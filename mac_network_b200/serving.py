@@ -42,6 +42,53 @@ def _parse_cpulist(text):
     return cpus
 
 
+def gpu_numa_nodes():
+    """[NUMA node of visible CUDA device i] (-1 where /sys does not say)."""
+    out = []
+    for i in range(torch.cuda.device_count()):
+        node = -1
+        try:
+            prop = torch.cuda.get_device_properties(i)
+            bus = "%04x:%02x:%02x.0" % (getattr(prop, "pci_domain_id", 0), prop.pci_bus_id, prop.pci_device_id)
+            with open("/sys/bus/pci/devices/%s/numa_node" % bus) as f:
+                node = int(f.read().strip())
+        except Exception:           # noqa: BLE001 -- advisory only
+            node = -1
+        out.append(node)
+    return out
+
+
+def spread_order(nodes):
+    """Visible devices re-ordered round-robin over their NUMA nodes (node order = first appearance, device order kept
+    inside a node): [0,0,0,0,1,1,1,1] -> [0,4,1,5,2,6,3,7].  A job of fewer ranks than GPUs then puts its ranks on as many
+    sockets as possible, so that each rank's host staging has a socket's memory bandwidth and cores to itself."""
+    groups, seen = {}, []
+    for i, n in enumerate(nodes):
+        if n not in groups:
+            groups[n] = []
+            seen.append(n)
+        groups[n].append(i)
+    order, k = [], 0
+    while len(order) < len(nodes):
+        for n in seen:
+            if k < len(groups[n]):
+                order.append(groups[n][k])
+        k += 1
+    return order
+
+
+def device_for_rank(local_rank, local_world):
+    """CUDA device index of a local rank: the identity when every visible GPU is used (or the topology is unknown), else the
+    NUMA-spread order above.  Deterministic, so every rank computes the same assignment without talking."""
+    n = torch.cuda.device_count()
+    if local_world >= n or os.environ.get("MAC_NO_GPU_SPREAD", "0") == "1":
+        return local_rank
+    nodes = gpu_numa_nodes()
+    if len(set(nodes)) <= 1 or any(x < 0 for x in nodes):
+        return local_rank
+    return spread_order(nodes)[local_rank]
+
+
 def bind_to_gpu_numa(device_index):
     """Pin this process (and the threads / pinned host buffers it creates afterwards: first touch) to the NUMA node the
     GPU's PCIe root hangs off.  One process per GPU on a 2-socket host otherwise leaves half of the ranks staging their

@@ -77,6 +77,10 @@ CASES = {
                                         "--readCtrlConcatKB", "--readCtrlConcatProj", "--readSmryKBProj"], SMALL, True),
     "p2_read_plain_train": (None, ["--relu=STD", "--controlContextual", "--readCtrl", "--readCtrlConcatKB",
                                    "--mulBias=0.25", "--initCtrl=Q"], SMALL, True),
+    # batch-normalised memory (mac_cell.py:369-373): stored statistics at eval, batch statistics + their update in training
+    "p2_memory_bn": (None, ARGS + ["--memoryBN", "--bnCenter", "--bnScale", "--bnDecay=0.9"], SMALL, False),
+    "p2_memory_bn_train": (None, ARGS + ["--memoryBN", "--bnCenter", "--bnDecay=0.9", "--writeGate"],
+                           dict(B=5, S=5, N=7, d=16, L=3), True),
     # BASELINE.json configs[0]/[1]: B=32, S=20, 14x14 KB, d=512, netLength=4 (float32 storage)
     "args_cpu_ref": ("@args.txt", [], dict(B=32, S=20, N=196, d=512, L=4), False),
     "gqa_mid": ("@args3.txt", ["--writeGate"], dict(B=8, S=30, N=49, d=512, L=6), False),
@@ -111,6 +115,8 @@ def cell_flags_from_reference():
     import dataclasses
     kw = {}
     for f in dataclasses.fields(MACConfig):
+        if f.name in ("bnDecay", "bnCenter", "bnScale") and not _ref_config.config.memoryBN:
+            continue          # recorded only where they matter, so the older fixtures regenerate byte for byte
         kw[f.name] = getattr(_ref_config.config, f.name)
     return kw
 
@@ -166,6 +172,10 @@ def run_case(name, src, extra, shape, train, seed=7):
         out["att_self_%d" % i] = np.asarray(a, st)
     for i, u in enumerate(store.uniform_draws):
         out["uniform_%03d" % i] = u.astype(np.float64)
+    if rc.memoryBN:          # the stored statistics after the forward (moved by the training forward, untouched at eval)
+        for k, v in store.vars.items():
+            if "/BatchNorm/moving_" in k:
+                out["final_bn_" + k.rsplit("/", 1)[-1]] = np.asarray(v, np.float64)
     # the cell must not modify its inputs (SURVEY 8(b) ownership)
     chk = make_inputs(B, S, N, d, seed=seed, dtype=np.float64)
     for k in chk:
@@ -202,6 +212,10 @@ def run_output_case(name, train, seed=17, B=6, d=16, A=12, hidden=(8,)):
            "memory": memory, "vecQuestions": vecq, "answers": answers}
     for i, u in enumerate(store.uniform_draws):
         out["uniform_%03d" % i] = u.astype(np.float64)
+    if rc.memoryBN:          # the stored statistics after the forward (moved by the training forward, untouched at eval)
+        for k, v in store.vars.items():
+            if "/BatchNorm/moving_" in k:
+                out["final_bn_" + k.rsplit("/", 1)[-1]] = np.asarray(v, np.float64)
     meta = {"case": name, "train": train, "keep": keep, "B": B, "d": d, "A": A, "hidden": list(hidden), "param_seed": seed,
             "relu": rc.relu, "variables": created, "n_uniform": len(store.uniform_draws)}
     out["meta_json"] = np.frombuffer(json.dumps(meta, sort_keys=True).encode(), dtype=np.uint8)
@@ -228,6 +242,10 @@ def run_stem_case(name, train, seed=23, B=2, H=5, W=4, cin=8, cout=8):
     out = {"images": images, "kb": np.asarray(kb)}
     for i, u in enumerate(store.uniform_draws):
         out["uniform_%03d" % i] = u.astype(np.float64)
+    if rc.memoryBN:          # the stored statistics after the forward (moved by the training forward, untouched at eval)
+        for k, v in store.vars.items():
+            if "/BatchNorm/moving_" in k:
+                out["final_bn_" + k.rsplit("/", 1)[-1]] = np.asarray(v, np.float64)
     meta = {"case": name, "train": train, "keep": keep, "shape": [B, H, W, cin, cout], "layers": rc.stemNumLayers,
             "ksize": rc.stemKernelSize, "param_seed": seed, "relu": rc.relu, "variables": created,
             "n_uniform": len(store.uniform_draws)}
@@ -270,6 +288,10 @@ def run_encoder_case(name, train, proj, seed=29, B=5, S=7, V=11, E=12, enc_dim=1
            "questionCntxWords": np.asarray(cntx), "vecQuestions": np.asarray(vecq)}
     for i, u in enumerate(store.uniform_draws):
         out["uniform_%03d" % i] = u.astype(np.float64)
+    if rc.memoryBN:          # the stored statistics after the forward (moved by the training forward, untouched at eval)
+        for k, v in store.vars.items():
+            if "/BatchNorm/moving_" in k:
+                out["final_bn_" + k.rsplit("/", 1)[-1]] = np.asarray(v, np.float64)
     meta = {"case": name, "train": train, "proj": proj, "bi": bi, "keep_input": keep_in, "keep_question": keep_q,
             "shape": {"B": B, "S": S, "V": V, "E": E, "encDim": enc_dim, "ctrlDim": ctrl}, "param_seed": seed,
             "variables": created, "n_uniform": len(store.uniform_draws)}

@@ -61,6 +61,7 @@ class MACOracle(object):
         self.prefix = prefix
         self.p = {k: np.asarray(v, dtype=dtype) for k, v in params.items()}
         self.uniforms = None      # iterator over uniform draws, in the reference's call order
+        self.train = False        # the cell's `train` argument (mac_cell.py:64): only memoryBN reads it here
 
     # -------------------------------------------------------------- variable access
     def var(self, scope, name):
@@ -290,7 +291,30 @@ class MACOracle(object):
             z = 1.0 / (1.0 + np.exp(-z))
             self.attentions["gate"].append(z)
             new_mem = new_mem * z + memory * (1 - z)
+        if c.memoryBN:
+            new_mem = self.batch_norm(new_mem, sc + "BatchNorm/")
         return new_mem
+
+    def batch_norm(self, x, scope):
+        """mac_cell.py:370-373: tf.contrib.layers.batch_norm(newMemory, decay=bnDecay, center=bnCenter, scale=bnScale,
+        is_training=self.train, updates_collections=None), epsilon at its default 0.001.  TF 1.x semantics (fused path for
+        a rank-2 input): training normalises with the batch mean and biased variance and moves the stored statistics by
+        (1 - decay) towards the batch mean / the Bessel-corrected batch variance, once per call (i.e. per reasoning step);
+        inference normalises with the stored statistics."""
+        c, eps = self.cfg, 1e-3
+        P = self.prefix + scope
+        beta = self.p[P + "beta"] if c.bnCenter else 0.0
+        gamma = self.p[P + "gamma"] if c.bnScale else 1.0
+        if self.train:
+            n = x.shape[0]
+            mean = x.mean(axis=0)
+            var = ((x - mean) ** 2).mean(axis=0)
+            mm, mv = self.p[P + "moving_mean"], self.p[P + "moving_variance"]
+            self.p[P + "moving_mean"] = mm - (mm - mean) * (1.0 - c.bnDecay)
+            self.p[P + "moving_variance"] = mv - (mv - var * (float(n) / max(n - 1, 1))) * (1.0 - c.bnDecay)
+        else:
+            mean, var = self.p[P + "moving_mean"], self.p[P + "moving_variance"]
+        return (x - mean) / np.sqrt(var + eps) * gamma + beta
 
     # -------------------------------------------------------------- one step / unroll
     def step(self, state):

@@ -430,8 +430,33 @@ class _layers(object):
     xavier_initializer = staticmethod(_xavier_uniform)
 
     @staticmethod
-    def batch_norm(*a, **k):
-        raise NotImplementedError("batch_norm is outside the hot-path scope (memoryBN defaults off)")
+    def batch_norm(inputs, decay=0.999, center=True, scale=False, epsilon=0.001, is_training=True,
+                   updates_collections="update_ops", scope=None, **kw):
+        """tf.contrib.layers.batch_norm on a [B, C] input, restated from TF 1.x contrib/layers/python/layers/layers.py:
+        rank 2 takes the fused path (reshaped to [B,1,1,C]).  Training: batch mean and BIASED variance normalise; the moving
+        mean / variance are updated by assign_moving_average(decay, zero_debias=False) with the batch mean and the
+        Bessel-corrected variance FusedBatchNorm returns; `updates_collections=None` forces the update with the forward.
+        Inference: the moving statistics normalise.  beta / gamma exist only with center / scale."""
+        assert updates_collections is None, "the reference passes updates_collections=None (mac_cell.py:371-373)"
+        x = np.asarray(inputs)
+        C = x.shape[-1]
+        with variable_scope(scope or "BatchNorm"):
+            beta = get_variable("beta", [C], initializer=zeros_initializer()) if center else 0.0
+            gamma = get_variable("gamma", [C], initializer=ones_initializer()) if scale else 1.0
+            full = "/".join(_store.scope)
+            mm = get_variable("moving_mean", [C], initializer=zeros_initializer())
+            mv = get_variable("moving_variance", [C], initializer=ones_initializer())
+            if bool(is_training):
+                n = x.shape[0]
+                mean = np.mean(x, axis=0)
+                var = np.mean((x - mean) ** 2, axis=0)
+                y = (x - mean) / np.sqrt(var + epsilon) * gamma + beta
+                unbiased = var * (float(n) / max(n - 1, 1))
+                _store.vars[full + "/moving_mean"] = _t(mm - (mm - mean) * (1.0 - decay))
+                _store.vars[full + "/moving_variance"] = _t(mv - (mv - unbiased) * (1.0 - decay))
+            else:
+                y = (x - mm) / np.sqrt(mv + epsilon) * gamma + beta
+        return _t(y)
 
 
 class _rnn(object):

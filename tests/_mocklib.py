@@ -72,7 +72,7 @@ def install(monkeypatch):
     import importlib
     mock = MockLib()
     monkeypatch.setattr(_lib, "load", lambda: mock)
-    for mod in ("encoder", "stem", "output_unit", "dp", "mac_cell", "autograd"):
+    for mod in ("encoder", "stem", "output_unit", "dp", "mac_cell", "autograd", "tape"):
         m = importlib.import_module("mac_network_b200." + mod)
         if hasattr(m, "stream_ptr"):
             monkeypatch.setattr(m, "stream_ptr", lambda: None)

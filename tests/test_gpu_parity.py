@@ -55,8 +55,11 @@ def run_gpu(cfg, params_np, inputs_np, L, dropouts=(1.0, 1.0, 1.0), train=False,
     return out, cell
 
 
-def run_oracle(cfg, params_np, inputs_np, L, dropouts=(1.0, 1.0, 1.0), uniforms=None):
+def run_oracle(cfg, params_np, inputs_np, L, dropouts=(1.0, 1.0, 1.0), uniforms=None, train=False, keep=None):
     orc = MACOracle(cfg, params_np, dtype=np.float64)
+    orc.train = train                   # read by memoryBN only
+    if keep is not None:
+        keep.append(orc)
     orc.run(L, inputs_np["vecQuestions"], inputs_np["questionWords"], inputs_np["questionCntxWords"],
             inputs_np["questionLengths"], inputs_np["knowledgeBase"], memoryDropout=dropouts[0],
             readDropout=dropouts[1], writeDropout=dropouts[2], uniforms=uniforms)

@@ -227,3 +227,65 @@ def test_general_path_training_dropout_host_calls(monkeypatch, case):
     assert len(draws) == meta["n_uniform"]
     for i, u in enumerate(draws):
         assert tuple(u.shape) == tuple(arrays["uniform_%03d" % i].shape), i
+
+
+def test_rank_to_gpu_spreads_over_numa_nodes(monkeypatch):
+    """serving.device_for_rank: fewer ranks than GPUs -> round-robin over the sockets; all GPUs used / unknown topology /
+    one socket -> the identity (so LOCAL_RANK keeps its usual meaning)."""
+    from mac_network_b200 import serving
+    assert serving.spread_order([0, 0, 0, 0, 1, 1, 1, 1]) == [0, 4, 1, 5, 2, 6, 3, 7]
+    assert serving.spread_order([1, 1, 0]) == [0, 2, 1]
+    assert serving._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    monkeypatch.setattr(serving.torch.cuda, "device_count", lambda: 8)
+    monkeypatch.setattr(serving, "gpu_numa_nodes", lambda: [0, 0, 0, 0, 1, 1, 1, 1])
+    assert [serving.device_for_rank(r, 2) for r in range(2)] == [0, 4]
+    assert [serving.device_for_rank(r, 4) for r in range(4)] == [0, 4, 1, 5]
+    assert [serving.device_for_rank(r, 8) for r in range(8)] == list(range(8))
+    monkeypatch.setattr(serving, "gpu_numa_nodes", lambda: [0] * 8)
+    assert [serving.device_for_rank(r, 2) for r in range(2)] == [0, 1]
+    monkeypatch.setattr(serving, "gpu_numa_nodes", lambda: [-1] * 8)
+    assert [serving.device_for_rank(r, 4) for r in range(4)] == [0, 1, 2, 3]
+    monkeypatch.setenv("MAC_NO_GPU_SPREAD", "1")
+    monkeypatch.setattr(serving, "gpu_numa_nodes", lambda: [0, 0, 0, 0, 1, 1, 1, 1])
+    assert serving.device_for_rank(1, 2) == 1
+
+
+P2_CASES = ["p2_control", "p2_control_feed", "p2_ablations", "p2_wholeq", "p2_unshared", "p2_read_bl", "p2_read_add",
+            "p2_read_plain", "p2_read_noproj", "p2_write_info", "p2_write_sum", "p2_write_mem", "p2_write_mul",
+            "p2_read_add_train", "p2_read_plain_train", "p2_memory_bn", "p2_memory_bn_train"]
+
+
+@pytest.mark.filterwarnings("ignore:invalid value")
+@pytest.mark.parametrize("case", P2_CASES + ["args_train_small", "args1_train_small", "gqa_train_small"])
+def test_tape_backward_host_calls(monkeypatch, case):
+    """Backward of the flag combinations outside the hand-scheduled sweep (tape.py): every forward launch leaves a node, the
+    sweep calls the matching backward entry points with well-formed arguments, and every parameter the flag set creates that
+    the forward read has a gradient slot.  (The shipped flag files go through the same tape with MAC_TAPE_BWD=1.)"""
+    mock = _mocklib.install(monkeypatch)
+    monkeypatch.setattr(torch.Tensor, "is_cuda", property(lambda self: True), raising=False)
+    monkeypatch.setenv("MAC_TAPE_BWD", "1")
+    from mac_network_b200.autograd import mac_backward
+    from mac_network_b200.mac_cell import MACCell, MACParams, mac_network
+    from tests._util import load_golden, rebuild
+    meta, _ = load_golden(case)
+    cfg, inputs, pv = rebuild(meta, dtype=np.float32)
+    sh = meta["shape"]
+    B, N, d, L = sh["B"], sh["N"], sh["d"], sh["L"]
+    params = MACParams(cfg, L, values=pv, device="cpu")
+    x = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in inputs.items()}
+    dp = meta["dropouts"]
+    cell = MACCell(x["vecQuestions"], x["questionWords"], x["questionCntxWords"], x["questionLengths"], x["knowledgeBase"],
+                   dp["memory"], dp["read"], dp["write"], B, True, config=cfg, params=params, save_for_backward=True)
+    assert cell._use_tape
+    mac_network(cell, L)
+    n_nodes = len(cell._tape.nodes)
+    assert n_nodes >= 3 * L
+    fwd_calls = len(mock.calls)
+    g = mac_backward(cell, torch.zeros(B, d), torch.zeros(B, d))
+    assert g["knowledgeBase"].shape == (B, N, d) and g["vecQuestions"].shape == (B, d)
+    assert len(mock.calls) - fwd_calls >= n_nodes           # at least one backward launch per node
+    assert set(params.t) <= set(g)
+    if not cell._fused_read:
+        assert mock.calls.count("mac_rowdot_bwd") >= L and mock.calls.count("mac_kb_attend_bwd") >= L
+    else:
+        assert mock.calls.count("mac_read_bwd") == L

@@ -17,6 +17,7 @@ def test_oracle_matches_reference_fixture(case):
     cfg, inputs, params = rebuild(meta, np.float64)
     sh = meta["shape"]
     orc = MACOracle(cfg, params, dtype=np.float64)
+    orc.train = meta["train"]
     dp = meta["dropouts"]
     orc.run(sh["L"], inputs["vecQuestions"], inputs["questionWords"], inputs["questionCntxWords"],
             inputs["questionLengths"], inputs["knowledgeBase"], memoryDropout=dp["memory"],
@@ -31,6 +32,12 @@ def test_oracle_matches_reference_fixture(case):
         err = np.max(np.abs(out[k] - g)) / (np.max(np.abs(g)) + 1e-300)
         assert err < tol, (case, k, err)
     assert np.allclose(orc.trace[-1]["memory"], gold["final_memory"], rtol=0, atol=tol * 10)
+    for k in gold:              # memoryBN: the stored statistics after the forward (moved only by a training forward)
+        if k.startswith("final_bn_"):
+            name = [n for n in orc.p if n.endswith("/BatchNorm/" + k[len("final_bn_"):])]
+            assert len(name) == 1 and np.allclose(orc.p[name[0]], gold[k], rtol=0, atol=1e-12), (case, k)
+            moved = not np.array_equal(orc.p[name[0]], params[name[0]])
+            assert moved == bool(meta["train"]), (case, k, "statistics move in training only")
     # all draws consumed in train mode: the oracle makes the same dropout calls in the same order
     assert next(orc.uniforms, None) is None
 

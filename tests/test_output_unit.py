@@ -76,3 +76,24 @@ def test_output_unit_gpu_forward_backward(keep):
     assert max_rel(dq.cpu().numpy(), Q_.grad.numpy()) < 2e-4
     for k in pv:
         assert max_rel(grads[k].cpu().numpy(), P[k].grad.numpy()) < 2e-4, k
+
+
+@pytest.mark.gpu
+def test_softmax_xent_out_of_range_label_is_nan_not_a_wild_read():
+    """A label outside [0, A) (a data bug) must not index outside the logits row: that sample's loss is NaN, its gradient the
+    plain softmax, and the other samples are untouched."""
+    import torch
+    from mac_network_b200 import _lib as L
+    lib = L.load()
+    B, A = 6, 28
+    rng = np.random.RandomState(8)
+    logits = torch.from_numpy(rng.standard_normal((B, A)).astype(np.float32)).cuda()
+    labels = torch.tensor([3, -1, 27, 28, 0, 1 << 20], dtype=torch.int32).cuda()
+    losses, dl = torch.empty(B, device="cuda"), torch.empty(B, A, device="cuda")
+    L.check(lib.mac_softmax_xent(L.ptr(logits), L.ptr(labels), L.ptr(losses), L.ptr(dl), 1.0, B, A, L.stream_ptr()))
+    torch.cuda.synchronize()
+    ls, sm = losses.cpu().numpy(), torch.softmax(logits, 1).cpu().numpy()
+    assert np.isnan(ls[[1, 3, 5]]).all() and np.isfinite(ls[[0, 2, 4]]).all()
+    assert np.allclose(dl.cpu().numpy()[[1, 3, 5]], sm[[1, 3, 5]], atol=1e-6)
+    ref = -np.log(sm[[0, 2, 4], [3, 27, 0]])
+    assert np.allclose(ls[[0, 2, 4]], ref, atol=1e-5)
