@@ -207,6 +207,9 @@ int mac_write_fwd_next_y(const float* memory, const float* info, const float* Wf
 int mac_bcast_mul(const float* x, const float* v, float mul_bias, float* out, int B, int N, int d, mac_stream_t stream);
 /* out = act(x) elementwise */
 int mac_activation(const float* x, int act, float* out, long long n, mac_stream_t stream);
+/* fp32 <- bf16 widening of up to three equally long slabs in ONE launch (n elements each, n % 8 == 0, 16-byte aligned): the
+ * activations the tensor-core training forward leaves in bf16, read in fp32 by the backward kernels */
+int mac_widen_bf16(const void* const* src_bf16, float* const* dst, int nslab, long long n, mac_stream_t stream);
 /* ---- general (unfused) path: primitives for the flag combinations outside mac_read_fwd / mac_write_fwd ---- */
 /* out[r] = sum_s x_s[r,:] . w[k-range of s] + b      (ops.linear with outDim == 1 on concatenated inputs, ops.py:316-317) */
 int mac_rowdot_fwd(const float* const* x_segs, const int* k_segs, const int* ldx, int nseg, const float* w, float b,

@@ -83,6 +83,7 @@ PROTOTYPES = {
     "mac_read_bwd_tc_workspace_bytes": (c_sz, [c_int, c_int, c_int]),
     "mac_gate_bwd": (c_int, [c_fp] * 7 + [c_ll, c_fp]),
     "mac_activation_bwd": (c_int, [c_fp, c_fp, c_int, c_fp, c_ll, c_fp]),
+    "mac_widen_bf16": (c_int, [ctypes.POINTER(c_fp), ctypes.POINTER(c_fp), c_int, c_ll, c_fp]),
     "mac_batchnorm_fwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_f, c_f, c_int, c_fp, c_fp, c_fp, c_int, c_int, c_fp]),
     "mac_batchnorm_bwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_fp, c_fp, c_fp, c_int, c_int, c_fp]),
     "mac_bcast_op_bwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_int, c_f, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_fp]),

@@ -18,6 +18,59 @@ __global__ void axpy_kernel(float* __restrict__ dst, const float* __restrict__ s
   if (i < n) dst[i] += alpha * src[i];
 }
 
+// dst += dropout(src): the gradient through tf.nn.dropout added onto an accumulator in one pass (same Philox numbering as
+// mac_dropout_fwd: one draw per aligned quad of elements)
+__global__ void axpy_dropout_kernel(float4* __restrict__ dst, const float4* __restrict__ src, uint32_t thresh, float scale,
+                                    uint64_t seed, int site, int step, long long n4) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 v = src[i];
+  float4 o = dst[i];
+  const Philox4 r = philox4x32_10(seed, (uint64_t)i, (uint32_t)site, (uint32_t)step);
+  if ((r.x >> 8) >= thresh) o.x = fmaf(v.x, scale, o.x);
+  if ((r.y >> 8) >= thresh) o.y = fmaf(v.y, scale, o.y);
+  if ((r.z >> 8) >= thresh) o.z = fmaf(v.z, scale, o.z);
+  if ((r.w >> 8) >= thresh) o.w = fmaf(v.w, scale, o.w);
+  dst[i] = o;
+}
+
+// dZ = g * ELU'(H) (through the saved output H: H > 0 ? 1 : H + 1) and dbm_part[b,:] += sum_n dZ[b,n,:] in one pass.
+// grid (ceil(d/128), B), 256 threads: 32 column quads x 8 row groups (the map of read_bwd_logits_kernel), d % 4 == 0.
+__global__ void __launch_bounds__(256) elu_bwd_colsum_kernel(const float* __restrict__ H, const float* __restrict__ g,
+                                                            float* __restrict__ dZ, float* __restrict__ dsum_part, int N,
+                                                            int d) {
+  __shared__ float s_red[8][128];
+  const int q = threadIdx.x & 31, rg = threadIdx.x >> 5, b = blockIdx.y;
+  const int k = blockIdx.x * 128 + q * 4;
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
+  if (k < d) {
+    for (int n = rg; n < N; n += 8) {
+      const size_t o = ((size_t)b * N + n) * d + k;
+      const float4 h = *reinterpret_cast<const float4*>(H + o);
+      const float4 gi = *reinterpret_cast<const float4*>(g + o);
+      float4 z;
+      z.x = gi.x * (h.x > 0.f ? 1.f : h.x + 1.f);
+      z.y = gi.y * (h.y > 0.f ? 1.f : h.y + 1.f);
+      z.z = gi.z * (h.z > 0.f ? 1.f : h.z + 1.f);
+      z.w = gi.w * (h.w > 0.f ? 1.f : h.w + 1.f);
+      *reinterpret_cast<float4*>(dZ + o) = z;
+      s[0] += z.x; s[1] += z.y; s[2] += z.z; s[3] += z.w;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) s_red[rg][q * 4 + j] = s[j];
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int kk = blockIdx.x * 128 + threadIdx.x;
+    if (kk < d) {
+      float a = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a += s_red[i][threadIdx.x];
+      dsum_part[(size_t)b * d + kk] += a;
+    }
+  }
+}
+
 // dx = dy * act'(.) expressed through the saved OUTPUT y (tanh: 1-y^2; sigmoid: y(1-y); elu: y>0?1:y+1; relu: y>0)
 __global__ void act_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dy, int act,
                                float* __restrict__ dx, long long n) {
@@ -859,13 +912,18 @@ extern "C" int mac_read_bwd(const float* kb, const float* memory_in, const float
 // cast kernels (mac_cast_bf16, mac_pack_weight_bf16):
 //   dgrad  dX[M, in]   = dY[M, out] @ W^T        x = bf16(dY) [M, out],  Wt operand = bf16(W) in its own [in, out] layout
 //   wgrad  dW[in, out] = X^T[in, M] @ dY[M, out]  x = bf16(X)^T [in, M],  Wt operand = bf16(dY)^T [out, M]   (K = M = B*N)
-// The prologue / epilogue fusions of the fp32 kernels become separate fp32 passes here (P*y, dropout(KB), * ELU'(H),
-// dropout mask on dKB); the arithmetic of every pass is the forward's, so the masks and saved tensors are shared.
+// The prologue fusions of the fp32 kernels live in the transposing cast here (pack_t_bf16_kernel applies P*y / the KB dropout
+// mask while it builds the bf16 operand, and writes the row-major bf16 copy of a gradient from the same read); * ELU'(H) with
+// its column sums and the dropout mask on dKB are one fp32 pass each.  The arithmetic of every pass is the forward's, so the
+// masks and saved tensors are shared.
 // Requires d % 128 == 0 and (B*N) % 64 == 0 (the UMMA K block); otherwise MAC_ERR_UNSUPPORTED (use mac_read_bwd).
 // ------------------------------------------------------------------------------------------------------------------
 extern "C" int mac_tc_wgrad_splitk_(const void* xT, const void* gT, float* dW, float* partial, int in_dim, int out_dim, int K,
                                     mac_stream_t stream_);
 extern "C" size_t mac_tc_wgrad_partial_bytes_(int in_dim, int out_dim);
+extern "C" int mac_pack_t_bf16_(int mode, const float* X, void* Xt, void* Xrm, int K, int N, const float* rowvec,
+                                int rows_per_batch, uint32_t thresh, float scale, uint64_t seed, int site, int step,
+                                mac_stream_t stream_);
 static size_t rbt_align(size_t x) { return (x + 1023) & ~(size_t)1023; }
 
 extern "C" size_t mac_read_bwd_tc_workspace_bytes(int B, int N, int d) {
@@ -922,17 +980,20 @@ extern "C" int mac_read_bwd_tc(const float* kb, const float* memory_in, const fl
     st = (call);                  \
     if (st != MAC_OK) return st;  \
   } while (0)
-  // wgrad: dW[in, out] += X^T @ G with X^T already packed as xT [in, M]
+  // activations / gradients for the tensor-core operands: fp32 [M, d] -> bf16 transposed [d, M] (+ optionally the row-major
+  // bf16 copy), with the forward's P*y scaling or KB dropout applied on the way (pack_t_bf16_kernel, csrc/tc_gemm.cuh)
+  auto packT = [&](int mode, const float* X, void* Xt, void* Xrm, const float* rowvec) -> int {
+    return mac_pack_t_bf16_(mode, X, Xt, Xrm, M, d, rowvec, N, thr, scale, seed, MAC_SITE_READ_KB, step, stream_);
+  };
+  // wgrad: dW[in, out] += X^T @ G with X^T already packed as xT [in, M]; leaves bf16(G) row-major in g16 for the dgrad below
   auto wgrad = [&](const void* xT, int in, const float* G, float* dW) -> int {
-    int s = mac_pack_weight_bf16(G, gT16, M, d, stream_);                                   // G [M, d] -> G^T [d, M]
+    int s = packT(0, G, gT16, g16, nullptr);                                                 // G [M, d] -> G^T [d, M], bf16(G)
     if (s != MAC_OK) return s;
     return mac_tc_wgrad_splitk_(xT, gT16, dW, dWtmp, in, d, M, stream_);                          // dW[in, d] += xT @ (G^T)^T, split-K
   };
-  // dgrad: out[M, in] = G[M, d] @ W[in, d]^T   (W fp32 in its own [in, out = d] layout)
-  auto dgrad = [&](const float* G, const float* W, int in, float* out) -> int {
-    int s = mac_cast_bf16(G, g16, (long long)M * d, stream_);
-    if (s != MAC_OK) return s;
-    s = mac_cast_bf16(W, w16, (long long)in * d, stream_);
+  // dgrad: out[M, in] = G[M, d] @ W[in, d]^T   (W fp32 in its own [in, out = d] layout; G = the g16 of the preceding wgrad)
+  auto dgrad = [&](const float* W, int in, float* out) -> int {
+    int s = mac_cast_bf16(W, w16, (long long)in * d, stream_);
     if (s != MAC_OK) return s;
     return mac_linear_tc_fwd(g16, w16, nullptr, MAC_ACT_NON, out, 0, M, d, in, stream_);
   };
@@ -942,33 +1003,33 @@ extern "C" int mac_read_bwd_tc(const float* kb, const float* memory_in, const fl
   read_bwd_logits_kernel<<<dim3((d + 127) / 128, B), 256, 0, stream>>>(I1, control, w->wr, dkl, thr, scale, seed, step,
                                                                       bufA, dcontrol, dwr_part, dbm2_part, N, d);
   MAC_LAUNCH_CHECK();
-  // (3) I1 = H @ Wm2 + bm2:  dWm2 += H^T dI1 ;  dZ = (dI1 @ Wm2^T) * ELU'(H)
-  RBT(mac_pack_weight_bf16(H, xT16, M, d, stream_));
+  // (3) I1 = H @ Wm2 + bm2:  dWm2 += H^T dI1 ;  dZ = (dI1 @ Wm2^T) * ELU'(H) ; dbm += colsum(dZ)
+  RBT(packT(0, H, xT16, nullptr, nullptr));
   RBT(wgrad(xT16, d, bufA, dWm2));
-  RBT(dgrad(bufA, w->Wm2, d, tmp32));
-  RBT(mac_activation_bwd(H, tmp32, MAC_ACT_ELU, bufB, (long long)Md, stream_));
-  RBT(launch_colsum(bufB, dbm_part, B, N, d, 1, stream));
+  RBT(dgrad(w->Wm2, d, tmp32));
+  elu_bwd_colsum_kernel<<<dim3((d + 127) / 128, B), 256, 0, stream>>>(H, tmp32, bufB, dbm_part, N, d);
+  MAC_LAUNCH_CHECK();
   // (4) Z = [P*y, P] @ Wm + bm:  dWm += [P*y, P]^T dZ ;  dI0 = dZ @ Wm^T
-  RBT(mac_bcast_mul(P, y, 0.f, tmp32, B, N, d, stream_));                                        // P*y   (ops.py:694-703)
-  RBT(mac_pack_weight_bf16(tmp32, xT16, M, d, stream_));                                         // rows 0..d-1   of [2d, M]
-  RBT(mac_pack_weight_bf16(P, reinterpret_cast<__nv_bfloat16*>(xT16) + (size_t)d * M, M, d, stream_));   // rows d..2d-1
+  RBT(packT(1, P, xT16, nullptr, y));                                                            // rows 0..d-1   of [2d, M]: (P*y)^T
+  RBT(packT(0, P, reinterpret_cast<__nv_bfloat16*>(xT16) + (size_t)d * M, nullptr, nullptr));    // rows d..2d-1: P^T
   RBT(wgrad(xT16, 2 * d, bufB, dWm));
-  RBT(dgrad(bufB, w->Wm, 2 * d, bufC));
+  RBT(dgrad(w->Wm, 2 * d, bufC));
   // (5) I0 = [P*y, P]:  dP (bufA), dy, dbx
   read_bwd_p_kernel<<<dim3((d + 127) / 128, B), 256, 0, stream>>>(bufC, P, y, bufA, dy, dbx_part, N, d);
   MAC_LAUNCH_CHECK();
   // (6) P = dropout(KB) @ Wx + bx:  dWx += Kd^T dP ;  dKB += (dP @ Wx^T) * mask/keep
-  const float* kbd = kb;
-  if (drop) {
-    RBT(mac_dropout_fwd(kb, keep_read, seed, MAC_SITE_READ_KB, step, tmp32, (long long)Md, stream_));
-    kbd = tmp32;
-  }
-  RBT(mac_pack_weight_bf16(kbd, xT16, M, d, stream_));
+  RBT(packT(drop ? 2 : 0, kb, xT16, nullptr, nullptr));                                          // dropout(KB)^T: the forward's mask
   RBT(wgrad(xT16, d, bufA, dWx));
   if (dkb) {
-    RBT(dgrad(bufA, w->Wx, d, tmp32));
-    if (drop) RBT(mac_dropout_fwd(tmp32, keep_read, seed, MAC_SITE_READ_KB, step, tmp32, (long long)Md, stream_));
-    RBT(mac_axpy(dkb, tmp32, 1.f, (long long)Md, stream_));
+    RBT(dgrad(w->Wx, d, tmp32));
+    if (drop) {
+      axpy_dropout_kernel<<<(unsigned)((Md / 4 + 255) / 256), 256, 0, stream>>>(
+          reinterpret_cast<float4*>(dkb), reinterpret_cast<const float4*>(tmp32), thr, scale, seed, MAC_SITE_READ_KB, step,
+          (long long)(Md / 4));
+      MAC_LAUNCH_CHECK();
+    } else {
+      RBT(mac_axpy(dkb, tmp32, 1.f, (long long)Md, stream_));
+    }
   }
   // (7) y = md @ Wy + by with md = dropout(memory_in): an M = B product, fp32 (mac_linear_bwd)
   const float* mdp = memory_in;

@@ -1072,6 +1072,95 @@ __global__ void pack_weight_bf16_kernel(const float* __restrict__ W, __nv_bfloat
   }
 }
 
+// Activations for a tensor-core weight gradient: fp32 X [K rows, N cols] -> bf16 X^T [N, K] (the contraction index K = B*N rows
+// becomes the K-major direction of both wgrad operands), optionally also the row-major bf16 copy (the A operand of the matching
+// data gradient) from the same read.  64x64 tiles: 256-byte row reads, 128-byte row writes.
+//   MODE 0 plain; 1 x * rowvec[row / rows_per_batch, col] (P * y, ops.py:694-703); 2 dropout(x) with the forward's Philox stream
+//   (one draw per aligned column quad, element index row*N + col: mac_dropout_fwd's numbering).      N % 4 == 0, K % 2 == 0.
+template <int MODE>
+__global__ void __launch_bounds__(256) pack_t_bf16_kernel(const float* __restrict__ X, __nv_bfloat16* __restrict__ Xt,
+                                                         __nv_bfloat16* __restrict__ Xrm, int K, int N,
+                                                         const float* __restrict__ rowvec, int rows_per_batch, uint32_t thresh,
+                                                         float scale, uint64_t seed, int site, int step) {
+  __shared__ float tile[64][65];                              // [col][row]
+  const int k0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  const int tq = threadIdx.x & 15, tr = threadIdx.x >> 4;     // 16 column quads x 16 rows per pass
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    const int kk = tr + 16 * p;
+    const int k = k0 + kk, n = n0 + tq * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (k < K && n < N) {
+      v = *reinterpret_cast<const float4*>(X + (size_t)k * N + n);
+      if (MODE == 1) {
+        const float4 y = *reinterpret_cast<const float4*>(rowvec + (size_t)(k / rows_per_batch) * N + n);
+        v.x *= y.x; v.y *= y.y; v.z *= y.z; v.w *= y.w;
+      }
+      if (MODE == 2) {
+        const uint64_t e = (uint64_t)k * (uint64_t)N + (uint64_t)n;
+        const Philox4 r = philox4x32_10(seed, e >> 2, (uint32_t)site, (uint32_t)step);
+        v.x = ((r.x >> 8) >= thresh) ? v.x * scale : 0.f;
+        v.y = ((r.y >> 8) >= thresh) ? v.y * scale : 0.f;
+        v.z = ((r.z >> 8) >= thresh) ? v.z * scale : 0.f;
+        v.w = ((r.w >> 8) >= thresh) ? v.w * scale : 0.f;
+      }
+      if (Xrm) *reinterpret_cast<uint2*>(Xrm + (size_t)k * N + n) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+    }
+    tile[tq * 4 + 0][kk] = v.x;
+    tile[tq * 4 + 1][kk] = v.y;
+    tile[tq * 4 + 2][kk] = v.z;
+    tile[tq * 4 + 3][kk] = v.w;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int r = warp; r < 64; r += 8) {
+    const int n = n0 + r, k = k0 + 2 * lane;
+    if (n < N && k + 1 < K)
+      *reinterpret_cast<uint32_t*>(Xt + (size_t)n * K + k) = pack_bf16(tile[r][2 * lane], tile[r][2 * lane + 1]);
+  }
+}
+
+struct PackTArgs {
+  const float* rowvec = nullptr;
+  int rows_per_batch = 1;
+  uint32_t thresh = 0;
+  float scale = 1.f;
+  uint64_t seed = 0;
+  int site = 0, step = 0;
+};
+
+inline int pack_t_bf16_launch(int mode, const float* X, void* Xt, void* Xrm, int K, int N, const PackTArgs& a,
+                              cudaStream_t stream) {
+  if (!X || !Xt || K <= 0 || N <= 0 || (N & 3) || (K & 1)) return MAC_ERR_INVALID;
+  dim3 grid((N + 63) / 64, (K + 63) / 64);
+  __nv_bfloat16* t = reinterpret_cast<__nv_bfloat16*>(Xt);
+  __nv_bfloat16* r = reinterpret_cast<__nv_bfloat16*>(Xrm);
+  if (mode == 0)
+    pack_t_bf16_kernel<0><<<grid, 256, 0, stream>>>(X, t, r, K, N, nullptr, 1, 0u, 1.f, 0, 0, 0);
+  else if (mode == 1)
+    pack_t_bf16_kernel<1><<<grid, 256, 0, stream>>>(X, t, r, K, N, a.rowvec, a.rows_per_batch, 0u, 1.f, 0, 0, 0);
+  else
+    pack_t_bf16_kernel<2><<<grid, 256, 0, stream>>>(X, t, r, K, N, nullptr, 1, a.thresh, a.scale, a.seed, a.site, a.step);
+  MAC_LAUNCH_CHECK();
+  return MAC_OK;
+}
+
+// bf16 -> fp32 widening of up to three equally long slabs in one launch (the activations the tensor-core training forward
+// leaves in bf16, read in fp32 by the backward kernels)
+__global__ void __launch_bounds__(256) widen3_bf16_kernel(const uint4* __restrict__ s0, const uint4* __restrict__ s1,
+                                                         const uint4* __restrict__ s2, float4* __restrict__ d0,
+                                                         float4* __restrict__ d1, float4* __restrict__ d2, long long n8) {
+  const uint4* s = blockIdx.y == 0 ? s0 : blockIdx.y == 1 ? s1 : s2;
+  float4* d = blockIdx.y == 0 ? d0 : blockIdx.y == 1 ? d1 : d2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 v = s[i];
+    d[2 * i] = make_float4(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xffff0000u), __uint_as_float(v.y << 16),
+                           __uint_as_float(v.y & 0xffff0000u));
+    d[2 * i + 1] = make_float4(__uint_as_float(v.z << 16), __uint_as_float(v.z & 0xffff0000u), __uint_as_float(v.w << 16),
+                               __uint_as_float(v.w & 0xffff0000u));
+  }
+}
+
 // training mode: bf16 copy of dropout(KB) for this step (ops.py:678), same Philox stream as the fp32 path
 __global__ void dropout_cast_bf16_kernel(const float4* __restrict__ x, uint2* __restrict__ out, uint32_t thresh,
                                          float scale, uint64_t seed, int site, int step, long long n4) {

@@ -489,6 +489,33 @@ extern "C" int mac_tc_wgrad_splitk_(const void* xT, const void* gT, float* dW, f
 }
 extern "C" size_t mac_tc_wgrad_partial_bytes_(int in_dim, int out_dim) { return tc_wgrad_partial_bytes(in_dim, out_dim); }
 
+extern "C" int mac_pack_t_bf16_(int mode, const float* X, void* Xt, void* Xrm, int K, int N, const float* rowvec,
+                                int rows_per_batch, uint32_t thresh, float scale, uint64_t seed, int site, int step,
+                                mac_stream_t stream_) {
+  PackTArgs a;
+  a.rowvec = rowvec; a.rows_per_batch = rows_per_batch; a.thresh = thresh; a.scale = scale; a.seed = seed; a.site = site;
+  a.step = step;
+  return pack_t_bf16_launch(mode, X, Xt, Xrm, K, N, a, reinterpret_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int mac_widen_bf16(const void* const* src_bf16, float* const* dst, int nslab, long long n, mac_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!src_bf16 || !dst || nslab < 1 || nslab > 3 || n <= 0 || (n & 7)) return MAC_ERR_INVALID;
+  const uint4* s[3] = {nullptr, nullptr, nullptr};
+  float4* d[3] = {nullptr, nullptr, nullptr};
+  for (int i = 0; i < nslab; ++i) {
+    if (!src_bf16[i] || !dst[i]) return MAC_ERR_INVALID;
+    if ((reinterpret_cast<uintptr_t>(src_bf16[i]) | reinterpret_cast<uintptr_t>(dst[i])) & 15) return MAC_ERR_ALIGN;
+    s[i] = reinterpret_cast<const uint4*>(src_bf16[i]);
+    d[i] = reinterpret_cast<float4*>(dst[i]);
+  }
+  const long long n8 = n / 8;
+  const unsigned gx = (unsigned)std::min<long long>((n8 + 255) / 256, 148 * 16);
+  widen3_bf16_kernel<<<dim3(gx, nslab), 256, 0, stream>>>(s[0], s[1], s[2], d[0], d[1], d[2], n8);
+  MAC_LAUNCH_CHECK();
+  return MAC_OK;
+}
+
 extern "C" int mac_pack_weight_split3(const float* W, void* Wt3_bf16, int K, int N, mac_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (!W || !Wt3_bf16 || K <= 0 || N <= 0) return MAC_ERR_INVALID;

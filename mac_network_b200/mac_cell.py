@@ -550,7 +550,13 @@ class MACCell(object):
         base = self.ws.read.data_ptr()
         off = ((base + fp32_total + 1023) & ~1023) - base
         slab = (M * d * 2 + 1023) & ~1023
-        for k, src_slab in enumerate((0, 2, 3)):                       # P, H, I1  (slab 1 is P*y)
+        n = M * d
+        if n % 8 == 0:                                                 # one launch for the three slabs (mac_widen_bf16)
+            srcs = (ctypes.c_void_p * 3)(*[base + off + s_ * slab for s_ in (0, 2, 3)])       # P, H, I1  (slab 1 is P*y)
+            dsts = (ctypes.c_void_p * 3)(*[save.data_ptr() + 4 * k * n for k in range(3)])
+            check(self.lib.mac_widen_bf16(srcs, dsts, 3, n, stream_ptr()), "mac_widen_bf16")
+            return
+        for k, src_slab in enumerate((0, 2, 3)):
             src = self.ws.read[off + src_slab * slab: off + src_slab * slab + M * d * 2].view(torch.bfloat16)
             save[k * M * d:(k + 1) * M * d].copy_(src)
 
