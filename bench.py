@@ -471,6 +471,25 @@ def kernel_rooflines(shape, prec, pk):
     return out
 
 
+def h2d_probe_gbs(mb=128):
+    """Pinned-host -> device copy bandwidth of this rank with nothing else running (after NUMA binding): what the end-to-end
+    line's H2D of the batches can get at best."""
+    try:
+        src = torch.empty(mb << 20, dtype=torch.uint8).pin_memory()
+        dst = torch.empty(mb << 20, dtype=torch.uint8, device="cuda")
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(4):
+            dst.copy_(src, non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        return round(4 * (mb << 20) / (e0.elapsed_time(e1) * 1e-3) / 1e9, 1)
+    except Exception:          # noqa: BLE001 -- informational
+        return None
+
+
 def cast_threads_for(world, numa):
     """Host-cast pool size of one rank: its share of the CPUs it may run on.  After NUMA binding the affinity mask is one
     socket, shared by the ranks whose GPUs hang off it (half of the ranks on a 2-socket box); a cgroup quota caps the total."""
@@ -498,9 +517,11 @@ def run_ours(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = _lib.load()
-    # one process per GPU: stay on the GPU's NUMA node before any host thread / pinned buffer exists (multi-rank runs only)
-    numa = {"bound": False, "why": "single rank"}
-    if world > 1 and os.environ.get("MAC_NO_NUMA_BIND", "0") != "1":
+    # one process per GPU: stay on the GPU's NUMA node before any host thread / pinned buffer exists.  Single-rank runs too: a
+    # process that happens to start on the other socket stages every batch across the socket interconnect (H2D measured at
+    # 39 GB/s instead of the link's ~52: the end-to-end line of one rank was copy-bound, not kernel-bound)
+    numa = {"bound": False, "why": "MAC_NO_NUMA_BIND=1"}
+    if os.environ.get("MAC_NO_NUMA_BIND", "0") != "1":
         from mac_network_b200.serving import bind_to_gpu_numa
         numa = bind_to_gpu_numa(local)
     # how many ranks stage their batches through this rank's socket (they share its memory bandwidth)
@@ -511,6 +532,7 @@ def run_ours(args):
         ranks_on_node = max(1, sum(1 for x in nodes if x == numa.get("numa_node", -1)))
     numa["ranks_on_node"] = ranks_on_node
     numa["cuda_device"] = local
+    numa["h2d_gbs_alone"] = h2d_probe_gbs()
     shape = SHAPES[WORKLOAD]
     B, S, N, d, L = shape
     cfg = MACConfig.args("args", netLength=L)

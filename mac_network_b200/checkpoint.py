@@ -90,13 +90,16 @@ def save_training_state(path, trainer):
     out["beta1_power"] = np.float32(trainer.hp["b1"] ** step)
     out["beta2_power"] = np.float32(trainer.hp["b2"] ** step)
     out["mac_b200/step"] = np.int64(step)
-    np.savez(path, **out)
+    np.savez(path, **out)                 # numpy appends ".npz" to a path without it; load_training_state looks for both
     return list(out)
 
 
 def load_training_state(path, trainer):
     """Restore what `save_training_state` wrote into an identically configured `DPTrainer` (every rank calls it)."""
+    import os
     import torch
+    if not os.path.exists(path) and os.path.exists(path + ".npz"):
+        path = path + ".npz"
     z = np.load(path)
     p = trainer.params
     flats = {"": p.flat, EMA_SUFFIX: trainer.ema, ADAM_M: trainer.adam_m, ADAM_V: trainer.adam_v}

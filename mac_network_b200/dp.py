@@ -78,7 +78,7 @@ class DPTrainer(object):
             from .output_unit import OutputUnit
             self.out = OutputUnit({k: self.params.t[k] for k in extra_specs
                                    if k.startswith(("outputUnit/", "classifier/"))}, relu=cfg.relu, keep=output_dropout,
-                                  seed=seed)
+                                  seed=seed, version=lambda: self.params.version)
             self._views_of = views_of
         self.enc = self.stem = None
         if self._enc_specs is not None:
@@ -86,7 +86,8 @@ class DPTrainer(object):
             from .stem import Stem
             self.enc = QuestionEncoder({k: self.params.t[k] for k in self._enc_specs}, keep_input=enc_dropouts[0],
                                        keep_question=enc_dropouts[1], seed=seed)
-            self.stem = Stem({k: self.params.t[k] for k in self._stem_specs}, relu=cfg.relu, prec="fp32", seed=seed)
+            self.stem = Stem({k: self.params.t[k] for k in self._stem_specs}, relu=cfg.relu, prec="fp32", seed=seed,
+                             version=lambda: self.params.version)
             self.stem_dropout = float(stem_dropout)
             self._full_bufs = {}
         n = self.params.numel

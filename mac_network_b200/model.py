@@ -46,9 +46,9 @@ class MACnet(object):
         t = self.trainer
         # evaluation-mode views of the same variables: every dropout at 1.0 (model.py:118-125)
         self._enc = QuestionEncoder({k: p.t[k] for k in t._enc_specs}, keep_input=1.0, keep_question=1.0)
-        self._stem = Stem({k: p.t[k] for k in t._stem_specs}, relu=cfg.relu, prec=prec)
+        self._stem = Stem({k: p.t[k] for k in t._stem_specs}, relu=cfg.relu, prec=prec, version=lambda: p.version)
         self._out = OutputUnit({k: p.t[k] for k in p.specs if k.startswith(("outputUnit/", "classifier/"))}, relu=cfg.relu,
-                               keep=1.0)
+                               keep=1.0, version=lambda: p.version)
         self.device = p.device
         self.macCell = None                      # the cell of the last batch (model.py:740 reads macCell.attentions)
 

@@ -49,9 +49,12 @@ class OutputUnit(object):
     """Forward / loss / backward of the output unit on device tensors.  `params` / `grads`: dict name -> tensor
     (e.g. views into the trainer's flat buckets)."""
 
-    def __init__(self, params, relu="ELU", keep=1.0, seed=0):
+    def __init__(self, params, relu="ELU", keep=1.0, seed=0, version=None):
+        """`version`: optional callable returning a counter that changes whenever the parameter values do
+        (`MACParams.version`): the transposed weight copies of the backward are rebuilt when it moves."""
         self.lib = _lib.load()
         self.p = params
+        self._version_fn, self._wt_version = version, None
         self.relu, self.keep, self.seed = relu, float(keep), int(seed)
         self.nfc = len([k for k in params if k.startswith("classifier/linearLayerfc_") and k.endswith("weights/weight")])
         for k, v in params.items():
@@ -122,6 +125,10 @@ class OutputUnit(object):
         self._wt.clear()
 
     def _wt_of(self, name):
+        v = self._version_fn() if self._version_fn is not None else None
+        if v != self._wt_version:
+            self._wt.clear()
+            self._wt_version = v
         if name not in self._wt:
             self._wt[name] = self.p[name].t().contiguous()
         return self._wt[name]

@@ -44,13 +44,16 @@ def init_stem_params(specs, seed=0, dtype=np.float32, bias_scale=0.1):
 
 
 class Stem(object):
-    def __init__(self, params, relu="ELU", prec="fp32", seed=0):
-        """`params`: dict TF-name -> CUDA fp32 tensor (HWIO kernels, biases)."""
+    def __init__(self, params, relu="ELU", prec="fp32", seed=0, version=None):
+        """`params`: dict TF-name -> CUDA fp32 tensor (HWIO kernels, biases).  `version`: optional callable returning a counter
+        that changes whenever the parameter values do (`MACParams.version`): the packed bf16 kernels are rebuilt when it moves
+        (optimizer step, checkpoint restore, EMA swap -- ADVICE r1), whoever changed the values."""
         self.lib = _lib.load()
         self.p = params
         self.relu, self.prec, self.seed = relu, prec, int(seed)
         self.nlayers = len([k for k in params if k.endswith("kernels/kernel")])
         self._packed = {}
+        self._version_fn, self._packed_version = version, None
         dev = next(iter(params.values())).device
         self.device = dev
 
@@ -58,6 +61,10 @@ class Stem(object):
         K = self.p["stem/cnnLayercnn_%d/kernels/kernel" % i]
         W = K.reshape(-1, K.shape[3])                       # [9*Cin, Cout], row-major view of the HWIO kernel
         if self.prec == "bf16":
+            v = self._version_fn() if self._version_fn is not None else None
+            if v != self._packed_version:
+                self._packed.clear()
+                self._packed_version = v
             if i not in self._packed:
                 Wt = torch.empty((W.shape[1], W.shape[0]), dtype=torch.bfloat16, device=W.device)
                 check(self.lib.mac_pack_weight_bf16(ptr(W), ptr(Wt), W.shape[0], W.shape[1], stream_ptr()), "pack")

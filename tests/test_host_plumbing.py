@@ -140,6 +140,14 @@ def test_training_state_roundtrip(monkeypatch, tmp_path):
     k = "MACnetwork/MACCell/read/linearLayermemKbProj/weights/weight"
     o = a.params.offsets[k]
     assert np.array_equal(vals[k].reshape(-1), a.ema[o:o + vals[k].size].numpy())
+    # a path without the extension round-trips too (numpy appends ".npz" on save, not on load: ADVICE r1)
+    save_training_state(str(tmp_path / "bare"), a)
+    assert load_training_state(str(tmp_path / "bare"), b) == 17
+    # weight-derived caches of the stem / output unit follow the parameter version, whoever changed the values
+    wt = b.out._wt_of("classifier/linearLayerfc_0/weights/weight")
+    assert b.out._wt_of("classifier/linearLayerfc_0/weights/weight") is wt          # cached while nothing changes
+    b.params.touch()
+    assert b.out._wt_of("classifier/linearLayerfc_0/weights/weight") is not wt      # rebuilt after a restore / step
 
 
 @pytest.mark.parametrize("prec,tc", [("fp32", True), ("bf16", False), ("bf16", True)])
