@@ -1017,7 +1017,8 @@ def main():
     ap.add_argument("--skip-train", action="store_true", help="skip the short DP-training arm of the default run")
     ap.add_argument("--mode", default="infer", choices=["infer", "train", "quick"])
     ap.add_argument("--batch-mult", type=int, default=1, help="--mode quick: requests of B=64 concatenated per pass")
-    ap.add_argument("--streams", type=int, default=6, help="independent passes in flight (each on its own stream)")
+    ap.add_argument("--streams", type=int, default=8, help="independent passes in flight (each on its own stream); "
+                    "measured on the B200: 1: 15.9k, 2: 27.3k, 4: 28.8k, 6: 29.5k, 8: 30.0k reasoning-steps/s")
     ap.add_argument("--fold-y", type=int, default=-1, help="write unit folded with the next step's projY: 1/0, -1 = by --streams")
     ap.add_argument("--rooflines-only", action="store_true", help="only the per-kernel measurements (for ncu)")
     ap.add_argument("--min-time", type=float, default=0.5, help="repeat the --steps block until this many seconds are timed")
