@@ -66,6 +66,13 @@ struct ReadStepParams {
   const __nv_bfloat16* Wy_t;        // [d, d]   read/.../linearLayerprojY weight, bf16 [out, in]
   const float* by;                  // [d]
   float* mem_out;                   // [B, d]   memory of THIS step (written when info_prev != NULL)
+  // packed form (pair kernel, N > 128, no whole-step prologue): CTA i takes knowledge-base rows [128 i, 128 i + 128) of the
+  // [B*N, d] matrices whatever samples they belong to (at most two when N > 128) -- no padded rows: ceil(B*N / 128) CTAs
+  // instead of 2 B (98 instead of 128 at B = 64, N = 196).  Each CTA leaves, per sample it touches, an un-normalised softmax
+  // partial (local max, sum of exponentials, sum of exp * KB rows) in `part`, and exp values in `att`; read_step_combine_kernel
+  // merges the 2-3 partials of every sample.  part = [B][3][d] partial sums, then [B][3][2] (max, sum).
+  int packed;
+  float* part;
   int dbg_flags;                    // profiling only (mac_dbg_read_step_flags; results are WRONG when set): 1 skip the P*y
                                     // smem pass, 2 skip the GEMM-1/2 MMAs, 4 skip the Wm loads of GEMM 1 (pair kernel)
   long long* dbg;                   // profiling only (mac_dbg_read_step_timestamps): [gridDim.x][64] SM-clock stamps, or NULL
@@ -586,9 +593,13 @@ read_step2_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_consta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int N = p.N;
   const uint32_t rank = cluster_rank();
-  const int s0 = blockIdx.x >> 1;
-  const int row0 = s0 * N + (int)rank * 128;
-  const int valid = min(128, N - (int)rank * 128);
+  const bool packed = p.packed != 0;
+  // per-sample form: pair = sample, rank = its row half.  packed form: CTA = 128 consecutive rows of [B*N, d]
+  const int row0 = packed ? (int)blockIdx.x * 128 : (int)(blockIdx.x >> 1) * N + (int)rank * 128;
+  const int valid = packed ? max(0, min(128, p.B * N - row0)) : min(128, N - (int)rank * 128);
+  const int s0 = packed ? min(row0 / N, p.B - 1) : (int)(blockIdx.x >> 1);      // sample of the tile's first row
+  const int s1 = min(s0 + 1, p.B - 1);                                          // packed: sample of the rows from `bnd` on
+  const int bnd = packed ? max(0, min(valid, (s0 + 1) * N - row0)) : valid;     // rows [0, bnd): s0, [bnd, valid): s1
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_p);
@@ -717,6 +728,7 @@ read_step2_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_consta
       par[i] = __ldg(p.bm2 + i);
       par[RS_D + i] = __ldg(p.wr + i);
       par[2 * RS_D + i] = __ldg(p.ctrl + (size_t)s0 * RS_D + i);
+      par[3 * RS_D + i] = __ldg(p.ctrl + (size_t)s1 * RS_D + i);
     }
     const bool row_ok = row < valid;
     const int wi = warp - 2;
@@ -830,7 +842,7 @@ read_step2_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_consta
       }
       if (wt == 0) rs_stamp(p, 57);                // y ready
     }
-    const __nv_bfloat16* qrow = p.Q + (size_t)(row0 + (row_ok ? row : 0)) * RS_D + cg * 16;
+    const __nv_bfloat16* qrow = p.Q + (size_t)(row_ok ? row0 + row : 0) * RS_D + cg * 16;
     uint4 qv[8];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -843,8 +855,8 @@ read_step2_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_consta
       const int pc = wt & 7;
       const int lc_a = pc ^ (r_a & 7), lc_b = pc ^ (r_b & 7);
       const bool ok_a = r_a < valid, ok_b = r_b < valid;
-      const float* y_a = (p.Wy_t ? s_y : p.y + (size_t)s0 * RS_D) + lc_a * 8;
-      const float* y_b = (p.Wy_t ? s_y : p.y + (size_t)s0 * RS_D) + lc_b * 8;
+      const float* y_a = (p.Wy_t ? s_y : p.y + (size_t)(r_a < bnd ? s0 : s1) * RS_D) + lc_a * 8;
+      const float* y_b = (p.Wy_t ? s_y : p.y + (size_t)(r_b < bnd ? s0 : s1) * RS_D) + lc_b * 8;
       auto scale16 = [](uint4 v, const float4 f0, const float4 f1) {
         uint4 o;
         o.x = pack_bf16(bf16lo(v.x) * f0.x, bf16hi(v.x) * f0.y);
@@ -927,7 +939,7 @@ read_step2_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_consta
 
     // ---- epilogue 2
     rs_worker_bar();
-    const float* crow = par + 2 * RS_D;
+    const float* crow = par + (row < bnd ? 2 : 3) * RS_D;          // this row's sample's control state
     float part = 0.f;
 #pragma unroll 1
     for (int h = 0; h < 2; ++h) {
@@ -976,6 +988,85 @@ read_step2_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_consta
         v[i] = n < nrows ? ldg_nc_v4(kbase + (size_t)n * RS_D) : make_uint4(0u, 0u, 0u, 0u);
       }
     }
+    if (packed) {
+      // ---- packed tail: up to two row segments (samples s0, s0 + 1); warp 0 / warp 1 form the local maximum, the exp values
+      //      and their sum of segment 0 / 1, then one weighted-sum pass per non-empty segment; no pair exchange at all.
+      if (wi < 2) {
+        const int lo = wi == 0 ? 0 : bnd, hi = wi == 0 ? bnd : valid;
+        float e_lane[4] = {0.f, 0.f, 0.f, 0.f};
+        float mx = -INFINITY, sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int n = lane + 32 * i;
+          if (n >= lo && n < hi) mx = fmaxf(mx, s_att[n]);
+        }
+        mx = warp_max(mx);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int n = lane + 32 * i;
+          if (n >= lo && n < hi) {
+            e_lane[i] = __expf(s_att[n] - mx);
+            sum += e_lane[i];
+          }
+        }
+        sum = warp_sum(sum);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int n = lane + 32 * i;
+          if (n >= lo && n < hi) s_att[n] = e_lane[i];
+        }
+        if (lane == 0) {
+          s_xch[2 * wi] = mx;
+          s_xch[2 * wi + 1] = sum;
+        }
+      }
+      rs_worker_bar();
+      if (wt == 0) rs_stamp(p, 6);
+      if (wt < valid) p.att[(size_t)row0 + wt] = s_att[wt];        // exp values; the combine kernel scales them by c_r / Z
+      // both segments' weighted sums in ONE pass over the KB rows held in registers (each row's weight goes to the
+      // accumulators of its own segment, the other set gets an exact zero), into two [8][512] reduction slabs (units 9, 10)
+      {
+        float accA[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        float accB[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int n = rg + RS_RED_GROUPS * i;
+          const float a = n < valid ? s_att[n] : 0.f;
+          const float aA = n < bnd ? a : 0.f, aB = n < bnd ? 0.f : a;
+          const float k0 = bf16lo(v[i].x), k1 = bf16hi(v[i].x), k2 = bf16lo(v[i].y), k3 = bf16hi(v[i].y);
+          const float k4 = bf16lo(v[i].z), k5 = bf16hi(v[i].z), k6 = bf16lo(v[i].w), k7 = bf16hi(v[i].w);
+          accA[0] = fmaf(aA, k0, accA[0]); accA[1] = fmaf(aA, k1, accA[1]); accA[2] = fmaf(aA, k2, accA[2]);
+          accA[3] = fmaf(aA, k3, accA[3]); accA[4] = fmaf(aA, k4, accA[4]); accA[5] = fmaf(aA, k5, accA[5]);
+          accA[6] = fmaf(aA, k6, accA[6]); accA[7] = fmaf(aA, k7, accA[7]);
+          accB[0] = fmaf(aB, k0, accB[0]); accB[1] = fmaf(aB, k1, accB[1]); accB[2] = fmaf(aB, k2, accB[2]);
+          accB[3] = fmaf(aB, k3, accB[3]); accB[4] = fmaf(aB, k4, accB[4]); accB[5] = fmaf(aB, k5, accB[5]);
+          accB[6] = fmaf(aB, k6, accB[6]); accB[7] = fmaf(aB, k7, accB[7]);
+        }
+        float4* dst = reinterpret_cast<float4*>(s_red + rg * RS_D + cq * 8);
+        dst[0] = make_float4(accA[0], accA[1], accA[2], accA[3]);
+        dst[1] = make_float4(accA[4], accA[5], accA[6], accA[7]);
+        dst += RS_RED_GROUPS * RS_D / 4;
+        dst[0] = make_float4(accB[0], accB[1], accB[2], accB[3]);
+        dst[1] = make_float4(accB[4], accB[5], accB[6], accB[7]);
+      }
+      rs_worker_bar();
+#pragma unroll 1
+      for (int seg = 0; seg < 2; ++seg) {
+        if ((seg == 0 ? bnd : valid - bnd) <= 0) continue;
+        float t = 0.f;
+#pragma unroll
+        for (int g = 0; g < RS_RED_GROUPS; ++g) t += s_red[(seg * RS_RED_GROUPS + g) * RS_D + wt];
+        const int smp = seg == 0 ? s0 : s1;
+        const int slot = (int)blockIdx.x - (smp * N) / 128;        // 0 .. 2: this tile's position among the sample's tiles
+        p.part[((size_t)smp * 3 + slot) * RS_D + wt] = t;
+        if (wt == 0) {
+          float* mz = p.part + (size_t)p.B * 3 * RS_D + ((size_t)smp * 3 + slot) * 2;
+          mz[0] = s_xch[2 * seg];
+          mz[1] = s_xch[2 * seg + 1];
+        }
+      }
+      if (wt == 0) rs_stamp(p, 7);
+    } else {
     // ---- softmax over the sample's N rows, split over the pair: each CTA forms its LOCAL maximum m_r, exp values
     //      e[n] = exp(l[n] - m_r), their sum z_r and the un-normalised partial I_r = sum_n e[n] KB[n, :]; rank 1 ships
     //      (m_1, z_1, e_1[], I_1[]) into rank 0's shared memory, ONE cluster barrier, and rank 0 writes
@@ -1051,8 +1142,9 @@ read_step2_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_consta
       }
     }
     if (wt == 0) rs_stamp(p, 7);
+    }                                              // !packed
   }
-  if (warp < 2) {                                  // the producer / MMA warps take part in the tail's cluster barrier
+  if (warp < 2 && !packed) {                       // the producer / MMA warps take part in the tail's cluster barrier
     __syncwarp();
     cluster_barrier();
   }
@@ -1073,6 +1165,44 @@ inline int& read_step_dbg_flags() { static int f = 0; return f; }
 
 // can the fused kernel take this shape?
 inline bool read_step_supported(int B, int N, int d) { return d == RS_D && N >= 1 && N <= 256 && B >= 1; }
+
+// Packed form: merge the per-tile softmax partials of every sample (read_step2_kernel, `packed`).  Sample s owns tiles
+// first = floor(s N / 128) .. last = floor((s N + N - 1) / 128) (2 or 3 of them for 128 < N <= 256); with the local maxima m_r,
+// sums z_r and un-normalised partial sums I_r:  M = max m_r, c_r = exp(m_r - M), Z = sum c_r z_r,
+//   info[s, :] = sum_r c_r I_r / Z ,   att[s, n] = e[n] * c_{r(n)} / Z   (e[n] left in `att` by the tile that owns row n).
+// grid B, RS_D threads.
+__global__ void __launch_bounds__(RS_D) read_step_combine_kernel(const float* __restrict__ part, float* __restrict__ att,
+                                                                float* __restrict__ info, int B, int N) {
+  const int s = blockIdx.x, k = threadIdx.x;
+  const int first = (s * N) / 128, last = (s * N + N - 1) / 128;
+  const int ns = last - first + 1;                                 // <= 3
+  const float* mz = part + (size_t)B * 3 * RS_D + (size_t)s * 3 * 2;
+  float m[3], c[3];
+  float M = -INFINITY;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    m[r] = r < ns ? mz[2 * r] : -INFINITY;
+    M = fmaxf(M, m[r]);
+  }
+  float Z = 0.f;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    c[r] = r < ns ? __expf(m[r] - M) : 0.f;
+    if (r < ns) Z = fmaf(c[r], mz[2 * r + 1], Z);
+  }
+  const float rZ = 1.f / Z;
+  float acc = 0.f;
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+    if (r < ns) acc = fmaf(c[r], part[((size_t)s * 3 + r) * RS_D + k], acc);
+  info[(size_t)s * RS_D + k] = acc * rZ;
+  for (int n = k; n < N; n += RS_D) {
+    const int r = (s * N + n) / 128 - first;
+    att[(size_t)s * N + n] *= c[r] * rZ;
+  }
+}
+
+inline size_t read_step_partial_bytes(int B) { return (size_t)B * 3 * (RS_D + 2) * sizeof(float) + 1024; }
 
 // inv = [P | Q] (tc_read_invariant); y, control [B, d] fp32; att [B, N], info [B, d]
 // whole-step form: the write unit of the previous step and this step's memory projection in the kernel's prologue
@@ -1137,8 +1267,15 @@ inline int read_step_launch(const void* inv, const void* kb_bf16, const float* y
       attr_set[2] = true;
     }
     p.spc = 1;
+    // packed tiles (no padded rows) unless the whole-step prologue needs the pair = sample mapping; MAC_READ_PACKED=0 reverts
+    static const bool packed_ok = !(getenv("MAC_READ_PACKED") && atoi(getenv("MAC_READ_PACKED")) == 0);
+    const bool packed = packed_ok && !ws;
+    const int ntiles = (M + 127) / 128;
+    p.packed = packed ? 1 : 0;
+    // the partials live behind [P | Q] in the invariant buffer (tc_read_invariant_bytes reserves read_step_partial_bytes)
+    p.part = packed ? reinterpret_cast<float*>(const_cast<char*>(ibase) + 2 * slab) : nullptr;
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(2 * B, 1, 1);
+    cfg.gridDim = dim3(packed ? 2 * ((ntiles + 1) / 2) : 2 * B, 1, 1);
     cfg.blockDim = dim3(RS_THREADS, 1, 1);
     cfg.dynamicSmemBytes = RS2_SMEM_BYTES;
     cfg.stream = stream;
@@ -1150,6 +1287,10 @@ inline int read_step_launch(const void* inv, const void* kb_bf16, const float* y
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     MAC_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, mp, hw1, hw2, p));
+    if (packed) {
+      MAC_LAUNCH_CHECK();
+      read_step_combine_kernel<<<B, RS_D, 0, stream>>>(p.part, att, info, B, N);
+    }
   } else if (N > 128) {
     auto kern = read_step_kernel<true>;
     if (!attr_set[0]) {

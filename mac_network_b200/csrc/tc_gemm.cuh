@@ -1229,7 +1229,8 @@ inline int tc_read_chain(const float* kb_f32, const void* kb_bf16, const float* 
 //   PY = P * y_b ;  H = ELU(PY @ Wm[0:d, :] + Q) ;  logits = ... (unchanged)
 // i.e. 2 x d instead of 4 x d MACs per knowledge-base element and step.
 inline size_t tc_read_invariant_bytes(int B, int N, int d) {
-  return (size_t)2 * (((size_t)B * N * d * 2 + 1023) & ~(size_t)1023) + 1024;
+  // [P | Q] bf16 slabs + the per-tile softmax partials of the packed fused read step (read_step.cuh: B x 3 x (512 + 2) floats)
+  return (size_t)2 * (((size_t)B * N * d * 2 + 1023) & ~(size_t)1023) + 1024 + (size_t)B * 3 * (512 + 2) * sizeof(float) + 1024;
 }
 
 // PY[m, :] = P[m, :] * y[m / rows_per_batch, :]   (8 bf16 per thread)

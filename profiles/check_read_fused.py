@@ -90,7 +90,8 @@ def main():
     d = 512
     res = []
     for (B, N, tm) in ((2, 196, False), (3, 49, False), (5, 130, False), (2, 256, False), (7, 128, False), (3, 100, False),
-                       (4, 17, False), (64, 196, True), (64, 49, True), (384, 196, True)):
+                       (4, 17, False), (9, 200, False), (1, 129, False), (3, 255, False), (11, 131, False),
+                       (64, 196, True), (64, 49, True), (384, 196, True)):
         r = case(lib, B, N, d, 100 + B + N, time_it=tm)
         print(json.dumps(r), flush=True)
         res.append(r)

@@ -47,15 +47,17 @@ def main():
             torch.cuda.synchronize()
             raw.mac_dbg_read_step_timestamps(None)
             full = dbg.cpu().numpy().astype(np.float64)
+            lead_all = full[0::2]
+            full = full[full[:, 7] != 0]               # the packed form launches fewer CTAs than the buffer has rows
             s = full[:, :8]
             dl = np.diff(s, axis=1)
             names = ["scale(GEMM1 feed)", "GEMM1 tail", "epilogue1", "GEMM2", "epilogue2", "softmax", "weighted sum"]
-            out = {"B": B, "N": N, "cold_L2": cold, "grid": grid, "dbg_flags": flags,
+            out = {"B": B, "N": N, "cold_L2": cold, "grid": int(full.shape[0]), "dbg_flags": flags,
                    "total_clk_median": float(np.median(s[:, 7] - s[:, 0])), "total_clk_max": float(np.max(s[:, 7] - s[:, 0])),
                    "phases_median_clk": {n: float(np.median(dl[:, i])) for i, n in enumerate(names)},
                    "phases_max_clk": {n: float(np.max(dl[:, i])) for i, n in enumerate(names)}}
             if N > 128 and full[:, 8:].any():
-                lead = full[0::2]                      # leader CTAs (rank 0 of each pair)
+                lead = lead_all[lead_all[:, 7] != 0]   # leader CTAs (rank 0 of each pair)
                 rel = lambda a, b: [float(np.median(lead[:, a + i] - lead[:, 0])) if lead[:, a + i].any() else None for i in range(b)]
                 out["pair_pipeline_clk_from_start_leader_median"] = {
                     "tma_issue_kb": rel(16, 8), "a_landed_kb": rel(24, 8), "a_scaled_both_kb": rel(48, 8),
