@@ -74,7 +74,8 @@ struct ReadStepParams {
   int packed;
   float* part;
   int dbg_flags;                    // profiling only (mac_dbg_read_step_flags; results are WRONG when set): 1 skip the P*y
-                                    // smem pass, 2 skip the GEMM-1/2 MMAs, 4 skip the Wm loads of GEMM 1 (pair kernel)
+                                    // smem pass, 2 skip the GEMM-1/2 MMAs, 4 skip the Wm loads of GEMM 1 (pair kernel),
+                                    // 8 skip the combine launch of the packed form
   long long* dbg;                   // profiling only (mac_dbg_read_step_timestamps): [gridDim.x][64] SM-clock stamps, or NULL
 };
 
@@ -1287,7 +1288,7 @@ inline int read_step_launch(const void* inv, const void* kb_bf16, const float* y
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     MAC_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, mp, hw1, hw2, p));
-    if (packed) {
+    if (packed && !(p.dbg_flags & 8)) {            // flag 8 (profiling: time the main kernel alone) leaves att / info unmerged
       MAC_LAUNCH_CHECK();
       read_step_combine_kernel<<<B, RS_D, 0, stream>>>(p.part, att, info, B, N);
     }
