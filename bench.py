@@ -618,7 +618,10 @@ def run_ours(args):
     torch.cuda.empty_cache()
     pipe = HostPipeline(cfg, params, shape, prec=args.prec, slots=ND, use_graph=use_graph, fold_y=fold_y,
                         cast_threads=cast_threads_for(world, numa),
-                        host_cast=None if ranks_on_node <= 1 else False)      # see HostPipeline: socket memory bandwidth
+                        # host bf16 cast while at most two ranks stage through one socket (its staging ring stays in the
+                        # last-level cache: 43.4k vs 40.0k without the cast at 2 ranks / socket); with more, fp32 over PCIe
+                        host_cast=None if (ranks_on_node <= 2 or os.environ.get("MAC_FORCE_HOST_CAST", "0") == "1")
+                        else False, stage_ring=3 if ranks_on_node <= 1 else 2)
     h2d_bytes, d2h_bytes = pipe.h2d_bytes, pipe.d2h_bytes
     e2e_host_cast, e2e_cast_threads, pipe_cast_ms = pipe.host_kb_bf16, pipe.cast_threads, pipe.cast_ms
 

@@ -145,7 +145,7 @@ class _Slot(object):
         c = self.cell
         self.outs_dev = {"control": c._hc[L], "memory": c._hm[L], "att_kb": c._att_kb, "att_question": c._att_q}
         self.outs_host = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in self.outs_dev.items()}
-        self.kb_stage = (torch.empty(B, N, d, dtype=torch.bfloat16).pin_memory() if host_kb_bf16 else None)
+        self.kb_stage = None        # assigned per submit from HostPipeline's small staging ring
         self.h2d_done = torch.cuda.Event()
         self.done = torch.cuda.Event()
         self.busy = False
@@ -158,7 +158,7 @@ class HostPipeline(object):
     state, per-step KB and question attention maps) that stay valid until the slot is reused `slots` submits later."""
 
     def __init__(self, cfg, params, shape, prec="bf16", slots=4, use_graph=True, cast_threads=None, fold_y=None,
-                 host_cast=None):
+                 host_cast=None, stage_ring=None):
         """`host_cast`: None = decide here (bf16 path: cast the knowledge base to bf16 on the host if that is faster than the
         PCIe time it saves); False = never.  Callers that run several ranks per socket pass False: the cast makes a pass touch
         ~57 MB of host DRAM (fp32 read + bf16 write + DMA read) instead of 31 MB, and the ranks of one socket share its memory
@@ -189,6 +189,26 @@ class HostPipeline(object):
         self._cast_for = None
         self._next = 0
         B, S, N, d, L = shape
+        # bf16 staging of the knowledge base through a SMALL ring of pinned buffers (not one buffer per device slot), so that
+        # what the cast writes and the H2D engine reads stays in the socket's last-level cache -- the cast then costs DRAM only
+        # its fp32 read.  Measured with two ranks on one socket (reasoning-steps/s, both ranks): 30.3k with 12 full-size buffers
+        # per rank, 36.9k with 3, 43.4k with 2; no cast: 40.0k.  One rank: 28.4k / 28.9k / 25.2k with 2 / 3 / 12.
+        # The batch can also go through the ring in several pieces (MAC_HOST_CAST_CHUNKS), the cast of piece c+1 under the
+        # copy of piece c: measured WORSE (4 pieces: 18.6k with one rank, 18.8-24.3k with two) -- every piece is one more
+        # wake-up of the cast pool and one more blocking wait in the submit loop -- so the default is one piece.
+        self.chunks = max(1, int(os.environ.get("MAC_HOST_CAST_CHUNKS", "1")))
+        n_kb = B * N * d
+        while n_kb % (self.chunks * 64):
+            self.chunks -= 1
+        self.chunk_elems = n_kb // self.chunks
+        # `stage_ring`: 3 full-size buffers when this rank has its socket to itself (one more pass of slack between a buffer's
+        # copy and its next cast), 2 when the socket's cache is shared with another rank's ring (callers pass it; default 3)
+        ring = int(os.environ.get("MAC_HOST_STAGE_RING", "0")) or (int(stage_ring) if stage_ring else 3) * self.chunks
+        ring = max(2, ring)
+        self._stages = ([torch.empty(self.chunk_elems, dtype=torch.bfloat16).pin_memory() for _ in range(ring)]
+                        if self.host_kb_bf16 else [])
+        self._stage_busy = [None] * len(self._stages)      # event after the copy that last read each buffer
+        self._piece = 0                                     # running index of the next piece to cast (pass * chunks + c)
         kb_bytes = B * N * d * (2 if self.host_kb_bf16 else 4)
         self.h2d_bytes = kb_bytes + B * S * d * 4 + B * d * 4 + B * 4
         self.d2h_bytes = sum(v.numel() * v.element_size() for v in self.slots[0].outs_host.values())
@@ -205,10 +225,24 @@ class HostPipeline(object):
             best = min(best, time.perf_counter() - t0)
         return best * 1e3
 
-    # -- host cast of the knowledge base, one batch ahead of the GPU work, on the library's thread pool
+    # -- host cast of the knowledge base on the library's thread pool, one PIECE ahead of the copies
     #    (mac_host_cast_bf16_begin returns at once; no Python threads, so no GIL hand-offs in the submit loop)
+    def _cast_begin(self, kb, c):
+        """Start the cast of piece c of `kb` into the next staging buffer; returns that buffer's ring index."""
+        si = self._piece % len(self._stages)
+        self._piece += 1
+        if self._stage_busy[si] is not None:
+            self._stage_busy[si].synchronize()         # the previous copy out of this staging buffer has finished
+            self._stage_busy[si] = None
+        src = kb.data_ptr() + 4 * c * self.chunk_elems
+        st = self.lib.mac_host_cast_bf16_begin(ctypes.c_void_p(src), ctypes.c_void_p(self._stages[si].data_ptr()),
+                                               self.chunk_elems, self.cast_threads)
+        if st != 0:
+            raise _lib.MacB200Error("mac_host_cast_bf16_begin failed: %d" % st)
+        return si
+
     def prefetch(self, batch):
-        """Optional: start the host cast for the batch that the NEXT submit() will take."""
+        """Optional: start the host cast (of the first piece) for the batch that the NEXT submit() will take."""
         if not self.host_kb_bf16:
             return
         kb = batch["knowledgeBase"]
@@ -216,31 +250,40 @@ class HostPipeline(object):
             if self._cast_for[0] == self._next and self._cast_for[1] is kb:
                 return
             self.lib.mac_host_cast_bf16_end()
-        slot = self.slots[self._next % len(self.slots)]
-        if slot.busy:
-            slot.h2d_done.synchronize()                # the previous copy out of this staging buffer has finished
-        st = self.lib.mac_host_cast_bf16_begin(ctypes.c_void_p(kb.data_ptr()), ctypes.c_void_p(slot.kb_stage.data_ptr()),
-                                               kb.numel(), self.cast_threads)
-        if st != 0:
-            raise _lib.MacB200Error("mac_host_cast_bf16_begin failed: %d" % st)
-        self._cast_for = (self._next, kb)
+            self._piece -= 1                           # that piece is discarded: its staging buffer is taken again
+        si = self._cast_begin(kb, 0)
+        self._cast_for = (self._next, kb, si)
 
     def submit(self, batch, next_batch=None):
         t = self._next
         slot = self.slots[t % len(self.slots)]
         if self.host_kb_bf16:
-            self.prefetch(batch)
-            self.lib.mac_host_cast_bf16_end()
+            self.prefetch(batch)                       # no-op when the caller (or the previous submit) already started it
+            si = self._cast_for[2]
             self._cast_for = None
         self._next = t + 1
-        if next_batch is not None:
-            self.prefetch(next_batch)
         with torch.cuda.stream(slot.stream):
             slot.x["vecQuestions"].copy_(batch["vecQuestions"], non_blocking=True)
             slot.x["questionCntxWords"].copy_(batch["questionCntxWords"], non_blocking=True)
             slot.x["questionLengths"].copy_(batch["questionLengths"], non_blocking=True)
-            slot.x["knowledgeBase"].copy_(slot.kb_stage if self.host_kb_bf16 else batch["knowledgeBase"], non_blocking=True)
-            slot.h2d_done.record(slot.stream)
+            if self.host_kb_bf16:
+                kb, dev = batch["knowledgeBase"], slot.x["knowledgeBase"].view(-1)
+                for c in range(self.chunks):
+                    self.lib.mac_host_cast_bf16_end()                  # piece c is in its staging buffer
+                    cur = si
+                    if c + 1 < self.chunks:
+                        si = self._cast_begin(kb, c + 1)               # cast of the next piece runs under this piece's copy
+                    elif next_batch is not None:
+                        si = self._cast_begin(next_batch["knowledgeBase"], 0)
+                        self._cast_for = (self._next, next_batch["knowledgeBase"], si)
+                    dev[c * self.chunk_elems:(c + 1) * self.chunk_elems].copy_(self._stages[cur], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(slot.stream)
+                    self._stage_busy[cur] = ev
+            else:
+                slot.x["knowledgeBase"].copy_(batch["knowledgeBase"], non_blocking=True)
+                if next_batch is not None:
+                    self.prefetch(next_batch)
             if slot.graph is not None:
                 slot.graph.replay()
             else:

@@ -277,18 +277,23 @@ def test_step_invariant_read_hoist_is_the_same_function(monkeypatch, prec, varia
     print(prec, variant, {k: (max_rel(hoisted[k], ref[k]), max_rel(stepwise[k], ref[k])) for k in ("memory", "info")})
 
 
-@pytest.mark.parametrize("prec", ["bf16", "fp32"])
-def test_host_pipeline_matches_direct_cell(prec, monkeypatch):
-    """serving.HostPipeline (host fp32 in -> [host bf16 cast] -> H2D -> graph -> D2H) returns what the cell computes from
-    device-resident inputs; in-flight slots do not mix batches up."""
+@pytest.mark.parametrize("prec,force_cast", [("bf16", False), ("bf16", True), ("fp32", False)])
+def test_host_pipeline_matches_direct_cell(prec, force_cast, monkeypatch):
+    """serving.HostPipeline (host fp32 in -> [host bf16 cast in pieces through the staging ring] -> H2D -> graph -> D2H) returns
+    what the cell computes from device-resident inputs; in-flight slots and staging buffers do not mix batches up."""
     from mac_network_b200.mac_cell import MACParams
     from mac_network_b200.serving import HostPipeline
     monkeypatch.setenv("MAC_SMALL_TC", "1")      # the pipeline's cells use the throughput form (small_tc): same form for the direct cell
+    if force_cast:                               # the timing rule would switch the host cast off at this small shape
+        monkeypatch.setenv("MAC_NO_HOST_CAST", "0")
+        monkeypatch.setenv("MAC_HOST_CAST_CHUNKS", "4")      # the multi-piece form of the ring (default: one piece)
     B, S, N, d, L = 8, 6, 49, 128, 3
     cfg = MACConfig.args("args", netLength=L, memDim=d, ctrlDim=d, attDim=d)
     pv = perturb_biases(init_params(cfg, L, seed=82), seed=83)
     params = MACParams(cfg, L, values=pv)
     pipe = HostPipeline(cfg, params, (B, S, N, d, L), prec=prec, slots=2, cast_threads=3)
+    if force_cast:
+        assert pipe.host_kb_bf16 and pipe.chunks == 4 and len(pipe._stages) == 12
     batches = [make_inputs(B, S, N, d, seed=90 + i) for i in range(5)]
     host = [{k: torch.from_numpy(v).pin_memory() for k, v in b.items() if k != "questionWords"} for b in batches]
     got = []
