@@ -95,7 +95,9 @@ def test_fused_read_step_equals_unfused_chain(monkeypatch):
     from mac_network_b200 import _lib as L_
     lib = L_.load()
     d = 512
-    for (B, N) in ((64, 196), (3, 49), (5, 130), (2, 256), (7, 128), (4, 17)):
+    # N > 128: packed 128-row tiles across sample boundaries -- incl. an odd tile count (9 x 200 = 15 tiles: the last pair's
+    # second tile is past the end), samples spread over three tiles (N = 200, 255) and a single-sample launch
+    for (B, N) in ((64, 196), (3, 49), (5, 130), (2, 256), (7, 128), (4, 17), (9, 200), (1, 129), (3, 255), (11, 131)):
         g = torch.Generator(device="cuda").manual_seed(B * 1000 + N)
 
         def rn(*s, scale=1.0):
