@@ -149,7 +149,10 @@ int mac_read_fwd_inv(const float* kb, const void* kb_bf16, const void* inv, cons
  * knowledge base, y = memory @ Wy + by [B, d] (ops.py:689) and the control state [B, d], computes
  *   H = ELU((P*y) @ Wm[0:d] + Q);  logits = ELU((H @ Wm2 + bm2) * control) . wr + br;  att = softmax_n(logits);
  *   info = sum_n att * KB                                     (mac_cell.py:230-275 at readDropout == 1)
- * with P*y, H, I1, I2 and the logits kept on the SM (shared / tensor memory).  mac_read_fwd_inv dispatches to it when
+ * with P*y, H, I1, I2 and the logits kept on the SM (shared / tensor memory).  For N > 128 the kernel walks the [B*N, d]
+ * matrices in packed 128-row tiles across sample boundaries (ceil(B*N/128) CTAs), leaves per-tile softmax partials in the scratch
+ * that mac_read_invariant_bytes reserves behind [P | Q] in `inv`, and a second, B-CTA launch merges them into att / info (so
+ * `inv` is read AND written by this call: one call at a time per `inv`).  mac_read_fwd_inv dispatches to it when
  * mac_read_step_fused_supported(B, N, d) (d == 512, N <= 256) unless the environment sets MAC_READ_FUSED=0.
  * Returns MAC_ERR_UNSUPPORTED for other shapes. */
 int mac_read_step_fused(const void* inv, const void* kb_bf16, const float* y, const float* control,
