@@ -8,7 +8,6 @@ the concatenated batch.  Per step:
 The loss of this cell-level harness is a linear probe of the final state, sum(memory_L * t_m + control_L * t_c) / B_global,
 standing in for the out-of-scope output unit / classifier (it supplies dL/dmemory and dL/dcontrol exactly as they would).
 """
-import ctypes
 
 import numpy as np
 import torch

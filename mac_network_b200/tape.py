@@ -17,7 +17,6 @@ import ctypes
 
 import torch
 
-from . import _lib
 from ._lib import ACT, check, ptr, stream_ptr
 from .params import PREFIX
 
