@@ -69,8 +69,9 @@ class _Bwd(object):
         sc = scope + "linearLayer" + name + "/"
         return sc + "weights/weight", sc + "biases/bias"
 
-    def linear_bwd(self, xs, wname, bname, dy, dxs, accum):
-        """ops.linear backward: xs/dxs lists of 2-D views (dxs entries may be None)."""
+    def linear_bwd(self, xs, wname, bname, dy, dxs, accum, wgrad=True):
+        """ops.linear backward: xs/dxs lists of 2-D views (dxs entries may be None).  wgrad=False: data gradients only (the
+        weight / bias gradients of this call are formed later, batched over the steps)."""
         n = len(xs)
         W = self.p[wname]
         Wt = _t(self.p, W, wname) if any(d is not None for d in dxs) else None
@@ -82,8 +83,8 @@ class _Bwd(object):
         arr_ldd = (ctypes.c_int * n)(*[(d.stride(0) if d is not None else 0) for d in dxs])
         arr_acc = (ctypes.c_int * n)(*[int(a) for a in accum])
         check(self.lib.mac_linear_bwd(arr_x, arr_k, arr_ld, n, ptr(Wt), ptr(dy), dy.stride(0), arr_dx, arr_ldd, arr_acc,
-                                      ptr(self.G(wname)), ptr(self.G(bname)) if bname else None, M, n_out,
-                                      ptr(self.lws), self.lws_bytes, stream_ptr()), "mac_linear_bwd")
+                                      ptr(self.G(wname)) if wgrad else None, ptr(self.G(bname)) if (bname and wgrad) else None,
+                                      M, n_out, ptr(self.lws), self.lws_bytes, stream_ptr()), "mac_linear_bwd")
 
     def axpy(self, dst, src, alpha=1.0):
         check(self.lib.mac_axpy(ptr(dst), ptr(src), float(alpha), src.numel(), stream_ptr()), "mac_axpy")
@@ -141,7 +142,10 @@ class _Bwd(object):
             nW, nb = self.lin_names(wsc, "newMemory")
             xs = [hm[i], hi[i + 1]] + ([cell._ss[i]] if c.writeSelfAtt else [])
             dxs = [gM[i], dinfo] + ([dss] if c.writeSelfAtt else [])
-            self.linear_bwd(xs, nW, nb, dmp, dxs, [1, 0] + ([0] if c.writeSelfAtt else []))
+            # without a gate the gradient of the write unit's output IS the history slot gM[i+1], which nothing modifies
+            # afterwards: its weight / bias gradient over all L steps is ONE [L*B]-row product after the loop
+            defer_w = not c.writeGate
+            self.linear_bwd(xs, nW, nb, dmp, dxs, [1, 0] + ([0] if c.writeSelfAtt else []), wgrad=not defer_w)
             if c.writeSelfAtt:
                 lsc = wsc + "inter2attselfAttention/inter2logits/linearLayerlogits/"
                 check(lib.mac_control_attend_bwd(ptr(cell._sc[i]), 0, d, ptr(hc), d, B * d, ptr(hm), d, B * d,
@@ -186,6 +190,11 @@ class _Bwd(object):
             if self.recurrent:
                 self._control_step_bwd(i, gC, dwords, du_rec, part, spart, S)
 
+        if not c.writeGate:             # deferred weight / bias gradient of write/newMemory (see the loop): K = L*B rows at once
+            nW, nb = self.lin_names(wsc, "newMemory")
+            LB = L * B
+            xs = [hm[:L].reshape(LB, d), hi[1:L + 1].reshape(LB, d)] + ([cell._ss.reshape(LB, d)] if c.writeSelfAtt else [])
+            self.linear_bwd(xs, nW, nb, gM[1:L + 1].reshape(LB, d), [None] * len(xs), [0] * len(xs))
         lsc = "MACCell/control/inter2logits/linearLayerlogits/"
         if self.recurrent:
             return self._finish(gC, gM, dkb, dwords, dq, du_rec, part, spart, rsc, wsc, lsc, nbx, nbm, nbm2)
